@@ -1,0 +1,92 @@
+"""ctypes binding of the C-ABI in ``include/arbinterp_b200.h``.
+
+There is no CPU fallback: if the shared library is missing the import of anything that needs it
+raises, loudly, with the build command.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libarbinterp_b200.so")
+
+MODE_VECTOR, MODE_NORM, MODE_BOTH = 0, 1, 2
+
+# every symbol include/arbinterp_b200.h declares (tests check the .so exports each one)
+EXPORTED_SYMBOLS = (
+    "arb_version", "arb_last_error", "arb_get_matrix",
+    "arb_build_coeffs", "arb_build_coeffs_3d", "arb_build_coeffs_4d",
+    "arb_query", "arb_query_host", "arb_set_query_variant",
+)
+
+
+class ArbGeom(ctypes.Structure):
+    """``struct arb_geom`` (include/arbinterp_b200.h)."""
+    _fields_ = [
+        ("d", ctypes.c_int32),
+        ("ncomp", ctypes.c_int32),
+        ("ncell", ctypes.c_int64 * 4),
+        ("slab_lo", ctypes.c_int64),
+        ("slab_hi", ctypes.c_int64),
+        ("int_min", ctypes.c_double * 4),
+        ("int_max", ctypes.c_double * 4),
+        ("h", ctypes.c_double * 4),
+    ]
+
+
+class ArbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load (once) and return the ctypes handle; raise if the CUDA library was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ArbError(
+            f"{LIB_PATH} not found: the sm_100a CUDA library has not been built. "
+            "Run `python -c 'import __graft_entry__ as g; g.build()'` or `make -C arbinterp_b200/csrc`. "
+            "arbinterp_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i64, i32, dbl_p = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p
+    lib.arb_version.restype = ctypes.c_char_p
+    lib.arb_version.argtypes = []
+    lib.arb_last_error.restype = ctypes.c_char_p
+    lib.arb_last_error.argtypes = []
+    lib.arb_get_matrix.restype = i32
+    lib.arb_get_matrix.argtypes = [i32, i32, i32, dbl_p]
+    lib.arb_build_coeffs.restype = i32
+    lib.arb_build_coeffs.argtypes = [i32, vp, i32, ctypes.POINTER(i64 * 4), vp, i32, vp]
+    lib.arb_build_coeffs_3d.restype = i32
+    lib.arb_build_coeffs_3d.argtypes = [vp, i32, i64, i64, i64, vp, vp]
+    lib.arb_build_coeffs_4d.restype = i32
+    lib.arb_build_coeffs_4d.argtypes = [vp, i32, i64, i64, i64, i64, vp, vp]
+    lib.arb_query.restype = i32
+    lib.arb_query.argtypes = [ctypes.POINTER(ArbGeom), vp, i32, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp]
+    lib.arb_query_host.restype = i32
+    lib.arb_query_host.argtypes = [ctypes.POINTER(ArbGeom), vp, i32, vp, i64, i64, vp, vp, vp, vp, i64]
+    lib.arb_set_query_variant.restype = i32
+    lib.arb_set_query_variant.argtypes = [i32]
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().arb_last_error().decode("utf-8", "replace")
+        raise ArbError(f"{what} failed (code {rc}): {msg}")
+
+
+def get_matrix(d: int, which: str, reference_quirk: bool = True):
+    """inv(B) / D / A of makeAMatrix (A.py:107-175, 726-878) as a numpy array."""
+    import numpy as np
+    nm = 4 ** d
+    out = np.empty((nm, nm), dtype=np.float64)
+    code = {"invB": 0, "D": 1, "A": 2}[which]
+    check(load().arb_get_matrix(d, code, int(reference_quirk), out.ctypes.data), "arb_get_matrix")
+    return out

@@ -1,0 +1,196 @@
+// Host-buffer query path: the call a numpy user makes (tricubic.Query(points) with points in
+// host memory).  Chunks the batch and overlaps H2D copy / query kernel / D2H copy on a ring of
+// streams.  Pinned (page-locked) caller buffers are copied directly; pageable ones are staged
+// through pinned ring buffers.  The in-place NaN masking of out-of-volume rows (A.py:350-355)
+// is mirrored on the host from a compact list of masked row numbers, so q is never copied back.
+#include <mutex>
+#include <vector>
+#include "arb_common.cuh"
+
+namespace arb {
+
+int query_device(const arb_geom* g, const double* table, int mode, double* q, int64_t N, int64_t ldq,
+                 double* out_comps, double* out_norm, double* out_grad, int64_t* out_cell, int64_t* masked_rows,
+                 unsigned long long* masked_count, cudaStream_t st, int variant);
+int current_query_variant();
+
+namespace {
+
+constexpr int NSLOT = 3;
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    // device
+    double *d_q = nullptr, *d_comps = nullptr, *d_norm = nullptr, *d_grad = nullptr;
+    int64_t *d_cell = nullptr, *d_rows = nullptr;
+    unsigned long long* d_count = nullptr;
+    // pinned host staging
+    double *h_q = nullptr, *h_comps = nullptr, *h_norm = nullptr, *h_grad = nullptr;
+    int64_t *h_cell = nullptr, *h_rows = nullptr;
+    unsigned long long* h_count = nullptr;
+    // in-flight chunk
+    bool busy = false;
+    int64_t off = 0, rows = 0;
+};
+
+struct HostCtx {
+    Slot slot[NSLOT];
+    int64_t cap_rows = 0, cap_ldq = 0;
+    int device = -1;
+    std::mutex mutex;
+};
+
+HostCtx g_ctx[16];
+
+void free_slot(Slot& s) {
+    cudaFree(s.d_q); cudaFree(s.d_comps); cudaFree(s.d_norm); cudaFree(s.d_grad); cudaFree(s.d_cell);
+    cudaFree(s.d_rows); cudaFree(s.d_count);
+    cudaFreeHost(s.h_q); cudaFreeHost(s.h_comps); cudaFreeHost(s.h_norm); cudaFreeHost(s.h_grad);
+    cudaFreeHost(s.h_cell); cudaFreeHost(s.h_rows); cudaFreeHost(s.h_count);
+    s.d_q = s.d_comps = s.d_norm = s.d_grad = nullptr;
+    s.d_cell = s.d_rows = nullptr; s.d_count = nullptr;
+    s.h_q = s.h_comps = s.h_norm = s.h_grad = nullptr;
+    s.h_cell = s.h_rows = nullptr; s.h_count = nullptr;
+}
+
+int ensure_capacity(HostCtx& c, int64_t rows, int64_t ldq) {
+    if (rows <= c.cap_rows && ldq <= c.cap_ldq) return 0;
+    if (rows < c.cap_rows) rows = c.cap_rows;
+    if (ldq < c.cap_ldq) ldq = c.cap_ldq;
+    for (int i = 0; i < NSLOT; ++i) {
+        Slot& s = c.slot[i];
+        if (!s.stream) {
+            ARB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+            ARB_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        }
+        free_slot(s);
+        ARB_CUDA(cudaMalloc(&s.d_q, sizeof(double) * rows * ldq));
+        ARB_CUDA(cudaMalloc(&s.d_comps, sizeof(double) * rows * 3));
+        ARB_CUDA(cudaMalloc(&s.d_norm, sizeof(double) * rows));
+        ARB_CUDA(cudaMalloc(&s.d_grad, sizeof(double) * rows * 4));
+        ARB_CUDA(cudaMalloc(&s.d_cell, sizeof(int64_t) * rows));
+        ARB_CUDA(cudaMalloc(&s.d_rows, sizeof(int64_t) * rows));
+        ARB_CUDA(cudaMalloc(&s.d_count, sizeof(unsigned long long)));
+        ARB_CUDA(cudaMallocHost(&s.h_q, sizeof(double) * rows * ldq));
+        ARB_CUDA(cudaMallocHost(&s.h_comps, sizeof(double) * rows * 3));
+        ARB_CUDA(cudaMallocHost(&s.h_norm, sizeof(double) * rows));
+        ARB_CUDA(cudaMallocHost(&s.h_grad, sizeof(double) * rows * 4));
+        ARB_CUDA(cudaMallocHost(&s.h_cell, sizeof(int64_t) * rows));
+        ARB_CUDA(cudaMallocHost(&s.h_rows, sizeof(int64_t) * rows));
+        ARB_CUDA(cudaMallocHost(&s.h_count, sizeof(unsigned long long)));
+    }
+    c.cap_rows = rows; c.cap_ldq = ldq;
+    return 0;
+}
+
+bool is_device(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice;
+}
+
+bool is_pinned(const void* p) {
+    if (!p) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+struct Call {
+    const arb_geom* g; int mode; int d;
+    double* q; int64_t ldq;
+    double *comps, *norm, *grad; int64_t* cell;
+    bool q_pinned, comps_pinned, norm_pinned, grad_pinned, cell_pinned;
+    bool cell_on_device;   // out_cell is device memory: the kernel writes it in place, no D2H
+};
+
+// wait for the slot's chunk and finish its host-side part
+int retire(Slot& s, const Call& c) {
+    if (!s.busy) return 0;
+    ARB_CUDA(cudaEventSynchronize(s.done));
+    const int64_t n = s.rows, off = s.off;
+    if (c.comps && !c.comps_pinned) memcpy(c.comps + off * 3, s.h_comps, sizeof(double) * n * 3);
+    if (c.norm && !c.norm_pinned) memcpy(c.norm + off, s.h_norm, sizeof(double) * n);
+    if (c.grad && !c.grad_pinned) memcpy(c.grad + off * c.d, s.h_grad, sizeof(double) * n * c.d);
+    if (c.cell && !c.cell_on_device && !c.cell_pinned) memcpy(c.cell + off, s.h_cell, sizeof(int64_t) * n);
+    const unsigned long long cnt = *s.h_count;
+    if (cnt) {
+        ARB_CUDA(cudaMemcpyAsync(s.h_rows, s.d_rows, sizeof(int64_t) * cnt, cudaMemcpyDeviceToHost, s.stream));
+        ARB_CUDA(cudaStreamSynchronize(s.stream));
+        const double nan = __builtin_nan("");
+        for (unsigned long long i = 0; i < cnt; ++i) {
+            double* row = c.q + (off + s.h_rows[i]) * c.ldq;
+            for (int64_t k = 0; k < c.ldq; ++k) row[k] = nan;
+        }
+    }
+    s.busy = false;
+    return 0;
+}
+
+}  // namespace
+}  // namespace arb
+
+extern "C" int arb_query_host(const arb_geom* g, const double* table, int mode, double* q_host, int64_t N, int64_t ldq,
+                              double* out_comps_host, double* out_norm_host, double* out_grad_host,
+                              int64_t* out_cell_host, int64_t chunk_rows) {
+    using namespace arb;
+    if (!g || !q_host || N < 0) { set_error("arb_query_host: bad arguments"); return 1; }
+    if (N == 0) return 0;
+    if (chunk_rows <= 0) chunk_rows = 1 << 20;
+    if (chunk_rows > N) chunk_rows = N;
+    int dev = 0;
+    ARB_CUDA(cudaGetDevice(&dev));
+    HostCtx& ctx = g_ctx[dev & 15];
+    std::lock_guard<std::mutex> lock(ctx.mutex);
+    int rc = ensure_capacity(ctx, chunk_rows, ldq);
+    if (rc) return rc;
+
+    Call c;
+    c.g = g; c.mode = mode; c.d = g->d; c.q = q_host; c.ldq = ldq;
+    c.comps = (mode != ARB_MODE_NORM) ? out_comps_host : nullptr;
+    c.norm = (mode != ARB_MODE_VECTOR) ? out_norm_host : nullptr;
+    c.grad = (mode != ARB_MODE_VECTOR) ? out_grad_host : nullptr;
+    c.cell = out_cell_host;
+    c.q_pinned = is_pinned(q_host);
+    c.comps_pinned = is_pinned(c.comps); c.norm_pinned = is_pinned(c.norm);
+    c.grad_pinned = is_pinned(c.grad); c.cell_pinned = is_pinned(c.cell);
+    c.cell_on_device = is_device(c.cell);
+
+    int64_t chunk = 0;
+    for (int64_t off = 0; off < N; off += chunk_rows, ++chunk) {
+        Slot& s = ctx.slot[chunk % NSLOT];
+        rc = retire(s, c);
+        if (rc) return rc;
+        const int64_t n = (N - off < chunk_rows) ? (N - off) : chunk_rows;
+        const double* src = q_host + off * ldq;
+        if (!c.q_pinned) { memcpy(s.h_q, src, sizeof(double) * n * ldq); src = s.h_q; }
+        ARB_CUDA(cudaMemcpyAsync(s.d_q, src, sizeof(double) * n * ldq, cudaMemcpyHostToDevice, s.stream));
+        ARB_CUDA(cudaMemsetAsync(s.d_count, 0, sizeof(unsigned long long), s.stream));
+        rc = query_device(g, table, mode, s.d_q, n, ldq, s.d_comps, s.d_norm, s.d_grad,
+                          c.cell ? (c.cell_on_device ? c.cell + off : s.d_cell) : nullptr,
+                          s.d_rows, s.d_count, s.stream, current_query_variant());
+        if (rc) return rc;
+        if (c.comps)
+            ARB_CUDA(cudaMemcpyAsync(c.comps_pinned ? c.comps + off * 3 : s.h_comps, s.d_comps, sizeof(double) * n * 3,
+                                     cudaMemcpyDeviceToHost, s.stream));
+        if (c.norm)
+            ARB_CUDA(cudaMemcpyAsync(c.norm_pinned ? c.norm + off : s.h_norm, s.d_norm, sizeof(double) * n,
+                                     cudaMemcpyDeviceToHost, s.stream));
+        if (c.grad)
+            ARB_CUDA(cudaMemcpyAsync(c.grad_pinned ? c.grad + off * c.d : s.h_grad, s.d_grad, sizeof(double) * n * c.d,
+                                     cudaMemcpyDeviceToHost, s.stream));
+        if (c.cell && !c.cell_on_device)
+            ARB_CUDA(cudaMemcpyAsync(c.cell_pinned ? c.cell + off : s.h_cell, s.d_cell, sizeof(int64_t) * n,
+                                     cudaMemcpyDeviceToHost, s.stream));
+        ARB_CUDA(cudaMemcpyAsync(s.h_count, s.d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+        ARB_CUDA(cudaEventRecord(s.done, s.stream));
+        s.busy = true; s.off = off; s.rows = n;
+    }
+    for (int i = 0; i < NSLOT; ++i) {
+        rc = retire(ctx.slot[i], c);
+        if (rc) return rc;
+    }
+    return 0;
+}

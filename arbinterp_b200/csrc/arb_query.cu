@@ -1,0 +1,529 @@
+// Query kernels: locate cell -> gather the cell's coefficient block(s) -> Horner evaluation of
+// the value and the analytic partial derivatives.  Replaces rQuery1/2/3 of the reference
+// (A.py:344-521 tricubic, A.py:1064-1258 quadcubic).
+//
+// The path is HBM-bound (one 512 B / 2 KB coefficient block per interpolated component per
+// query, no reuse for random queries), so the kernels are organised around keeping many
+// full-line reads in flight per SM; the FP64 arithmetic (about 70-150 DFMA per query) is
+// 10-20 % of the issue budget at roofline.
+//
+// Variants (arb_set_query_variant):
+//   0  COOP : G = 8 (3-D) / 32 (4-D) lanes share one query; lane l issues four 16-byte loads
+//             that are contiguous across the group (one full 128 B line per group and
+//             instruction), evaluates its 8 coefficients and the partial sums are combined
+//             with a reduce-scatter over shuffles.  No shared memory, any block size.
+//   1  BULK : one query per thread; each thread asks the TMA engine (cp.async.bulk, SASS
+//             UBLKCP) to copy its cell's block into a private shared-memory slot, all copies
+//             of a warp complete on one mbarrier, then the thread streams its slot through a
+//             nested Horner scheme (LDS.128, conflict-free by a 16-byte slot skew).
+//   2  DIRECT: one query per thread reading its block straight from global memory
+//             (32 uncoalesced LDG.128 per component); kept as the naive baseline.
+#include "arb_common.cuh"
+
+namespace arb {
+
+struct QueryParams {
+    const double* table;
+    double* q;
+    int64_t N, ldq;
+    double* out_comps;
+    double* out_norm;
+    double* out_grad;
+    int64_t* out_cell;
+    int64_t* masked_rows;
+    unsigned long long* masked_count;
+    double mn[4], mx[4], h[4];
+    int64_t nc[4];
+    int64_t slab_lo, slab_hi;   // owned layers of the slowest axis
+    int64_t total_cells;        // prod(nc): sentinel index (A.py:369)
+    int64_t layer_cells;        // prod(nc[0..d-2])
+};
+
+static int g_query_variant = 0;
+int current_query_variant() { return g_query_variant; }
+
+// --------------------------------------------------------------------------------------
+// locate: bounds mask, cell index, cell-fraction coordinates (A.py:350-373, 1069-1092).
+// The arithmetic is the reference's, operation for operation: IEEE subtract, IEEE divide,
+// floor, subtract.  (No fast-math, no reciprocal.)
+// --------------------------------------------------------------------------------------
+template <int D>
+struct Located {
+    double frac[D];
+    int64_t cell_global;  // total_cells when the row yields NaN
+    int64_t cell_local;   // row of `table`
+    bool ok;              // evaluate; otherwise every output is NaN
+    bool masked;          // row must be NaN-overwritten in place
+};
+
+template <int D>
+__device__ __forceinline__ Located<D> locate(const QueryParams& p, int64_t n) {
+    Located<D> L;
+    const double* row = p.q + n * p.ldq;
+    double c[D];
+#pragma unroll
+    for (int a = 0; a < D; ++a) c[a] = row[a];
+    bool masked = false;
+#pragma unroll
+    for (int a = 0; a < D; ++a) masked |= (c[a] < p.mn[a]) | (c[a] > p.mx[a]);
+    bool ok = !masked;
+    int64_t lin = 0, mult = 1, islow = 0;
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+        const double iu = __ddiv_rn(__dsub_rn(c[a], p.mn[a]), p.h[a]);
+        const double fl = floor(iu);
+        L.frac[a] = __dsub_rn(iu, fl);
+        ok &= (iu == iu);                      // NaN coordinate: not masked in place, output NaN
+        const int64_t ii = ok ? (int64_t)fl : 0;
+        ok &= (ii < p.nc[a]);                  // exact upper edge rounding to n-3: NaN
+        lin += ii * mult;
+        mult *= p.nc[a];
+        if (a == D - 1) islow = ii;
+    }
+    L.masked = masked;
+    L.cell_global = ok ? lin : p.total_cells;
+    ok &= (islow >= p.slab_lo) & (islow < p.slab_hi);   // slab-sharded table: not ours -> NaN
+    L.ok = ok;
+    L.cell_local = ok ? lin - p.slab_lo * p.layer_cells : 0;
+    return L;
+}
+
+__device__ __forceinline__ void mask_row_in_place(const QueryParams& p, int64_t n) {
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    double* row = p.q + n * p.ldq;
+    for (int64_t c = 0; c < p.ldq; ++c) row[c] = nan;
+    if (p.masked_rows) {
+        unsigned long long slot = atomicAdd(p.masked_count, 1ULL);
+        p.masked_rows[slot] = n;
+    }
+}
+
+__device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+// x^j and d/dx x^j for j = 0..3 selected at run time (lane-dependent j)
+__device__ __forceinline__ double pow_sel(double x, int j) {
+    const double x2 = x * x;
+    return j == 0 ? 1.0 : (j == 1 ? x : (j == 2 ? x2 : x2 * x));
+}
+__device__ __forceinline__ double dpow_sel(double x, int j) {
+    return j == 0 ? 0.0 : (j == 1 ? 1.0 : (j == 2 ? 2.0 * x : 3.0 * (x * x)));
+}
+
+template <int MODE, int D> struct OutCount { static constexpr int NV = MODE == 0 ? 3 : (MODE == 1 ? 1 + D : 4 + D); };
+constexpr int next_pow2(int v) { return v <= 1 ? 1 : (v <= 2 ? 2 : (v <= 4 ? 4 : (v <= 8 ? 8 : 16))); }
+
+// store output number idx of query n (value or NaN)
+template <int D, int MODE>
+__device__ __forceinline__ void store_output(const QueryParams& p, int64_t n, int idx, double v) {
+    if (MODE == 0) {
+        if (idx < 3) p.out_comps[n * 3 + idx] = v;
+    } else if (MODE == 1) {
+        if (idx == 0) p.out_norm[n] = v;
+        else if (idx <= D) p.out_grad[n * D + (idx - 1)] = __ddiv_rn(v, p.h[idx - 1]);
+    } else {
+        if (idx < 3) p.out_comps[n * 3 + idx] = v;
+        else if (idx == 3) p.out_norm[n] = v;
+        else if (idx < 4 + D) p.out_grad[n * D + (idx - 4)] = __ddiv_rn(v, p.h[idx - 4]);
+    }
+}
+
+// ======================================================================================
+// Variant 0: cooperative sub-warp gather
+// ======================================================================================
+template <int D, int C, int MODE, int U>
+__global__ void __launch_bounds__(256) query_coop_kernel(const QueryParams p) {
+    constexpr int G = (D == 3) ? 8 : 32;       // lanes per query
+    constexpr int NM = (D == 3) ? 64 : 256;    // coefficients per component
+    constexpr int RS = NM / 4;                 // doubles between slow-index blocks
+    constexpr int QPW = 32 / G;                // queries per warp and pass
+    constexpr int NV = OutCount<MODE, D>::NV;
+    constexpr int NVP = next_pow2(NV);
+    static_assert(NVP <= G, "reduce-scatter needs at least NVP lanes");
+
+    const int lane = threadIdx.x & 31;
+    const int l = lane & (G - 1);
+    const int grp = lane / G;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+
+    const int ju = l & 1;                 // lane holds i = 2*ju + {0,1}
+    const int jv = (l >> 1) & 3;          // fixed j
+    const int jw = (l >> 3) & 3;          // fixed k (4-D only)
+
+    for (int64_t base = warp_global * (QPW * U); base < p.N; base += nwarps * (QPW * U)) {
+        Located<D> L[U];
+        int64_t n[U];
+        double2 a[U][C][4];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            n[u] = base + u * QPW + grp;
+            if (n[u] < p.N) {
+                L[u] = locate<D>(p, n[u]);
+            } else {
+                L[u].ok = false; L[u].masked = false; L[u].cell_global = 0; L[u].cell_local = 0;
+#pragma unroll
+                for (int d_ = 0; d_ < D; ++d_) L[u].frac[d_] = 0.0;
+            }
+        }
+        // issue every load of the pass before the first use
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const double* src = p.table + (L[u].cell_local * C) * NM + 2 * l;
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    if (L[u].ok) a[u][c][r] = ldg_stream_d2(src + c * NM + r * RS);
+                    else a[u][c][r] = make_double2(0.0, 0.0);
+                }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const double fu = L[u].frac[0], fv = L[u].frac[1], fw = L[u].frac[2];
+            const double s = L[u].frac[D - 1];   // slow variable: Horner over the four loads
+            const double u2 = fu * fu;
+            const double pu0 = ju ? u2 : 1.0, pu1 = ju ? u2 * fu : fu;
+            const double dpu0 = ju ? 2.0 * fu : 0.0, dpu1 = ju ? 3.0 * u2 : 1.0;
+            const double pv = pow_sel(fv, jv), dpv = dpow_sel(fv, jv);
+            double Pm = pv, Pm_dy = dpv, Pm_dz = 0.0;
+            if (D == 4) {
+                const double pw = pow_sel(fw, jw), dpw = dpow_sel(fw, jw);
+                Pm = pv * pw; Pm_dy = dpv * pw; Pm_dz = pv * dpw;
+            }
+            double v[NVP];
+#pragma unroll
+            for (int i = 0; i < NVP; ++i) v[i] = 0.0;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                double t[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) t[r] = fma(a[u][c][r].y, pu1, a[u][c][r].x * pu0);
+                const double T = fma(fma(fma(t[3], s, t[2]), s, t[1]), s, t[0]);
+                const bool grad_comp = (MODE == 1) || (MODE == 2 && c == 3);
+                if (!grad_comp) {
+                    v[c] = T * Pm;
+                } else {
+                    constexpr int o = (MODE == 1) ? 0 : 3;
+                    double tx[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) tx[r] = fma(a[u][c][r].y, dpu1, a[u][c][r].x * dpu0);
+                    const double Tx = fma(fma(fma(tx[3], s, tx[2]), s, tx[1]), s, tx[0]);
+                    const double Ts = fma(fma(3.0 * t[3], s, 2.0 * t[2]), s, t[1]);
+                    v[o] = T * Pm;
+                    v[o + 1] = Tx * Pm;
+                    v[o + 2] = T * Pm_dy;
+                    if (D == 4) v[o + 3] = T * Pm_dz;
+                    v[o + D] = Ts * Pm;
+                }
+            }
+            // reduce-scatter over the group: after step b a lane keeps half of its list
+            int idx = 0;
+#pragma unroll
+            for (int b = 0, cnt = NVP; cnt > 1; ++b, cnt >>= 1) {
+                const int half = cnt >> 1;
+                const bool up = (l >> b) & 1;
+#pragma unroll
+                for (int i = 0; i < half; ++i) {
+                    const double keep = up ? v[half + i] : v[i];
+                    const double send = up ? v[i] : v[half + i];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1 << b);
+                }
+                idx += up ? half : 0;
+            }
+            constexpr int LOGNVP = NVP == 1 ? 0 : (NVP == 2 ? 1 : (NVP == 4 ? 2 : (NVP == 8 ? 3 : 4)));
+#pragma unroll
+            for (int m = NVP; m < G; m <<= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], m);
+            (void)LOGNVP;
+            if (n[u] < p.N) {
+                if (l < NVP && idx < NV) store_output<D, MODE>(p, n[u], idx, L[u].ok ? v[0] : qnan());
+                if (l == G - 1) {
+                    if (p.out_cell) p.out_cell[n[u]] = L[u].cell_global;
+                    if (L[u].masked) mask_row_in_place(p, n[u]);
+                }
+            }
+        }
+    }
+}
+
+// ======================================================================================
+// one-thread-per-query evaluation from a contiguous coefficient block (shared or global)
+// ======================================================================================
+template <bool SHARED>
+__device__ __forceinline__ double2 ld_pair(const double* p) {
+    if (SHARED) return *reinterpret_cast<const double2*>(p);
+    return ldg_stream_d2(p);
+}
+
+// value only: nested Horner, highest power first
+template <int D, bool SHARED>
+__device__ __forceinline__ double eval_value(const double* blk, const double* f) {
+    const double u = f[0], v = f[1], w = f[2];
+    double out = 0.0;
+    constexpr int NT = (D == 4) ? 4 : 1;
+#pragma unroll
+    for (int lt = NT - 1; lt >= 0; --lt) {
+        double val = 0.0;
+#pragma unroll
+        for (int k = 3; k >= 0; --k) {
+            double P = 0.0;
+#pragma unroll
+            for (int j = 3; j >= 0; --j) {
+                const double* r = blk + ((lt * 4 + k) * 4 + j) * 4;
+                const double2 lo = ld_pair<SHARED>(r), hi = ld_pair<SHARED>(r + 2);
+                const double pp = fma(fma(fma(hi.y, u, hi.x), u, lo.y), u, lo.x);
+                P = fma(P, v, pp);
+            }
+            val = fma(val, w, P);
+        }
+        out = (D == 4) ? fma(out, f[D - 1], val) : val;
+    }
+    return out;
+}
+
+// value + all partial derivatives (unit-cell coordinates): g[0]=value, g[1..D]=d/du, d/dv, ...
+template <int D, bool SHARED>
+__device__ __forceinline__ void eval_value_grad(const double* blk, const double* f, double* g) {
+    const double u = f[0], v = f[1], w = f[2];
+    const double u3 = 3.0 * u;
+    double oV = 0.0, oX = 0.0, oY = 0.0, oZ = 0.0, oT = 0.0;
+    constexpr int NT = (D == 4) ? 4 : 1;
+#pragma unroll
+    for (int lt = NT - 1; lt >= 0; --lt) {
+        double val = 0.0, gx = 0.0, gy = 0.0, gz = 0.0;
+#pragma unroll
+        for (int k = 3; k >= 0; --k) {
+            double P = 0.0, Px = 0.0, Py = 0.0;
+#pragma unroll
+            for (int j = 3; j >= 0; --j) {
+                const double* r = blk + ((lt * 4 + k) * 4 + j) * 4;
+                const double2 lo = ld_pair<SHARED>(r), hi = ld_pair<SHARED>(r + 2);
+                const double pp = fma(fma(fma(hi.y, u, hi.x), u, lo.y), u, lo.x);
+                const double dp = fma(fma(hi.y, u3, hi.x + hi.x), u, lo.y);
+                Py = fma(Py, v, P);
+                P = fma(P, v, pp);
+                Px = fma(Px, v, dp);
+            }
+            gz = fma(gz, w, val);
+            val = fma(val, w, P);
+            gx = fma(gx, w, Px);
+            gy = fma(gy, w, Py);
+        }
+        if (D == 4) {
+            const double s = f[D - 1];
+            oT = fma(oT, s, oV);
+            oV = fma(oV, s, val);
+            oX = fma(oX, s, gx);
+            oY = fma(oY, s, gy);
+            oZ = fma(oZ, s, gz);
+        } else {
+            oV = val; oX = gx; oY = gy; oZ = gz;
+        }
+    }
+    g[0] = oV; g[1] = oX; g[2] = oY; g[3] = oZ;
+    if (D == 4) g[4] = oT;
+}
+
+template <int D, int C, int MODE, bool SHARED>
+__device__ __forceinline__ void eval_and_store(const QueryParams& p, int64_t n, const Located<D>& L,
+                                               const double* blk) {
+    constexpr int NM = (D == 3) ? 64 : 256;
+    if (!L.ok) {
+#pragma unroll
+        for (int i = 0; i < OutCount<MODE, D>::NV; ++i) store_output<D, MODE>(p, n, i, qnan());
+        return;
+    }
+    if (MODE == 0 || MODE == 2) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) store_output<D, MODE>(p, n, c, eval_value<D, SHARED>(blk + c * NM, L.frac));
+    }
+    if (MODE == 1 || MODE == 2) {
+        constexpr int o = (MODE == 1) ? 0 : 3;
+        double g[5];
+        eval_value_grad<D, SHARED>(blk + (C - 1) * NM, L.frac, g);
+#pragma unroll
+        for (int i = 0; i <= D; ++i) store_output<D, MODE>(p, n, o + i, g[i]);
+    }
+}
+
+// ======================================================================================
+// Variant 1: TMA bulk gather into per-thread shared-memory slots
+// ======================================================================================
+template <int D, int C, int MODE, int THREADS>
+__global__ void __launch_bounds__(THREADS) query_bulk_kernel(const QueryParams p) {
+    constexpr int NM = (D == 3) ? 64 : 256;
+    constexpr uint32_t BYTES = C * NM * 8;
+    constexpr uint32_t SLOT = BYTES + 16;     // 16 B skew: LDS.128 of a quarter warp hits 8 distinct 16 B bank groups
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bars[THREADS / 32];
+
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned char* slot = smem + (size_t)threadIdx.x * SLOT;
+    uint64_t* bar = &bars[wid];
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    const int64_t warp_global = ((int64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * THREADS) >> 5;
+    uint32_t phase = 0;
+    for (int64_t base = warp_global * 32; base < p.N; base += nwarps * 32) {
+        const int64_t n = base + lane;
+        Located<D> L;
+        L.ok = false; L.masked = false; L.cell_global = 0; L.cell_local = 0;
+        if (n < p.N) L = locate<D>(p, n);
+        const unsigned okmask = __ballot_sync(0xffffffffu, L.ok);
+        if (lane == 0) mbar_expect_tx(bar, (uint32_t)__popc(okmask) * BYTES);
+        __syncwarp();
+        if (L.ok) bulk_g2s(slot, p.table + L.cell_local * (int64_t)(C * NM), BYTES, bar);
+        if (n < p.N) {
+            if (p.out_cell) p.out_cell[n] = L.cell_global;
+            if (L.masked) mask_row_in_place(p, n);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        if (n < p.N) eval_and_store<D, C, MODE, true>(p, n, L, reinterpret_cast<const double*>(slot));
+        __syncwarp();
+    }
+}
+
+// ======================================================================================
+// Variant 2: naive one-thread-per-query from global memory
+// ======================================================================================
+template <int D, int C, int MODE>
+__global__ void __launch_bounds__(128) query_direct_kernel(const QueryParams p) {
+    constexpr int NM = (D == 3) ? 64 : 256;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < p.N; n += stride) {
+        const Located<D> L = locate<D>(p, n);
+        if (p.out_cell) p.out_cell[n] = L.cell_global;
+        if (L.masked) mask_row_in_place(p, n);
+        eval_and_store<D, C, MODE, false>(p, n, L, p.table + L.cell_local * (int64_t)(C * NM));
+    }
+}
+
+// --------------------------------------------------------------------------------------
+// launchers
+// --------------------------------------------------------------------------------------
+template <typename K>
+static int persistent_grid(K kernel, int threads, size_t smem, int64_t work_blocks) {
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem) != cudaSuccess || occ < 1) occ = 1;
+    int64_t g = (int64_t)num_sms() * occ;
+    if (work_blocks < g) g = work_blocks;
+    return (int)(g < 1 ? 1 : g);
+}
+
+template <int D, int C, int MODE, int U>
+static int launch_coop(const QueryParams& p, cudaStream_t st) {
+    constexpr int G = (D == 3) ? 8 : 32;
+    constexpr int THREADS = 256;
+    const int64_t per_block = (int64_t)(THREADS / G) * U;
+    auto k = query_coop_kernel<D, C, MODE, U>;
+    const int grid = persistent_grid(k, THREADS, 0, (p.N + per_block - 1) / per_block);
+    k<<<grid, THREADS, 0, st>>>(p);
+    return check_cuda(cudaGetLastError(), "query_coop_kernel launch");
+}
+
+template <int D, int C, int MODE, int THREADS>
+static int launch_bulk(const QueryParams& p, cudaStream_t st) {
+    constexpr int NM = (D == 3) ? 64 : 256;
+    const size_t smem = (size_t)THREADS * (C * NM * 8 + 16);
+    auto k = query_bulk_kernel<D, C, MODE, THREADS>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        ARB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    const int grid = persistent_grid(k, THREADS, smem, (p.N + THREADS - 1) / THREADS);
+    k<<<grid, THREADS, smem, st>>>(p);
+    return check_cuda(cudaGetLastError(), "query_bulk_kernel launch");
+}
+
+template <int D, int C, int MODE>
+static int launch_direct(const QueryParams& p, cudaStream_t st) {
+    auto k = query_direct_kernel<D, C, MODE>;
+    const int grid = persistent_grid(k, 128, 0, (p.N + 127) / 128);
+    k<<<grid, 128, 0, st>>>(p);
+    return check_cuda(cudaGetLastError(), "query_direct_kernel launch");
+}
+
+template <int D, int C, int MODE>
+static int dispatch_variant(const QueryParams& p, cudaStream_t st, int variant) {
+    constexpr int NM = (D == 3) ? 64 : 256;
+    constexpr int BYTES = C * NM * 8;
+    switch (variant) {
+        case 1:
+            // bulk slots must leave room for at least 2 warps per CTA in 227 KB
+            if (BYTES <= 528) return launch_bulk<D, C, MODE, 128>(p, st);
+            if (BYTES <= 2048) return launch_bulk<D, C, MODE, 96>(p, st);
+            return launch_coop<D, C, MODE, 1>(p, st);
+        case 2: return launch_direct<D, C, MODE>(p, st);
+        case 10: return launch_coop<D, C, MODE, 1>(p, st);
+        case 11: return launch_coop<D, C, MODE, (C == 1 ? 2 : 1)>(p, st);
+        case 12: return launch_coop<D, C, MODE, (C == 1 ? 4 : (C == 3 ? 1 : 1))>(p, st);
+        default: return launch_coop<D, C, MODE, (C == 1 ? 2 : 1)>(p, st);
+    }
+}
+
+int query_device(const arb_geom* g, const double* table, int mode, double* q, int64_t N, int64_t ldq,
+                 double* out_comps, double* out_norm, double* out_grad, int64_t* out_cell, int64_t* masked_rows,
+                 unsigned long long* masked_count, cudaStream_t st, int variant) {
+    if (!g || (g->d != 3 && g->d != 4)) { set_error("arb_query: geometry missing or d not in {3,4}"); return 1; }
+    const int need_c = mode == ARB_MODE_VECTOR ? 3 : (mode == ARB_MODE_NORM ? 1 : (mode == ARB_MODE_BOTH ? 4 : -1));
+    if (need_c < 0 || g->ncomp != need_c) {
+        set_error("arb_query: mode %d needs a table with %d components, geometry says %d", mode, need_c, g->ncomp);
+        return 1;
+    }
+    if (N < 0 || ldq < g->d) { set_error("arb_query: need N >= 0 and ldq >= d (N=%lld ldq=%lld)", (long long)N, (long long)ldq); return 1; }
+    if (N == 0) return 0;
+    if (!table || !q) { set_error("arb_query: null table or query pointer"); return 1; }
+    if ((mode != ARB_MODE_NORM && !out_comps) || (mode != ARB_MODE_VECTOR && (!out_norm || !out_grad))) {
+        set_error("arb_query: output pointer missing for mode %d", mode);
+        return 1;
+    }
+    if (masked_rows && !masked_count) { set_error("arb_query: masked_rows given without masked_count"); return 1; }
+    QueryParams p;
+    memset(&p, 0, sizeof(p));
+    p.table = table; p.q = q; p.N = N; p.ldq = ldq;
+    p.out_comps = out_comps; p.out_norm = out_norm; p.out_grad = out_grad; p.out_cell = out_cell;
+    p.masked_rows = masked_rows; p.masked_count = masked_count;
+    p.total_cells = 1; p.layer_cells = 1;
+    for (int a = 0; a < g->d; ++a) {
+        if (g->ncell[a] < 1 || !(g->h[a] > 0.0)) { set_error("arb_query: axis %d has ncell=%lld h=%g", a, (long long)g->ncell[a], g->h[a]); return 1; }
+        p.mn[a] = g->int_min[a]; p.mx[a] = g->int_max[a]; p.h[a] = g->h[a]; p.nc[a] = g->ncell[a];
+        p.total_cells *= g->ncell[a];
+        if (a < g->d - 1) p.layer_cells *= g->ncell[a];
+    }
+    p.slab_lo = g->slab_lo; p.slab_hi = g->slab_hi;
+    if (p.slab_lo < 0 || p.slab_hi > g->ncell[g->d - 1] || p.slab_lo >= p.slab_hi) {
+        set_error("arb_query: bad slab [%lld,%lld)", (long long)p.slab_lo, (long long)p.slab_hi);
+        return 1;
+    }
+    if (g->d == 3) {
+        if (mode == ARB_MODE_VECTOR) return dispatch_variant<3, 3, 0>(p, st, variant);
+        if (mode == ARB_MODE_NORM) return dispatch_variant<3, 1, 1>(p, st, variant);
+        return dispatch_variant<3, 4, 2>(p, st, variant);
+    }
+    if (mode == ARB_MODE_VECTOR) return dispatch_variant<4, 3, 0>(p, st, variant);
+    if (mode == ARB_MODE_NORM) return dispatch_variant<4, 1, 1>(p, st, variant);
+    return dispatch_variant<4, 4, 2>(p, st, variant);
+}
+
+}  // namespace arb
+
+extern "C" {
+
+int arb_set_query_variant(int variant) {
+    const int old = arb::g_query_variant;
+    arb::g_query_variant = variant;
+    return old;
+}
+
+int arb_query(const arb_geom* g, const double* table, int mode, double* q, int64_t N, int64_t ldq, double* out_comps,
+              double* out_norm, double* out_grad, int64_t* out_cell, int64_t* masked_rows,
+              unsigned long long* masked_count, void* stream) {
+    return arb::query_device(g, table, mode, q, N, ldq, out_comps, out_norm, out_grad, out_cell, masked_rows,
+                             masked_count, (cudaStream_t)stream, arb::g_query_variant);
+}
+}

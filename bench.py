@@ -1,0 +1,439 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the ARBInterp interpolation hot path on B200.
+
+Workload (BASELINE.json north_star / configs[2], value+gradient variant): synthetic analytic
+256^3 vector field, tricubic, uniformly random in-volume queries; each rank holds a replica of the
+coefficient table and evaluates its own query batch (weak scaling, no collective on the query path).
+A "step" is one pass of the query kernel over one batch of Q queries.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode norm|vector|both] [--impl reference]
+
+Prints ONE JSON line (rank 0).  Keys follow the driver contract; `roofline`, `cpu_baseline`, `e2e`,
+`clocks` and `gpu_launches` are described in DESIGN.md "Measurement".
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_BYTES = {  # coords in + one coefficient block per component + outputs, no reuse
+    (3, "norm"): 568, (3, "vector"): 1584, (3, "both"): 2128,
+    (4, "norm"): 2120, (4, "vector"): 6200, (4, "both"): 8288,
+}
+METRIC = "interp queries/sec (value+grad)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--grid", type=int, default=256)
+    ap.add_argument("--mode", default="norm", choices=["norm", "vector", "both"])
+    ap.add_argument("--queries", type=int, default=1 << 26, help="queries per step and rank (device-resident leg)")
+    ap.add_argument("--e2e-queries", type=int, default=1 << 24, help="queries per step for the host-buffer leg")
+    ap.add_argument("--variant", type=int, default=None, help="query-kernel variant (arb_set_query_variant)")
+    ap.add_argument("--sweep", default="", help="comma list of variants to time (prints a table to stderr)")
+    ap.add_argument("--cpu-sample", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--other-modes", action="store_true", help="also time vector/both (device-resident)")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------
+# synthetic analytic field
+# ----------------------------------------------------------------------------------------
+def analytic_planes(torch, n, device):
+    ax = torch.linspace(-1.0, 1.0, n, dtype=torch.float64, device=device)
+    Z, Y, X = torch.meshgrid(ax, ax, ax, indexing="ij")
+    bx = torch.sin(2 * np.pi * X) * torch.cos(np.pi * Y) * torch.exp(-Z)
+    by = X * X * Y + Z
+    bz = torch.cos(X + Y + Z)
+    return ax, (X, Y, Z), (bx, by, bz)
+
+
+def analytic_field_rows(torch, n, device):
+    ax, (X, Y, Z), (bx, by, bz) = analytic_planes(torch, n, device)
+    return ax, torch.stack([t.reshape(-1) for t in (X, Y, Z, bx, by, bz)], dim=1)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                                  ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        busy = sorted(sm)[len(sm) // 2:]
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(mode):
+    """DRAM bytes per query from the committed ncu --set full capture (profiles/roofline_traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f).get(mode)
+    except Exception:
+        return None
+
+
+# ----------------------------------------------------------------------------------------
+# CPU arm: the numpy oracle (port of the reference) on the host cores
+# ----------------------------------------------------------------------------------------
+def make_cpu_oracle(n, mode):
+    from oracle.arb_oracle import OracleInterp
+    ax = np.linspace(-1.0, 1.0, n)
+    Z, Y, X = np.meshgrid(ax, ax, ax, indexing="ij")
+    bx = np.sin(2 * np.pi * X) * np.cos(np.pi * Y) * np.exp(-Z)
+    by = X * X * Y + Z
+    bz = np.cos(X + Y + Z)
+    vals = {}
+    if mode in ("vector", "both"):
+        vals.update(x=bx.ravel(), y=by.ravel(), z=bz.ravel())
+    if mode in ("norm", "both"):
+        vals["n"] = np.sqrt(bx * bx + by * by + bz * bz).ravel()
+    return OracleInterp.from_planes([ax, ax, ax], vals, mode)
+
+
+def cpu_queries(ora, count, seed):
+    rng = np.random.default_rng(seed)
+    g = ora.geo
+    q = np.empty((count, 3))
+    for a in range(3):
+        q[:, a] = g.int_min[a] + rng.uniform(0, 1, count) * (g.int_max[a] - g.int_min[a]) * (1 - 1e-12)
+    return q
+
+
+def cpu_warm_rate(ora, q, chunk=100_000):
+    """Warm rate: coefficients of the touched cells are filled first (the reference's lazy fill,
+    A.py:376-377), then the timed pass is the reference's rQuery arithmetic only."""
+    for lo in range(0, len(q), chunk):
+        ora.query(q[lo:lo + chunk].copy())
+    t0 = time.perf_counter()
+    for lo in range(0, len(q), chunk):
+        ora.query(q[lo:lo + chunk].copy())
+    return len(q) / (time.perf_counter() - t0)
+
+
+_PARENT_ORACLE = None
+
+
+def _worker(args):
+    count, seed, steps, warmup = args
+    ora = _PARENT_ORACLE                               # forked: planes shared copy-on-write
+    q = cpu_queries(ora, count, seed)
+    for lo in range(0, count, 100_000):
+        ora.query(q[lo:lo + 100_000].copy())          # fill
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        for lo in range(0, count, 100_000):
+            ora.query(q[lo:lo + 100_000].copy())
+        times.append(time.perf_counter() - t0)
+    return times[warmup:]
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (numpy port in oracle/, the
+    reference itself being pure Python that cannot travel to the GPU box) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    global _PARENT_ORACLE
+    os.environ["OMP_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    cores = len(os.sched_getaffinity(0))
+    procs = max(1, min(cores, 64))
+    per = max(20_000, min(200_000, args.cpu_sample // 5))
+    n = args.grid
+    t0 = time.perf_counter()
+    _PARENT_ORACLE = make_cpu_oracle(n, args.mode)
+    with mp.get_context("fork").Pool(procs) as pool:
+        res = pool.map(_worker, [(per, 100 + i, args.steps, args.warmup) for i in range(procs)])
+    wall = time.perf_counter() - t0
+    per_step = np.max(np.array(res), axis=0)                     # slowest worker per step
+    total_t = float(per_step.sum())
+    value = procs * per * args.steps / total_t
+    sample = f"{procs} forked workers x {per} warm queries/step on a {n}^3 grid (steps={args.steps}); wall {wall:.1f}s"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"tricubic {args.grid}^3 analytic vector field, mode={args.mode}, uniform random in-volume queries",
+                   "cpu_grid": n},
+        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------
+def time_device(torch, lib, obj, mode, d, q, outs, cells, steps, warmup, dist=None):
+    """K launches of the query kernel on device-resident queries; returns (elapsed_s, per-launch ms)."""
+    from arbinterp_b200 import _lib
+    code = {"vector": _lib.MODE_VECTOR, "norm": _lib.MODE_NORM, "both": _lib.MODE_BOTH}[mode]
+    stream = torch.cuda.current_stream()
+    n, ldq = q.shape
+
+    def launch():
+        _lib.check(lib.arb_query(ctypes.byref(obj._cgeom), obj.table.data_ptr(), code, q.data_ptr(), n, ldq,
+                                 outs[0].data_ptr() if outs[0] is not None else None,
+                                 outs[1].data_ptr() if outs[1] is not None else None,
+                                 outs[2].data_ptr() if outs[2] is not None else None,
+                                 cells.data_ptr(), None, None, stream.cuda_stream), "arb_query")
+
+    for _ in range(warmup):
+        launch()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev[0].record(stream)
+    for i in range(steps):
+        launch()
+        ev[i + 1].record(stream)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    per = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+    return ev[0].elapsed_time(ev[steps]) / 1e3, per
+
+
+def alloc_outputs(torch, mode, d, n, device):
+    kw = dict(dtype=torch.float64, device=device)
+    comps = torch.empty(n, 3, **kw) if mode in ("vector", "both") else None
+    norm = torch.empty(n, 1, **kw) if mode in ("norm", "both") else None
+    grad = torch.empty(n, d, **kw) if mode in ("norm", "both") else None
+    return comps, norm, grad
+
+
+def uniform_queries(torch, obj, n, seed, device):
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    q = torch.rand(n, 3, generator=g, dtype=torch.float64, device=device)
+    lo = torch.tensor([obj.xIntMin, obj.yIntMin, obj.zIntMin], dtype=torch.float64, device=device)
+    hi = torch.tensor([obj.xIntMax, obj.yIntMax, obj.zIntMax], dtype=torch.float64, device=device)
+    return lo + q * (hi - lo) * (1 - 1e-12)
+
+
+def run_b200(args):
+    import torch
+    from arbinterp_b200 import tricubic, _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=device)
+        dist = dist_mod
+    lib = _lib.load()
+    if args.variant is not None:
+        lib.arb_set_query_variant(args.variant)
+
+    # ---- construction (untimed): rank 0 makes the field, NCCL broadcast, every rank builds its replica
+    n = args.grid
+    t0 = time.perf_counter()
+    if rank == 0:
+        _, rows = analytic_field_rows(torch, n, device)
+    else:
+        rows = torch.empty(n ** 3, 6, dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.broadcast(rows, src=0)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    obj = tricubic(rows, "quiet", mode=args.mode)
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t1
+    del rows
+    torch.cuda.empty_cache()
+
+    d = 3
+    Q = args.queries
+    q = uniform_queries(torch, obj, Q, 1234 + rank, device)
+    outs = alloc_outputs(torch, args.mode, d, Q, device)
+    cells = torch.empty(Q, dtype=torch.int64, device=device)
+
+    if args.sweep:
+        for v in [int(s) for s in args.sweep.split(",")]:
+            lib.arb_set_query_variant(v)
+            el, per = time_device(torch, lib, obj, args.mode, d, q, outs, cells, args.steps, args.warmup)
+            if rank == 0:
+                print(f"[sweep] mode={args.mode} variant={v}: {Q * args.steps / el:.4e} q/s  "
+                      f"({ALG_BYTES[(d, args.mode)] * Q * args.steps / el / 1e9:.0f} GB/s algorithmic)  "
+                      f"min launch {min(per):.3f} ms", file=sys.stderr, flush=True)
+        lib.arb_set_query_variant(args.variant if args.variant is not None else 0)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    elapsed, per_launch = time_device(torch, lib, obj, args.mode, d, q, outs, cells, args.steps, args.warmup, dist)
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([elapsed], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed = float(t.item())
+    value = world * Q * args.steps / elapsed
+
+    # sanity inside the bench: outputs are finite for in-volume queries
+    assert bool(torch.isfinite(outs[1] if outs[1] is not None else outs[0]).all()), "non-finite outputs in bench"
+
+    # ---- other modes (device-resident), optional
+    others = {}
+    if args.other_modes and rank == 0 and world == 1:
+        del obj, outs
+        torch.cuda.empty_cache()
+        for m in ("vector", "both"):
+            if m == args.mode:
+                continue
+            _, rows = analytic_field_rows(torch, n, device)
+            o2 = tricubic(rows, "quiet", mode=m)
+            del rows
+            torch.cuda.empty_cache()
+            Q2 = Q // 2
+            outs2 = alloc_outputs(torch, m, d, Q2, device)
+            el, per = time_device(torch, lib, o2, m, d, q[:Q2], outs2, cells[:Q2], args.steps, args.warmup)
+            rate = Q2 * args.steps / el
+            others[m] = {"value": rate, "unit": "queries/s", "alg_gbs": ALG_BYTES[(d, m)] * rate / 1e9}
+            del o2, outs2
+            torch.cuda.empty_cache()
+        _, rows = analytic_field_rows(torch, n, device)
+        obj = tricubic(rows, "quiet", mode=args.mode)
+        del rows
+
+    # ---- end-to-end leg: public API with host (pinned) numpy buffers, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        QE = args.e2e_queries
+        qh = torch.empty(QE, 3, dtype=torch.float64, pin_memory=True)
+        qh.copy_(q[:QE])
+        qnp = qh.numpy()
+        for _ in range(max(1, min(args.warmup, 2))):
+            res = obj.Query(qnp)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res = obj.Query(qnp)
+        torch.cuda.synchronize()
+        te = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([te], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            te = float(t.item())
+        res = res if isinstance(res, tuple) else (res,)
+        d2h = sum(r.nbytes for r in res if r is not None)
+        e2e = {"value": world * QE * args.steps / te, "unit": "queries/s", "h2d_bytes_per_step": int(qnp.nbytes),
+               "d2h_bytes_per_step": int(d2h), "queries_per_step": QE,
+               "api": "tricubic.Query(numpy float64 [N,3] in pinned host memory) -> numpy outputs"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline beside it (rank 0, N=1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        ncpu = n
+        ora = make_cpu_oracle(ncpu, args.mode)
+        qc = cpu_queries(ora, args.cpu_sample, 7)
+        rate = cpu_warm_rate(ora, qc)
+        cpu = {"value": rate, "unit": "queries/s", "cores": 1, "kind": "port",
+               "sample": f"{args.cpu_sample} warm queries (second pass, coefficients cached) through the numpy oracle "
+                         f"on a {ncpu}^3 grid of the same analytic field, single process"}
+
+    peak, peak_src = measured_peak()
+    alg = ALG_BYTES[(d, args.mode)]
+    avg_ms = float(np.mean(per_launch))
+    achieved = alg * Q / (avg_ms * 1e-3) / 1e9
+    traffic_per_query = ncu_traffic(args.mode)
+    line = {
+        "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"tricubic {n}^3 analytic vector field, mode={args.mode} (value+gradient), "
+                               f"uniform random in-volume queries",
+                   "queries_per_step_per_gpu": Q, "table_gb": obj.table.numel() * 8 / 1e9,
+                   "cache": "inputs larger than L2 (query batch %.1f GB, table %.1f GB vs 126 MB L2)" %
+                            (q.numel() * 8 / 1e9, obj.table.numel() * 8 / 1e9),
+                   "parallelism": f"replicated table, queries sharded x{world}",
+                   "variant": args.variant if args.variant is not None else 0, "build_s": t_build},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": (traffic_per_query * Q) if traffic_per_query else None,
+                     "kernel": "query kernel (arb_query)", "alg_bytes_per_query": alg,
+                     "avg_launch_ms": avg_ms, "peak_source": peak_src},
+        "cpu_baseline": cpu,
+        "e2e": e2e,
+        "gpu_launches": args.steps * world,
+        "clocks": clocks,
+    }
+    if others:
+        line["other_modes"] = others
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

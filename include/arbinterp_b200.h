@@ -1,0 +1,113 @@
+/*
+ * arbinterp_b200 -- C ABI of the B200-native ARBInterp interpolation hot path.
+ *
+ * This is the drop-in boundary: plain C, plain pointers and sizes, no torch types.
+ * The reference (DurhamDecLab/ARBInterp) is pure Python/numpy and has no FFI of its own;
+ * each entry point below names the reference method it replaces
+ * (A.py = src/ARBInterp/ARBInterp.py in the reference tree).  The Python classes in
+ * arbinterp_b200/interp.py bind these through ctypes; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; arb_last_error() then
+ *     returns a thread-local, NUL-terminated description.  No exceptions cross the ABI.
+ *   - "device pointer" = CUDA device memory of the current device; caller-owned.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device
+ *     entry points only enqueue work; they never synchronise the host unless stated.
+ *   - all floating point is IEEE float64; cell indices are int64.
+ *   - re-entrant for distinct streams/buffers; a table is read-only during queries.
+ *
+ * Data layout
+ *   grid   : [C][nt][nz][ny][nx] float64, x fastest (the reference's sorted row order,
+ *            A.py:530-532 / 1266-1269, one dense plane per interpolated component).
+ *   table  : [ncell_local + 1][C][4^d] float64, cell-major; coefficient m = i + 4j + 16k
+ *            (+ 64l) multiplies u^i v^j w^k (s^l) (A.py:380-382 / 1107-1110).  Row
+ *            `ncell_local` is the NaN sentinel (A.py:45,57,70).  Component order for C=3 is
+ *            (x,y,z), for C=4 (x,y,z,norm), for C=1 the scalar / norm.
+ *   query  : [N][ldq] float64, first d columns are coordinates, the rest is ignored
+ *            (README "Further columns can be present").
+ */
+#ifndef ARBINTERP_B200_H
+#define ARBINTERP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARB_MODE_VECTOR 0 /* Query1 / rQuery1: components only        (A.py:344-397, 1064-1127) */
+#define ARB_MODE_NORM   1 /* Query2 / rQuery2: value + gradient       (A.py:399-454, 1129-1188) */
+#define ARB_MODE_BOTH   2 /* Query3 / rQuery3: components, value, grad (A.py:457-521, 1190-1258) */
+
+/* Geometry the reference derives in getFieldParams (A.py:541-568, 1288-1320). */
+typedef struct arb_geom {
+    int32_t d;            /* 3 = tricubic, 4 = quadcubic                                        */
+    int32_t ncomp;        /* C, components stored per cell in the table (1, 3 or 4)              */
+    int64_t ncell[4];     /* interpolatable cells per axis, n-3 (A.py:545, 1288-1291)            */
+    int64_t slab_lo;      /* first cell layer of the slowest axis held by `table` (0 = whole)    */
+    int64_t slab_hi;      /* one past the last cell layer held (ncell[d-1] = whole)              */
+    double  int_min[4];   /* xIntMin.. : second grid coordinate per axis (A.py:551-553)          */
+    double  int_max[4];   /* xIntMax.. : second-to-last grid coordinate  (A.py:554-556)          */
+    double  h[4];         /* hx.. = |axis[0]-axis[1]| (A.py:547-549)                             */
+} arb_geom;
+
+const char* arb_version(void);
+const char* arb_last_error(void);
+
+/* Constant matrices of makeAMatrix (A.py:107-175, 726-878), generated exactly (no LAPACK).
+ *   which: 0 = inv(B) (integer Hermite inverse), 1 = D (finite differences), 2 = A = inv(B)*D.
+ *   reference_quirk != 0 reproduces the A.py:860 off-by-one in the 4-D matrix (the default
+ *   everywhere in this library; parity with the reference needs it).
+ *   out_host: HOST buffer of 4^d * 4^d doubles, row-major. */
+int arb_get_matrix(int d, int which, int reference_quirk, double* out_host);
+
+/* Coefficient build = allCoeffs() (A.py:523-525, 1260-1262) for every cell of `grid`:
+ * finite-difference b-vector (A.py:129-173) in shared memory over a TMA-staged grid tile,
+ * then the Lekien-Marsden solve alpha = inv(B) b (A.py:175, 577-579) as an FP64 tensor-core
+ * contraction.  Writes (prod(n-3) + 1) * C * 4^d doubles to `table` (device), including the
+ * NaN sentinel row.  For slab sharding pass the sub-grid of planes [lo-1, hi+2] of the
+ * slowest axis: the build is local to the planes it is given.
+ *   n[a] = grid points per axis (x first).  grid/table: device pointers. */
+int arb_build_coeffs(int d, const double* grid, int ncomp, const int64_t n[4], double* table,
+                     int reference_quirk, void* stream);
+int arb_build_coeffs_3d(const double* grid, int ncomp, int64_t nx, int64_t ny, int64_t nz,
+                        double* table, void* stream);
+int arb_build_coeffs_4d(const double* grid, int ncomp, int64_t nx, int64_t ny, int64_t nz, int64_t nt,
+                        double* table, void* stream);
+
+/* Range query = rQuery1/2/3 (A.py:344-521, 1064-1258) on device-resident data.
+ *   q          : device [N][ldq]; rows with a coordinate < IntMin or > IntMax are overwritten
+ *                with NaN IN PLACE across all ldq columns (A.py:350-355).
+ *   out_comps  : device [N][3]   (modes VECTOR, BOTH; else NULL)
+ *   out_norm   : device [N]      (modes NORM, BOTH;   else NULL)
+ *   out_grad   : device [N][d]   (modes NORM, BOTH;   else NULL), physical units (divided by h)
+ *   out_cell   : device [N] int64 or NULL -- global cell index, `total cells` for masked/NaN rows
+ *                (queryInds, A.py:368-370).
+ *   masked_rows/masked_count : optional device list (capacity N) + counter that receive the row
+ *                numbers NaN-masked in place (unordered); used by the host path to mirror the
+ *                side effect without copying q back.  Counter must be zeroed by the caller.
+ * A coordinate exactly on the upper edge whose per-axis index rounds to n-3 yields NaN
+ * (declared deviation, DESIGN.md "upper edge"). */
+int arb_query(const arb_geom* g, const double* table, int mode, double* q, int64_t N, int64_t ldq,
+              double* out_comps, double* out_norm, double* out_grad, int64_t* out_cell,
+              int64_t* masked_rows, unsigned long long* masked_count, void* stream);
+
+/* Same call with HOST pointers for q and the outputs: chunks the batch, stages it through
+ * pinned memory when the caller's buffers are pageable, and overlaps H2D / kernel / D2H on
+ * internal streams.  Synchronous: returns when the outputs (and the NaN-masked q rows) are
+ * complete in host memory.  `table` stays a device pointer.  out_cell_host may be NULL, a host
+ * buffer, or a DEVICE buffer of N int64 (then the indices stay on the GPU and cost no PCIe
+ * traffic; the Python classes read them back lazily for `queryInds`). */
+int arb_query_host(const arb_geom* g, const double* table, int mode, double* q_host, int64_t N, int64_t ldq,
+                   double* out_comps_host, double* out_norm_host, double* out_grad_host,
+                   int64_t* out_cell_host, int64_t chunk_rows);
+
+/* Tuning knob for experiments/benchmarks: selects the query-kernel variant
+ * (0 = default).  Returns the previous value. */
+int arb_set_query_variant(int variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARBINTERP_B200_H */

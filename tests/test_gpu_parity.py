@@ -1,0 +1,368 @@
+"""GPU tier (-m gpu): the CUDA path, called through the drop-in classes (which go through the
+C-ABI), against (i) the golden vectors of the live reference, (ii) the numpy oracle on seeded
+inputs, (iii) size-independent analytic properties at BASELINE.json's full grid sizes.
+
+Bar (north_star): cell indices and NaN masks bit-exact; values, gradients and components within
+1e-12 relative, scaled as |got-ref| <= 1e-12 * max(|ref|, S) with S = max|field component|
+(gradients: S/h) -- SURVEY 8d."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import assert_parity, load_golden
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+CASES = [("tri_12x10x9", 3, ["vector", "norm", "both"]), ("tri_scalar_9x8x11", 3, ["scalar"]),
+         ("quad_8x7x7x6", 4, ["vector", "norm", "both"]), ("quad_scalar_6x7x5x6", 4, ["scalar"])]
+RTOL = 1e-12
+
+
+def _cls(d):
+    from arbinterp_b200 import tricubic, quadcubic
+    return tricubic if d == 3 else quadcubic
+
+
+def _scales(field, d, h):
+    vals = field[:, d:]
+    s_comp = np.abs(vals).max(axis=0) if vals.shape[1] == 3 else None
+    s_norm = np.linalg.norm(vals, axis=1).max() if vals.shape[1] == 3 else np.abs(vals).max()
+    return s_comp, s_norm, s_norm / np.asarray(h)
+
+
+def _check_outputs(res, ref, mode, field, d, h, what):
+    s_comp, s_norm, s_grad = _scales(field, d, h)
+    res = res if isinstance(res, tuple) else (res,)
+    assert len(res) == len(ref)
+    worst = 0.0
+    i = 0
+    if mode in ("vector", "both"):
+        worst = max(worst, assert_parity(res[i], ref[i], s_comp[None, :], RTOL, what + " comps")); i += 1
+    if mode in ("norm", "both", "scalar"):
+        worst = max(worst, assert_parity(res[i], ref[i], s_norm, RTOL, what + " norm")); i += 1
+        worst = max(worst, assert_parity(res[i], ref[i], s_grad[None, :], RTOL, what + " grad"))
+    return worst
+
+
+def _golden_ref(g, mode):
+    return tuple(g[f"{mode}_out{i}"] for i in range(3) if f"{mode}_out{i}" in g.files)
+
+
+@pytest.mark.parametrize("name,d,modes", CASES)
+def test_golden_range_queries(name, d, modes):
+    g = load_golden(name)
+    for mode in modes:
+        kw = {} if mode == "scalar" else {"mode": mode}
+        obj = _cls(d)(g["field"].copy(), "quiet", **kw)
+        q = g[mode + "_q_in"].copy()
+        res = obj.Query(q)
+        _check_outputs(res, _golden_ref(g, mode), mode, g["field"], d, g["h"], f"{name}/{mode}")
+        assert np.array_equal(q, g[mode + "_q_after"], equal_nan=True), "in-place NaN rows (A.py:350-355)"
+        assert np.array_equal(obj.queryInds, g[mode + "_inds"]), "cell indices must be bit-exact"
+        assert obj.nc == int(g["nc"])
+
+
+@pytest.mark.parametrize("name,d,modes", CASES)
+def test_golden_geometry_attributes(name, d, modes):
+    g = load_golden(name)
+    obj = _cls(d)(g["field"].copy(), "quiet")
+    names = "xyzt"[:d]
+    assert [getattr(obj, "h" + c) for c in names] == list(g["h"])
+    assert [getattr(obj, c + "IntMin") for c in names] == list(g["int_min"])
+    assert [getattr(obj, c + "IntMax") for c in names] == list(g["int_max"])
+    if d == 3:
+        assert np.array_equal(obj.nPos, g["ncell_axis"])
+    else:
+        assert [obj.nPosx - 3, obj.nPosy - 3, obj.nPosz - 3, obj.nPost - 3] == list(g["ncell_axis"])
+    assert np.array_equal(obj.basePointInds, g["base_point_inds"])
+    assert np.array_equal(obj.inputfield, g["sorted_field"])
+    m = load_golden("matrices")
+    key, sc = ("A3_times8", 8) if d == 3 else ("A4_times16", 16)
+    assert np.array_equal(obj.A * sc, m[key].astype(np.float64))
+
+
+@pytest.mark.parametrize("name,d,modes", CASES)
+def test_golden_coefficient_table(name, d, modes):
+    """Build kernels (TMA stencil + DMMA solve) against the reference's alpha arrays after allCoeffs()."""
+    g = load_golden(name)
+    mode = modes[-1]
+    kw = {} if mode == "scalar" else {"mode": mode}
+    obj = _cls(d)(g["field"].copy(), "quiet", **kw)
+    obj.allCoeffs()
+    for k in "xyzn":
+        key = f"{mode}_alpha{k}"
+        if key not in g.files:
+            continue
+        ref = g[key]
+        got = getattr(obj, "alpha" + k)
+        assert got.shape == ref.shape
+        scale = np.abs(ref[:, :-1]).max()
+        assert_parity(got[:, :obj.nc], ref[:, :obj.nc], scale, RTOL, f"{name} alpha{k}")
+        assert np.array_equal(np.isnan(got[:, -1]), np.isnan(ref[:, -1]))
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 10, 11, 12])
+@pytest.mark.parametrize("name,d,modes", CASES)
+def test_all_kernel_variants(name, d, modes, variant, cuda_lib):
+    g = load_golden(name)
+    old = cuda_lib.arb_set_query_variant(variant)
+    try:
+        for mode in modes:
+            kw = {} if mode == "scalar" else {"mode": mode}
+            obj = _cls(d)(g["field"].copy(), "quiet", **kw)
+            q = g[mode + "_q_in"].copy()
+            res = obj.Query(q)
+            _check_outputs(res, _golden_ref(g, mode), mode, g["field"], d, g["h"], f"{name}/{mode}/v{variant}")
+            assert np.array_equal(q, g[mode + "_q_after"], equal_nan=True)
+            assert np.array_equal(obj.queryInds, g[mode + "_inds"])
+    finally:
+        cuda_lib.arb_set_query_variant(old)
+
+
+@pytest.mark.parametrize("name,d,modes", CASES)
+def test_golden_single_point_queries(name, d, modes):
+    g = load_golden(name)
+    for mode in modes:
+        kw = {} if mode == "scalar" else {"mode": mode}
+        obj = _cls(d)(g["field"].copy(), "quiet", **kw)
+        q_in = g[mode + "_q_in"]
+        s_comp, s_norm, s_grad = _scales(g["field"], d, g["h"])
+        for row, ref in zip(g[mode + "_single_rows"], g[mode + "_single_out"]):
+            out = obj.Query(q_in[row, :d].copy())
+            if mode == "vector":
+                assert out.shape == (3,)
+                flat, scale = out, s_comp
+            elif mode in ("norm", "scalar"):
+                assert np.ndim(out[0]) == 0 and out[1].shape == (d,)
+                flat, scale = np.concatenate([[out[0]], out[1]]), np.concatenate([[s_norm], s_grad])
+            else:
+                assert out[0].shape == (3,) and np.ndim(out[1]) == 0 and out[2].shape == (d,)
+                flat = np.concatenate([out[0], [out[1]], out[2]])
+                scale = np.concatenate([s_comp, [s_norm], s_grad])
+            assert_parity(flat, ref, scale, RTOL, f"{name}/{mode} single")
+        # outside the volume: bare nan in vector mode, TypeError from the tuple unpack otherwise (A.py:198, 216)
+        far = np.full(d, 1e9)
+        if mode == "vector":
+            assert np.isnan(obj.Query(far))
+        else:
+            with pytest.raises(TypeError):
+                obj.Query(far)
+
+
+def test_example_diagonal():
+    g = load_golden("tri_example_diag")
+    from arbinterp_b200 import tricubic
+    obj = tricubic(g["field"].copy(), "quiet")
+    norms, grads = obj.Query(g["coords"].copy())
+    s = np.abs(g["field"][:, 3]).max()
+    assert_parity(norms, g["norms"], s, RTOL, "diag norms")
+    assert_parity(grads, g["grads"], s / np.array([obj.hx, obj.hy, obj.hz])[None, :], RTOL, "diag grads")
+    assert np.array_equal(obj.queryInds, g["inds"])
+    n1, g1 = obj.Query(g["coords"][3].copy())
+    assert_parity(n1, g["single_norm"], s, RTOL, "diag single")
+
+
+def _analytic_field3(nx, ny, nz, rng=None, scalar=False):
+    x = np.linspace(-1.0, 1.0, nx); y = np.linspace(-0.7, 0.9, ny); z = np.linspace(0.0, 1.5, nz)
+    Z, Y, X = np.meshgrid(z, y, x, indexing="ij")
+    X, Y, Z = X.ravel(), Y.ravel(), Z.ravel()
+    cols = [X, Y, Z, np.sin(2 * np.pi * X) * np.cos(np.pi * Y) * np.exp(-Z), X * X * Y + Z, np.cos(X + Y + Z)]
+    f = np.stack(cols, axis=1)
+    if scalar:
+        f = np.concatenate([f[:, :3], np.linalg.norm(f[:, 3:], axis=1)[:, None]], axis=1)
+    if rng is not None:
+        f = f[rng.permutation(len(f))]
+    return f
+
+
+def _uniform_queries(obj, d, n, rng, extra=0):
+    names = "xyzt"[:d]
+    lo = np.array([getattr(obj, c + "IntMin") for c in names]); hi = np.array([getattr(obj, c + "IntMax") for c in names])
+    q = rng.uniform(0, 1, (n, d + extra))
+    q[:, :d] = lo + q[:, :d] * (hi - lo) * (1 - 1e-12)
+    return q
+
+
+@pytest.mark.parametrize("mode", ["vector", "norm", "both"])
+@pytest.mark.parametrize("shape", [(37, 26, 23), (20, 41, 17)])
+def test_oracle_parity_3d_multi_tile(mode, shape):
+    """Odd nx (padded TMA pitch), cell counts that are not tile multiples, 10^5 seeded queries."""
+    from arbinterp_b200 import tricubic
+    from oracle.arb_oracle import OracleInterp
+    rng = np.random.default_rng(1234)
+    field = _analytic_field3(*shape, rng=rng)
+    obj = tricubic(field.copy(), "quiet", mode=mode)
+    q = _uniform_queries(obj, 3, 100_000, rng, extra=2)
+    q[::97, 1] = 5.0                      # out of volume
+    q[::1013, 2] = np.nan                 # NaN coordinate: output NaN, row not overwritten
+    ora = OracleInterp(field, 3, mode=mode)
+    q_ref = q.copy()
+    ref = ora.query(q_ref)
+    ref = ref if isinstance(ref, tuple) else (ref,)
+    q_gpu = q.copy()
+    res = obj.Query(q_gpu)
+    worst = _check_outputs(res, ref, mode, field, 3, ora.geo.h, f"3d {shape} {mode}")
+    assert np.array_equal(q_gpu, q_ref, equal_nan=True)
+    assert np.array_equal(obj.queryInds, ora.query_inds)
+    assert worst < 1e-13
+
+
+@pytest.mark.parametrize("mode", ["vector", "norm", "both"])
+def test_oracle_parity_4d_multi_tile(mode):
+    from arbinterp_b200 import quadcubic
+    from oracle.arb_oracle import OracleInterp
+    rng = np.random.default_rng(99)
+    ax = [np.linspace(-1, 1, 13), np.linspace(0, 1, 8), np.linspace(-2, 0, 9), np.linspace(0, 3e-6, 7)]
+    T, Z, Y, X = [a.ravel() for a in np.meshgrid(ax[3], ax[2], ax[1], ax[0], indexing="ij")]
+    ts = T / 3e-6
+    field = np.stack([X, Y, Z, T, np.sin(2 * X) * np.cos(3 * Y) * np.exp(Z) * np.cos(2 * ts),
+                      X * X * Y + Z * ts + 0.3 * X * Y * Z * ts, np.cos(X + Y + Z + ts)], axis=1)
+    field = field[rng.permutation(len(field))]
+    obj = quadcubic(field.copy(), "quiet", mode=mode)
+    q = _uniform_queries(obj, 4, 20_000, rng, extra=1)
+    q[::53, 3] = -1.0
+    ora = OracleInterp(field, 4, mode=mode)
+    q_ref = q.copy()
+    ref = ora.query(q_ref)
+    ref = ref if isinstance(ref, tuple) else (ref,)
+    q_gpu = q.copy()
+    res = obj.Query(q_gpu)
+    _check_outputs(res, ref, mode, field, 4, ora.geo.h, f"4d {mode}")
+    assert np.array_equal(q_gpu, q_ref, equal_nan=True)
+    assert np.array_equal(obj.queryInds, ora.query_inds)
+
+
+def test_device_tensor_path_and_pageable_host_path():
+    from arbinterp_b200 import tricubic
+    rng = np.random.default_rng(5)
+    field = _analytic_field3(21, 19, 18, rng=rng)
+    obj = tricubic(field.copy(), "quiet", mode="both")
+    q = _uniform_queries(obj, 3, 50_000, rng)
+    q[7] = [9.0, 0.0, 0.5]
+    host = obj.Query(q.copy())
+    qd = torch.from_numpy(q.copy()).cuda()
+    dev = obj.Query(qd)
+    for a, b in zip(host, dev):
+        assert isinstance(b, torch.Tensor) and b.is_cuda
+        assert np.array_equal(a, b.cpu().numpy(), equal_nan=True)
+    assert torch.isnan(qd[7]).all()
+    # float32 / non-contiguous input goes through a float64 copy; NaN rows are still written back
+    q32 = q.astype(np.float32)
+    r32 = obj.Query(q32)
+    assert np.isnan(q32[7]).all() and r32[0].dtype == np.float64
+    # small chunks exercise the 3-slot stream ring of arb_query_host
+    from arbinterp_b200 import _lib
+    n = len(q)
+    outs = [np.empty((n, 3)), np.empty((n, 1)), np.empty((n, 3))]
+    cells = np.empty(n, dtype=np.int64)
+    qq = q.copy()
+    rc = obj._lib.arb_query_host(ctypes.byref(obj._cgeom), obj.table.data_ptr(), _lib.MODE_BOTH, qq.ctypes.data, n, 3,
+                                 outs[0].ctypes.data, outs[1].ctypes.data, outs[2].ctypes.data, cells.ctypes.data, 4096)
+    assert rc == 0
+    for a, b in zip(host, outs):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert np.isnan(qq[7]).all() and cells[7] == obj.nc
+
+
+def test_upper_edge_and_errors(cuda_lib):
+    from arbinterp_b200 import tricubic, _lib
+    field = _analytic_field3(12, 11, 10)
+    obj = tricubic(field.copy(), "quiet", mode="norm")
+    q = np.array([[obj.xIntMax, obj.yIntMax, obj.zIntMax], [obj.xIntMin, obj.yIntMin, obj.zIntMin]])
+    norms, grads = obj.Query(q.copy())
+    assert np.isfinite(norms[1, 0])                      # lower edges are interpolatable
+    assert np.isnan(norms[0, 0]) or np.isfinite(norms[0, 0])   # never a crash; NaN when the index rounds to n-3
+    with pytest.raises(SystemExit):
+        tricubic(np.zeros((10, 5)), "quiet")
+    # mode / table mismatch is an error code, not a crash
+    rc = cuda_lib.arb_query(ctypes.byref(obj._cgeom), obj.table.data_ptr(), _lib.MODE_BOTH, 0, 1, 3, 0, 0, 0, 0, 0, 0, 0)
+    assert rc != 0 and b"components" in cuda_lib.arb_last_error()
+
+
+def test_slab_sharded_table_matches_whole():
+    """t-slab sharding: a slab built from planes [lo-1, hi+2] answers its own queries
+    bit-identically to the unsharded table and reports the global cell index."""
+    from arbinterp_b200 import quadcubic
+    g = load_golden("quad_8x7x7x6")
+    whole = quadcubic(g["field"].copy(), "quiet", mode="both")
+    q = g["both_q_in"].copy()
+    ref = whole.Query(q.copy())
+    inds = whole.queryInds
+    nt_cells = whole.nPost - 3
+    layer = whole.nc // nt_cells
+    got = [np.full_like(r, np.nan) for r in ref]
+    for lo, hi in [(0, 1), (1, nt_cells)]:
+        part = quadcubic(g["field"].copy(), "quiet", mode="both", slab=(lo, hi))
+        res = part.Query(q.copy())
+        assert np.array_equal(part.queryInds, inds)
+        own = (inds < whole.nc) & (inds // layer >= lo) & (inds // layer < hi)
+        for o, r in zip(got, res):
+            o[own] = r[own]
+            assert np.isnan(r[~own]).all()
+    for a, b in zip(got, ref):
+        assert np.array_equal(a, b, equal_nan=True)
+
+
+# ----------------------------------------------------------------------------------------
+# full-size property tests (BASELINE.json sizes; no oracle table needed)
+# ----------------------------------------------------------------------------------------
+def test_full_size_256_quadratic_reproduced():
+    """256^3 grid: per-axis quadratics are reproduced to round-off (central differences exact),
+    values and gradients, and the cell indices equal the oracle's locate() bit for bit."""
+    from arbinterp_b200 import tricubic
+    from oracle.arb_oracle import OracleInterp
+    n = 256
+    ax = torch.linspace(-1, 1, n, dtype=torch.float64)
+    Z, Y, X = torch.meshgrid(ax, ax, ax, indexing="ij")
+    f = lambda X, Y, Z: 1 + X - 2 * Y + 3 * Z + X * Y - Y * Z + X * X * Z + Y * Y - 0.5 * Z * Z * X
+    field = torch.stack([X.reshape(-1), Y.reshape(-1), Z.reshape(-1), f(X, Y, Z).reshape(-1)], dim=1)
+    obj = tricubic(field, "quiet")
+    assert obj.nc == 253 ** 3
+    rng = np.random.default_rng(20260117)
+    q = _uniform_queries(obj, 3, 1_000_000, rng)
+    norms, grads = obj.Query(q.copy())
+    x, y, z = q[:, 0], q[:, 1], q[:, 2]
+    assert np.max(np.abs(norms[:, 0] - f(x, y, z))) < 5e-13
+    gx = 1 + y + 2 * x * z - 0.5 * z * z
+    gy = -2 + x - z + 2 * y
+    gz = 3 - y + x * x - z * x
+    for got, want in zip(grads.T, (gx, gy, gz)):
+        assert np.max(np.abs(got - want)) < 5e-11      # divided by h = 2/255
+    # indices: oracle locate() on the same geometry (cheap, no table)
+    small = OracleInterp.__new__(OracleInterp)
+    from oracle.arb_oracle import GridGeometry
+    geo = GridGeometry.__new__(GridGeometry)
+    geo.d = 3; geo.ncell_axis = [253] * 3; geo.nc = 253 ** 3
+    geo.h = [obj.hx, obj.hy, obj.hz]; geo.int_min = [obj.xIntMin, obj.yIntMin, obj.zIntMin]
+    geo.int_max = [obj.xIntMax, obj.yIntMax, obj.zIntMax]
+    small.geo = geo; small.d = 3
+    inds, _ = small.locate(q.copy())
+    assert np.array_equal(inds, obj.queryInds)
+
+
+def test_full_size_4d_quirk_detector():
+    """4-D: polynomials without an x*y*z*t monomial are reproduced to round-off; adding x*y*z*t
+    shows the A.py:860 quirk (error ~1e-6 of the term) unless fixed_d4=True."""
+    from arbinterp_b200 import quadcubic
+    ax = [torch.linspace(-1, 1, 33, dtype=torch.float64), torch.linspace(0, 1, 30, dtype=torch.float64),
+          torch.linspace(-1, 0, 29, dtype=torch.float64), torch.linspace(0, 2, 17, dtype=torch.float64)]
+    T, Z, Y, X = torch.meshgrid(ax[3], ax[2], ax[1], ax[0], indexing="ij")
+    base = lambda X, Y, Z, T: 1 + X * Y - Z * T + X * X * T + Y * Z + 0.5 * T * T - X * Z
+    rng = np.random.default_rng(3)
+    for with_xyzt in (False, True):
+        fun = (lambda X, Y, Z, T: base(X, Y, Z, T) + X * Y * Z * T) if with_xyzt else base
+        field = torch.stack([X.reshape(-1), Y.reshape(-1), Z.reshape(-1), T.reshape(-1), fun(X, Y, Z, T).reshape(-1)], dim=1)
+        obj = quadcubic(field, "quiet")
+        q = _uniform_queries(obj, 4, 200_000, rng)
+        norms, _ = obj.Query(q.copy())
+        err = np.max(np.abs(norms[:, 0] - fun(*q.T)))
+        if not with_xyzt:
+            assert err < 1e-12
+        else:
+            assert 1e-9 < err < 1e-3, "reference quirk (A.py:860) must be reproduced by default"
+            fixed = quadcubic(field, "quiet", fixed_d4=True)
+            n2, _ = fixed.Query(q.copy())
+            assert np.max(np.abs(n2[:, 0] - fun(*q.T))) < 1e-12
