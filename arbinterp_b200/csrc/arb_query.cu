@@ -8,11 +8,13 @@
 // 10-20 % of the issue budget at roofline.
 //
 // Variants (arb_set_query_variant):
-//   0  COOP : G = 8 (3-D) / 32 (4-D) lanes share one query; lane l issues four 16-byte loads
+//   0  BLOCK: default, see query_block_kernel below (TMA block gather, one lane per 64-coefficient
+//             block, all modes and both dimensionalities).
+//   10 COOP : G = 8 (3-D) / 32 (4-D) lanes share one query; lane l issues four 16-byte loads
 //             that are contiguous across the group (one full 128 B line per group and
 //             instruction), evaluates its 8 coefficients and the partial sums are combined
 //             with a reduce-scatter over shuffles.  No shared memory, any block size.
-//   1  BULK : one query per thread; each thread asks the TMA engine (cp.async.bulk, SASS
+//   1  BULK : first TMA design: one query per thread; each thread asks the TMA engine (cp.async.bulk, SASS
 //             UBLKCP) to copy its cell's block into a private shared-memory slot, all copies
 //             of a warp complete on one mbarrier, then the thread streams its slot through a
 //             nested Horner scheme (LDS.128, conflict-free by a 16-byte slot skew).
@@ -388,6 +390,106 @@ __global__ void __launch_bounds__(THREADS) query_bulk_kernel(const QueryParams p
 }
 
 // ======================================================================================
+// Variant 0 (default): TMA block gather, one lane per 64-coefficient block
+// ======================================================================================
+// Work item = (batch of queries, component).  In 3-D a lane owns (query, component); in 4-D the
+// 256-coefficient block of a component is four tricubic blocks alpha[.., l], l = 0..3, and four
+// adjacent lanes own (query, component, l): each evaluates its tricubic block in (u, v, w) and the
+// four results are combined with weights s^l (value, d/dx, d/dy, d/dz) and l s^(l-1) (d/dt) over
+// two shuffle steps.  Every lane therefore always gathers exactly one 512-byte block with one
+// cp.async.bulk (UBLKCP) into its own 528-byte shared-memory slot, whatever the mode: 128-thread
+// CTAs use 66 KB, three are resident per SM and up to 192 KB of coefficient reads are in flight
+// per SM.  All copies of a warp complete on the warp's own mbarrier, so warps never wait for each
+// other.  DEDUP: lanes of a warp that want the same block elect one leader to fetch it and read
+// the leader's slot (warp-level binning by cell; free for clustered queries such as particle
+// bunches, one MATCH instruction of overhead for random ones).
+template <int D, int MODE, int THREADS, bool DEDUP>
+__global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams p) {
+    constexpr int C = MODE == 0 ? 3 : (MODE == 1 ? 1 : 4);
+    constexpr int SL = (D == 4) ? 4 : 1;          // tricubic blocks per component
+    constexpr int QPW = 32 / SL;                  // queries per warp item
+    constexpr int NM = 64 * SL;
+    constexpr uint32_t BYTES = 512;
+    constexpr uint32_t SLOT = BYTES + 16;         // skew keeps LDS.128 conflict-free across lanes
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bars[THREADS / 32];
+
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int qi = lane / SL, sl = lane % SL;
+    uint64_t* bar = &bars[wid];
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    const int64_t warp_global = ((int64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * THREADS) >> 5;
+    const int64_t nbatch = (p.N + QPW - 1) / QPW;
+    const int64_t nitem = nbatch * C;
+    uint32_t phase = 0;
+    for (int64_t item = warp_global; item < nitem; item += nwarps) {
+        const int64_t batch = item / C;
+        const int comp = (int)(item - batch * C);
+        const int64_t n = batch * QPW + qi;
+        Located<D> L;
+        L.ok = false; L.masked = false; L.cell_global = 0; L.cell_local = 0;
+        if (n < p.N) L = locate<D>(p, n);
+        const int64_t blk = (L.cell_local * C + comp) * SL + sl;      // 512-byte block number in the table
+        int src_lane = lane;
+        bool fetch = L.ok;
+        if (DEDUP) {
+            const unsigned peers = __match_any_sync(0xffffffffu, L.ok ? blk : (int64_t)(-1 - lane));
+            src_lane = __ffs(peers) - 1;
+            fetch = L.ok && (src_lane == lane);
+        }
+        const unsigned fmask = __ballot_sync(0xffffffffu, fetch);
+        if (lane == 0) mbar_expect_tx(bar, (uint32_t)__popc(fmask) * BYTES);
+        __syncwarp();
+        unsigned char* slot = smem + (size_t)(wid * 32 + lane) * SLOT;
+        if (fetch) bulk_g2s(slot, p.table + blk * 64, BYTES, bar);
+        if (comp == 0 && sl == 0 && n < p.N) {
+            if (p.out_cell) p.out_cell[n] = L.cell_global;
+            if (L.masked) mask_row_in_place(p, n);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        const double* cb = reinterpret_cast<const double*>(smem + (size_t)(wid * 32 + src_lane) * SLOT);
+        const bool grad_comp = (MODE == 1) || (MODE == 2 && comp == 3);     // warp-uniform
+        double g[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        if (L.ok) {
+            if (grad_comp) eval_value_grad<3, true>(cb, L.frac, g);
+            else g[0] = eval_value<3, true>(cb, L.frac);
+        }
+        if (D == 4) {
+            const double s = L.frac[D - 1];
+            const double w = pow_sel(s, sl), dw = dpow_sel(s, sl);
+            g[4] = g[0] * dw;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) g[i] *= w;
+            const int nred = grad_comp ? 5 : 1;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                if (i < nred) {
+                    g[i] += __shfl_xor_sync(0xffffffffu, g[i], 1);
+                    g[i] += __shfl_xor_sync(0xffffffffu, g[i], 2);
+                }
+            }
+        }
+        if (n < p.N && sl == 0) {
+            const double nan = qnan();
+            if (!grad_comp) {
+                p.out_comps[n * 3 + comp] = L.ok ? g[0] : nan;
+            } else {
+                p.out_norm[n] = L.ok ? g[0] : nan;
+#pragma unroll
+                for (int a = 0; a < D; ++a) p.out_grad[n * D + a] = L.ok ? __ddiv_rn(g[1 + a], p.h[a]) : nan;
+            }
+        }
+        __syncwarp();   // every lane is done with the slots before the next item's copies land
+    }
+}
+
+// ======================================================================================
 // Variant 2: naive one-thread-per-query from global memory
 // ======================================================================================
 template <int D, int C, int MODE>
@@ -430,14 +532,23 @@ static int launch_bulk(const QueryParams& p, cudaStream_t st) {
     constexpr int NM = (D == 3) ? 64 : 256;
     const size_t smem = (size_t)THREADS * (C * NM * 8 + 16);
     auto k = query_bulk_kernel<D, C, MODE, THREADS>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        ARB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
+    ARB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = persistent_grid(k, THREADS, smem, (p.N + THREADS - 1) / THREADS);
     k<<<grid, THREADS, smem, st>>>(p);
     return check_cuda(cudaGetLastError(), "query_bulk_kernel launch");
+}
+
+template <int D, int MODE, int THREADS, bool DEDUP>
+static int launch_block(const QueryParams& p, cudaStream_t st) {
+    constexpr int C = MODE == 0 ? 3 : (MODE == 1 ? 1 : 4);
+    constexpr int QPW = (D == 4) ? 8 : 32;
+    const size_t smem = (size_t)THREADS * 528;
+    auto k = query_block_kernel<D, MODE, THREADS, DEDUP>;
+    ARB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t items = ((p.N + QPW - 1) / QPW) * C;
+    const int grid = persistent_grid(k, THREADS, smem, (items + THREADS / 32 - 1) / (THREADS / 32));
+    k<<<grid, THREADS, smem, st>>>(p);
+    return check_cuda(cudaGetLastError(), "query_block_kernel launch");
 }
 
 template <int D, int C, int MODE>
@@ -453,16 +564,18 @@ static int dispatch_variant(const QueryParams& p, cudaStream_t st, int variant) 
     constexpr int NM = (D == 3) ? 64 : 256;
     constexpr int BYTES = C * NM * 8;
     switch (variant) {
-        case 1:
-            // bulk slots must leave room for at least 2 warps per CTA in 227 KB
-            if (BYTES <= 528) return launch_bulk<D, C, MODE, 128>(p, st);
-            if (BYTES <= 2048) return launch_bulk<D, C, MODE, 96>(p, st);
-            return launch_coop<D, C, MODE, 1>(p, st);
+        case 1:   // per-thread slots holding all components of a query (first TMA design)
+            if constexpr (BYTES <= 528) return launch_bulk<D, C, MODE, 128>(p, st);
+            else if constexpr (BYTES <= 2048) return launch_bulk<D, C, MODE, 96>(p, st);
+            else return launch_coop<D, C, MODE, 1>(p, st);
         case 2: return launch_direct<D, C, MODE>(p, st);
         case 10: return launch_coop<D, C, MODE, 1>(p, st);
         case 11: return launch_coop<D, C, MODE, (C == 1 ? 2 : 1)>(p, st);
-        case 12: return launch_coop<D, C, MODE, (C == 1 ? 4 : (C == 3 ? 1 : 1))>(p, st);
-        default: return launch_coop<D, C, MODE, (C == 1 ? 2 : 1)>(p, st);
+        case 20: return launch_block<D, MODE, 128, false>(p, st);
+        case 21: return launch_block<D, MODE, 64, true>(p, st);
+        case 22: return launch_block<D, MODE, 192, true>(p, st);
+        case 23: return launch_block<D, MODE, 384, true>(p, st);
+        default: return launch_block<D, MODE, 128, true>(p, st);
     }
 }
 

@@ -144,6 +144,9 @@ class _CubicInterpolator:
             stream = torch.cuda.current_stream(self._device).cuda_stream
             _lib.check(self._lib.arb_build_coeffs(d, sub.data_ptr(), ncomp, ctypes.byref(n), self._table.data_ptr(),
                                                    int(self._reference_quirk), stream), "arb_build_coeffs")
+            # construction is one-off: finish it here so that queries issued from any stream
+            # (arb_query_host uses its own copy/compute streams) see a complete table
+            torch.cuda.current_stream(self._device).synchronize()
         g = _lib.ArbGeom()
         g.d, g.ncomp = d, ncomp
         for a in range(4):

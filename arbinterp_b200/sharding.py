@@ -1,0 +1,140 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed): slab planning, construction-time
+broadcast and query routing.  Nothing here is on the per-query compute path -- a rank's queries are
+evaluated by its local table with no collective; the only exchanges are
+
+  * construction: one broadcast of the raw field (NCCL over NVLink), after which every rank
+    builds its replica or its slab locally (cheaper than moving a 25-400 GB table), and
+  * slab-sharded tables only: one all-to-all that moves each query row to the rank owning its
+    slowest-axis cell layer, and one that returns the result rows.
+
+The reference has no counterpart (it is single-process numpy); the arithmetic that decides the
+owner is the reference's cell location, ``floor((t - tIntMin) / ht)`` (A.py:1081-1086).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Sequence, Tuple
+
+import torch
+
+
+def plan_slabs(n_layers: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous, balanced ``[lo, hi)`` ranges of the slowest-axis cell layers, one per rank.
+    The first ``n_layers % world`` ranks get one layer more (61 layers / 8 ranks -> 8,8,8,8,8,7,7,7).
+    Ranks beyond ``n_layers`` get an empty slab ``(n_layers, n_layers)``."""
+    if n_layers < 1 or world < 1:
+        raise ValueError("need n_layers >= 1 and world >= 1")
+    base, extra = divmod(n_layers, world)
+    out, lo = [], 0
+    for r in range(world):
+        size = base + (1 if r < extra else 0)
+        out.append((lo, lo + size))
+        lo += size
+    return out
+
+
+def slab_planes(slab: Tuple[int, int]) -> Tuple[int, int]:
+    """Grid planes ``[first, last)`` of the slowest axis a slab needs: cell layer k uses grid points
+    k .. k+3 (offsets -1..+2 around its lower corner k+1), i.e. one halo plane below, two above."""
+    lo, hi = slab
+    return lo, hi + 3
+
+
+def owner_ranks(coord_slow: torch.Tensor, int_min: float, int_max: float, h: float,
+                slabs: Sequence[Tuple[int, int]]) -> torch.Tensor:
+    """Owning rank of every query from its slowest-axis coordinate.  Rows that are outside the
+    volume or NaN have no owner and are sent to rank 0, whose kernel NaN-masks them like any other
+    out-of-volume row.  Same expression as the kernel's locate (subtract, divide, floor)."""
+    layer = torch.floor((coord_slow - int_min) / h)
+    valid = (coord_slow >= int_min) & (coord_slow <= int_max)
+    n_layers = slabs[-1][1]
+    layer = torch.where(valid, layer, torch.zeros_like(layer)).clamp_(0, n_layers - 1).to(torch.int64)
+    bounds = torch.tensor([hi for _, hi in slabs], dtype=torch.int64, device=coord_slow.device)
+    owner = torch.searchsorted(bounds, layer, right=True)
+    return torch.where(valid, owner, torch.zeros_like(owner))
+
+
+def exchange_and_query(q: torch.Tensor, owner: torch.Tensor, evaluate: Callable[[torch.Tensor], torch.Tensor],
+                       out_cols: int, group=None) -> torch.Tensor:
+    """Route rows of ``q`` to their owners, evaluate there, route the results back.
+
+    ``evaluate(rows) -> (len(rows), out_cols)`` runs on the receiving rank (the local slab's query
+    kernel).  Returns ``(len(q), out_cols)`` in the caller's row order.  Two all-to-alls, none of
+    them inside the query kernel."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    order = torch.argsort(owner, stable=True)
+    send_counts = torch.bincount(owner, minlength=world)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    send_split = send_counts.tolist()
+    recv_split = recv_counts.tolist()
+    sendbuf = q[order].contiguous()
+    recvbuf = q.new_empty((sum(recv_split), q.shape[1]))
+    dist.all_to_all_single(recvbuf, sendbuf, recv_split, send_split, group=group)
+    res = evaluate(recvbuf)
+    if res.shape != (recvbuf.shape[0], out_cols):
+        raise ValueError(f"evaluate returned {tuple(res.shape)}, expected {(recvbuf.shape[0], out_cols)}")
+    back = res.new_empty((sendbuf.shape[0], out_cols))
+    dist.all_to_all_single(back, res.contiguous(), send_split, recv_split, group=group)
+    out = torch.empty_like(back)
+    out[order] = back
+    return out
+
+
+def broadcast_field(field, src: int = 0, device=None, group=None) -> torch.Tensor:
+    """Construction-time replicate: rank ``src`` holds the (N, cols) field, everyone gets a copy."""
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    if rank == src:
+        t = torch.as_tensor(field).to(device=device, dtype=torch.float64).contiguous()
+        shape = torch.tensor(list(t.shape), dtype=torch.int64, device=t.device)
+    else:
+        shape = torch.empty(2, dtype=torch.int64, device=device)
+    dist.broadcast(shape, src=src, group=group)
+    if rank != src:
+        t = torch.empty(tuple(shape.tolist()), dtype=torch.float64, device=device)
+    dist.broadcast(t, src=src, group=group)
+    return t
+
+
+class SlabShardedInterp:
+    """A tricubic/quadcubic whose coefficient table is sharded over the ranks by slowest-axis
+    slabs (config 5: 96^3 x 64 'both' = 402 GB over 8 GPUs).  ``Query`` takes this rank's rows and
+    returns this rank's results; rows travel to the owning rank and back."""
+
+    def __init__(self, cls, field, *args, group=None, src: int = 0, **kwargs):
+        import torch.distributed as dist
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        device = kwargs.get("device") or torch.device("cuda", torch.cuda.current_device())
+        full = broadcast_field(field, src=src, device=device, group=group)
+        d = cls._d
+        n_slow = int(torch.unique(full[:, d - 1]).numel()) - 3
+        self.slabs = plan_slabs(n_slow, self.world)
+        lo, hi = self.slabs[self.rank]
+        if hi == lo:
+            raise ValueError(f"rank {self.rank} has an empty slab: {n_slow} layers over {self.world} ranks")
+        self.local = cls(full, *args, slab=(lo, hi), **kwargs)
+        del full
+        self.d = d
+        g = self.local._geo
+        self._slow = (g.int_min[d - 1], g.int_max[d - 1], g.h[d - 1])
+
+    def Query(self, q: torch.Tensor):
+        """``q``: CUDA tensor (N, >=d) of this rank.  Returns what the local class returns, as CUDA
+        tensors in the caller's row order."""
+        d, mode = self.d, self.local._mode
+        owner = owner_ranks(q[:, d - 1], *self._slow, self.slabs)
+        widths = {"vector": (3,), "norm": (1, d), "both": (3, 1, d)}[mode]
+
+        def evaluate(rows):
+            res = self.local.Query(rows[:, :d].contiguous())
+            res = res if isinstance(res, tuple) else (res,)
+            return torch.cat(res, dim=1)
+
+        flat = exchange_and_query(q[:, :d].contiguous(), owner, evaluate, sum(widths), self.group)
+        outs, col = [], 0
+        for w in widths:
+            outs.append(flat[:, col:col + w])
+            col += w
+        return outs[0] if len(outs) == 1 else tuple(outs)

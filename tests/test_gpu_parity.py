@@ -104,7 +104,7 @@ def test_golden_coefficient_table(name, d, modes):
         assert np.array_equal(np.isnan(got[:, -1]), np.isnan(ref[:, -1]))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 10, 11, 12])
+@pytest.mark.parametrize("variant", [0, 1, 2, 10, 11, 20, 21, 22, 23])
 @pytest.mark.parametrize("name,d,modes", CASES)
 def test_all_kernel_variants(name, d, modes, variant, cuda_lib):
     g = load_golden(name)
@@ -150,6 +150,37 @@ def test_golden_single_point_queries(name, d, modes):
         else:
             with pytest.raises(TypeError):
                 obj.Query(far)
+
+
+def test_norm_plane_bit_exact_on_gpu():
+    """Bn = ||(Bx,By,Bz)|| (A.py:58, 74): same products, same sum order, IEEE sqrt -> identical bits."""
+    from arbinterp_b200.ingest import ingest_field, norm_plane
+    g = load_golden("tri_12x10x9")
+    planes, _ = ingest_field(g["field"], 3, device="cuda")
+    ref = np.linalg.norm(g["sorted_field"][:, 3:], axis=1)
+    assert np.array_equal(norm_plane(planes).reshape(-1).cpu().numpy(), ref)
+
+
+def test_warp_dedup_clustered_queries():
+    """Many queries in few cells (the example scripts' line queries, particle bunches): lanes that
+    share a cell read one fetched block; results must equal the no-dedup kernel bit for bit."""
+    from arbinterp_b200 import tricubic, _lib
+    rng = np.random.default_rng(8)
+    field = _analytic_field3(16, 15, 14, rng=rng)
+    obj = tricubic(field.copy(), "quiet", mode="both")
+    centre = np.array([0.1, 0.05, 0.7])
+    q = centre + rng.normal(0, 0.03, (20_000, 3))
+    q[::7] = q[3]                                    # exact duplicates too
+    lib = _lib.load()
+    res = {}
+    for v in (0, 20):
+        old = lib.arb_set_query_variant(v)
+        try:
+            res[v] = obj.Query(q.copy())
+        finally:
+            lib.arb_set_query_variant(old)
+    for a, b in zip(res[0], res[20]):
+        assert np.array_equal(a, b, equal_nan=True)
 
 
 def test_example_diagonal():

@@ -1,0 +1,220 @@
+"""CPU tier: host-side logic (PyTorch ingest, C-ABI surface, slab planning and query routing).
+No GPU compute is called here."""
+import ctypes
+import os
+import re
+import socket
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+
+from arbinterp_b200 import _lib
+from arbinterp_b200.ingest import FieldError, ingest_field, norm_plane, sorted_field
+from arbinterp_b200.sharding import exchange_and_query, owner_ranks, plan_slabs, slab_planes
+
+
+# ----------------------------------------------------------------------------------------- ingest
+@pytest.mark.parametrize("name,d", [("tri_12x10x9", 3), ("quad_8x7x7x6", 4), ("tri_scalar_9x8x11", 3)])
+def test_ingest_matches_reference_geometry(name, d):
+    g = load_golden(name)
+    planes, geo = ingest_field(g["field"], d)             # rows are shuffled in the fixture
+    assert geo.h == list(g["h"]) and geo.int_min == list(g["int_min"]) and geo.int_max == list(g["int_max"])
+    assert geo.ncell == list(g["ncell_axis"]) and geo.nc == int(g["nc"])
+    srt = g["sorted_field"]                                # the reference's sorted inputfield
+    assert np.array_equal(sorted_field(planes, geo).numpy(), srt)
+    for c in range(planes.shape[0]):
+        assert np.array_equal(planes[c].reshape(-1).numpy(), srt[:, d + c])
+
+
+def test_ingest_does_not_modify_input_and_accepts_tensors():
+    g = load_golden("tri_12x10x9")
+    f = g["field"].copy()
+    p1, _ = ingest_field(f, 3)
+    assert np.array_equal(f, g["field"])
+    p2, _ = ingest_field(torch.from_numpy(f), 3)
+    assert torch.equal(p1, p2)
+
+
+def test_norm_plane_matches_numpy():
+    """Same operation order as np.linalg.norm(axis=1) (A.py:58).  torch's CPU sqrt is a vectorised
+    approximation that is 1 ulp off in places, so this CPU check allows 1 ulp; the CUDA sqrt is
+    IEEE and the gpu-marked twin of this test (test_gpu_parity.py) asserts bit equality."""
+    g = load_golden("tri_12x10x9")
+    planes, _ = ingest_field(g["field"], 3)
+    ref = np.linalg.norm(g["sorted_field"][:, 3:], axis=1)
+    got = norm_plane(planes).reshape(-1).numpy()
+    assert np.max(np.abs(got - ref) / np.spacing(ref)) <= 1.0
+
+
+def test_ingest_rejects_bad_grids():
+    g = load_golden("tri_12x10x9")
+    f = g["field"]
+    with pytest.raises(FieldError, match="full grid"):
+        ingest_field(f[:-1], 3)                            # a missing point
+    dup = f.copy(); dup[0, :3] = dup[1, :3]
+    with pytest.raises(FieldError, match="full grid"):
+        ingest_field(dup, 3)
+    x = np.linspace(0, 1, 3)
+    Z, Y, X = np.meshgrid(x, x, x, indexing="ij")
+    with pytest.raises(FieldError, match="at least 4"):
+        ingest_field(np.stack([X.ravel(), Y.ravel(), Z.ravel(), X.ravel()], 1), 3)
+    bad = f.copy(); bad[3, 1] = np.nan
+    with pytest.raises(FieldError, match="NaN"):
+        ingest_field(bad, 3)
+
+
+def test_ingest_warns_on_irregular_spacing():
+    x = np.array([0.0, 1.0, 2.0, 3.5, 4.0]); y = np.arange(4.0)
+    Z, Y, X = np.meshgrid(y, y, x, indexing="ij")
+    with pytest.warns(RuntimeWarning, match="not evenly spaced"):
+        ingest_field(np.stack([X.ravel(), Y.ravel(), Z.ravel(), X.ravel()], 1), 3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        ingest_field(load_golden("tri_12x10x9")["field"], 3)   # linspace grids pass
+
+
+# ----------------------------------------------------------------------------------------- C-ABI
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "arbinterp_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(arb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    declared = _declared_functions()
+    assert set(declared) == set(_lib.EXPORTED_SYMBOLS)
+    for sym in declared:
+        assert getattr(lib, sym) is not None
+    assert b"arbinterp_b200" in lib.arb_version()
+
+
+def test_exact_matrices_against_reference_fixtures():
+    from oracle.arb_oracle import a_matrix, difference_matrix, hermite_matrix
+    m = load_golden("matrices")
+    for d, key, sc in ((3, "A3_times8", 8), (4, "A4_times16", 16)):
+        assert np.array_equal(_lib.get_matrix(d, "A") * sc, m[key].astype(np.float64))
+        B = m["B3" if d == 3 else "B4"].astype(np.float64)
+        assert np.array_equal(_lib.get_matrix(d, "invB") @ B, np.eye(4 ** d))     # exact integer inverse
+        assert np.array_equal(_lib.get_matrix(d, "D"), difference_matrix(d))
+        assert np.array_equal(_lib.get_matrix(d, "A", False), a_matrix(d, False))
+        assert np.array_equal(hermite_matrix(d), B)
+
+
+def test_argument_validation_without_gpu():
+    lib = _lib.load()
+    g = _lib.ArbGeom()
+    g.d, g.ncomp = 3, 1
+    for a in range(3):
+        g.ncell[a], g.h[a], g.int_min[a], g.int_max[a] = 5, 0.1, 0.0, 0.5
+    g.slab_lo, g.slab_hi = 0, 5
+    assert lib.arb_query(ctypes.byref(g), None, _lib.MODE_NORM, None, 0, 3, None, None, None, None, None, None, None) == 0
+    assert lib.arb_query(ctypes.byref(g), None, _lib.MODE_BOTH, None, 4, 3, None, None, None, None, None, None, None) != 0
+    assert b"components" in lib.arb_last_error()
+    assert lib.arb_query(ctypes.byref(g), None, _lib.MODE_NORM, None, 4, 2, None, None, None, None, None, None, None) != 0
+    assert b"ldq" in lib.arb_last_error()
+    n = (ctypes.c_int64 * 4)(8, 8, 8, 1)
+    assert lib.arb_build_coeffs(5, None, 1, ctypes.byref(n), None, 1, None) != 0
+    assert lib.arb_get_matrix(2, 0, 1, None) != 0
+    old = lib.arb_set_query_variant(1)
+    assert lib.arb_set_query_variant(old) == 1
+
+
+def test_wrong_shape_exits_like_reference():
+    from arbinterp_b200 import quadcubic, tricubic
+    with pytest.raises(SystemExit, match="N x 4 or N x 6"):
+        tricubic(np.zeros((10, 5)), "quiet")                   # A.py:104
+    with pytest.raises(SystemExit, match="N x 5 or N x 7"):
+        quadcubic(np.zeros((10, 4)), "quiet")                  # A.py:723
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    from arbinterp_b200 import tricubic
+    with pytest.raises(_lib.ArbError, match="no CPU fallback"):
+        tricubic(load_golden("tri_12x10x9")["field"], "quiet")
+
+
+def test_drop_in_import_paths():
+    import ARBInterp.ARBInterp as a
+    import ARBTools.ARBInterp as b
+    import arbinterp_b200
+    assert a.tricubic is arbinterp_b200.tricubic and b.quadcubic is arbinterp_b200.quadcubic
+    assert a.__version__ == "1.8"
+
+
+# ----------------------------------------------------------------------------------------- sharding
+def test_plan_slabs():
+    assert plan_slabs(61, 8) == [(0, 8), (8, 16), (16, 24), (24, 32), (32, 40), (40, 47), (47, 54), (54, 61)]
+    assert plan_slabs(3, 1) == [(0, 3)]
+    assert plan_slabs(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
+    assert slab_planes((8, 16)) == (8, 19)                  # 1 halo plane below the first corner, 2 above
+    with pytest.raises(ValueError):
+        plan_slabs(0, 2)
+
+
+def test_owner_ranks_follow_cell_location():
+    slabs = plan_slabs(10, 3)                              # (0,4) (4,7) (7,10)
+    t0, h = 0.5, 0.25
+    t1 = t0 + 10 * h
+    t = torch.tensor([t0, t0 + 3.999 * h, t0 + 4 * h, t0 + 6.5 * h, t0 + 7 * h, t1, t0 - 1e-9, t1 + 1.0, float("nan")],
+                     dtype=torch.float64)
+    own = owner_ranks(t, t0, t1, h, slabs)
+    assert own.tolist() == [0, 0, 1, 1, 2, 2, 0, 0, 0]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _routing_worker(rank, world, port, field, q_all, out_dir):
+    import torch.distributed as dist
+    from oracle.arb_oracle import OracleInterp
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d = 4
+    ora = OracleInterp(field, d, mode="both")
+    geo = ora.geo
+    slabs = plan_slabs(geo.ncell_axis[d - 1], world)
+    lo, hi = slabs[rank]
+    seen = []
+
+    def evaluate(rows):
+        # the local "slab": must only ever be asked about its own layers (or unowned NaN rows on rank 0)
+        r = rows.numpy().copy()
+        layer = np.floor((r[:, d - 1] - geo.int_min[d - 1]) / geo.h[d - 1])
+        inside = (r[:, d - 1] >= geo.int_min[d - 1]) & (r[:, d - 1] <= geo.int_max[d - 1])
+        seen.append(bool(np.all(~inside | ((layer >= lo) & (layer < hi)) | (rank == world - 1))))
+        comps, norms, grads = ora.query(r, exact_gemv=True)
+        return torch.from_numpy(np.hstack([comps, norms, grads]))
+
+    mine = torch.from_numpy(q_all[rank::world].copy())
+    owner = owner_ranks(mine[:, d - 1], geo.int_min[d - 1], geo.int_max[d - 1], geo.h[d - 1], slabs)
+    out = exchange_and_query(mine, owner, evaluate, 3 + 1 + d)
+    np.save(os.path.join(out_dir, f"out{rank}.npy"), out.numpy())
+    np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array(seen))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_query_routing_world2_gloo(tmp_path):
+    """World-size-2 exchange on CPU: every row reaches the rank owning its t-layer and the results
+    come back in the caller's order, identical to a single-process evaluation."""
+    import torch.multiprocessing as mp
+    from oracle.arb_oracle import OracleInterp
+    g = load_golden("quad_8x7x7x6")
+    field, q_all = g["field"], g["both_q_in"][:, :4].copy()
+    world = 2
+    mp.spawn(_routing_worker, args=(world, _free_port(), field, q_all, str(tmp_path)), nprocs=world, join=True)
+    ref = np.hstack(OracleInterp(field, 4, mode="both").query(q_all.copy(), exact_gemv=True))
+    for rank in range(world):
+        got = np.load(tmp_path / f"out{rank}.npy")
+        assert np.array_equal(got, ref[rank::world], equal_nan=True)
+        assert np.load(tmp_path / f"ok{rank}.npy").all()
