@@ -24,19 +24,20 @@
 
 namespace arb {
 
-template <int D> struct BuildCfg;
-template <> struct BuildCfg<3> {
-    static constexpr int TX = 8, TY = 4, TZ = 4, TT = 1;
-    static constexpr int WARPS = 4, NT_W = 2;      // 8 n-tiles of 8 coefficients
-};
-template <> struct BuildCfg<4> {
-    static constexpr int TX = 8, TY = 2, TZ = 2, TT = 2;
-    static constexpr int WARPS = 8, NT_W = 4;      // 32 n-tiles
-};
+// Tile configurations.  MT = TY*TZ*TT x-rows of 8 cells per CTA; every warp owns NT_W n-tiles (8
+// coefficients each) for all MT m-tiles, so a thread holds MT*NT_W*2 FP64 accumulators.  Smaller
+// tiles trade halo re-reads (served by L2) for more resident warps per SM, which is what keeps the
+// DMMA pipe busy while other CTAs are in their TMA / stencil / store phases.
+struct Cfg3A { static constexpr int D = 3, TX = 8, TY = 4, TZ = 4, TT = 1, WARPS = 4, NT_W = 2, MINB = 3; };
+struct Cfg3B { static constexpr int D = 3, TX = 8, TY = 4, TZ = 2, TT = 1, WARPS = 4, NT_W = 2, MINB = 5; };
+struct Cfg3C { static constexpr int D = 3, TX = 8, TY = 2, TZ = 2, TT = 1, WARPS = 4, NT_W = 2, MINB = 6; };
+struct Cfg4A { static constexpr int D = 4, TX = 8, TY = 2, TZ = 2, TT = 2, WARPS = 8, NT_W = 4, MINB = 1; };
+struct Cfg4B { static constexpr int D = 4, TX = 8, TY = 2, TZ = 2, TT = 1, WARPS = 8, NT_W = 4, MINB = 2; };
+struct Cfg4C { static constexpr int D = 4, TX = 8, TY = 2, TZ = 1, TT = 1, WARPS = 8, NT_W = 4, MINB = 3; };
 
-template <int D>
+template <typename Cfg>
 struct BuildShape {
-    using Cfg = BuildCfg<D>;
+    static constexpr int D = Cfg::D;
     static constexpr int NM = (D == 3) ? 64 : 256;
     static constexpr int NTYPE = 1 << D;
     static constexpr int MT = Cfg::TY * Cfg::TZ * Cfg::TT;          // m-tiles (x-rows of 8 cells)
@@ -59,14 +60,46 @@ struct BuildParams {
     int64_t ntile[4];          // tiles per axis
     int ncomp;
     int quirk;
-    unsigned char mask_of_type[16];
+    unsigned char type_of_mask[16];   // derivative-axis bitmask -> b-vector type index (A.py:118-125 order)
 };
 
-template <int D>
-__global__ void __launch_bounds__(BuildShape<D>::THREADS)
+// Central differences of one grid point over its 3x3x3 neighbourhood, all 8 axis subsets at once:
+// o[mask], bit a of mask set = differentiated along axis a; unit spacing (the rows of D, A.py:132-173).
+// Differences are taken axis by axis (0.5*(g+ - g-)), so a mixed derivative is the reference's
+// +-0.25 / +-0.125 stencil up to the association order of the additions (scaling by 0.5 is exact).
+__device__ __forceinline__ void stencil_cube(const double* g, int sx, int sy, int sz, double (&o)[8]) {
+    double x0[3][3], x1[3][3];
+#pragma unroll
+    for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const double* r = g + (dz - 1) * sz + (dy - 1) * sy;
+            x0[dz][dy] = r[0];
+            x1[dz][dy] = 0.5 * (r[sx] - r[-sx]);
+        }
+    double y00[3], y01[3], y10[3], y11[3];     // [ydiff][xdiff][dz]
+#pragma unroll
+    for (int dz = 0; dz < 3; ++dz) {
+        y00[dz] = x0[dz][1];
+        y01[dz] = x1[dz][1];
+        y10[dz] = 0.5 * (x0[dz][2] - x0[dz][0]);
+        y11[dz] = 0.5 * (x1[dz][2] - x1[dz][0]);
+    }
+    o[0] = y00[1];                         // f
+    o[1] = y01[1];                         // fx
+    o[2] = y10[1];                         // fy
+    o[3] = y11[1];                         // fxy
+    o[4] = 0.5 * (y00[2] - y00[0]);        // fz
+    o[5] = 0.5 * (y01[2] - y01[0]);        // fxz
+    o[6] = 0.5 * (y10[2] - y10[0]);        // fyz
+    o[7] = 0.5 * (y11[2] - y11[0]);        // fxyz
+}
+
+template <typename Cfg>
+__global__ void __launch_bounds__(BuildShape<Cfg>::THREADS, Cfg::MINB)
 build_kernel(const __grid_constant__ CUtensorMap tmap, const BuildParams p) {
-    using S = BuildShape<D>;
-    using Cfg = BuildCfg<D>;
+    using S = BuildShape<Cfg>;
+    constexpr int D = Cfg::D;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* gtile = reinterpret_cast<double*>(smem_raw);            // [GT][GZ][GY][GX]
     double* deriv = gtile + S::GRID_ELEMS;                          // [type][PT][PZ][PY][PXS]
@@ -88,43 +121,46 @@ build_kernel(const __grid_constant__ CUtensorMap tmap, const BuildParams p) {
         if (D == 3) tma_load_4d(gtile, &tmap, &bar, x0, y0, z0, comp);
         else tma_load_5d(gtile, &tmap, &bar, x0, y0, z0, t0, comp);
     }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NKS = S::NM / 4;
+    // first B fragments travel while the tile is in flight
+    double bf[Cfg::NT_W];
+#pragma unroll
+    for (int j = 0; j < Cfg::NT_W; ++j) bf[j] = __ldg(p.bfrag + ((size_t)(warp * Cfg::NT_W + j)) * 32 + lane);
     __syncthreads();
     mbar_wait(&bar, 0);
 
-    // ---- stencil stage -------------------------------------------------------------
+    // ---- stencil stage: one thread per corner point, all 2^D derivative types in registers ----
     // corner point (px,py,pz,pt) of the tile sits at grid-tile coordinate (+1,+1,+1,+1)
-    for (int e = threadIdx.x; e < S::NPOINT * S::NTYPE; e += S::THREADS) {
-        const int type = e / S::NPOINT;
-        int pt_ = e - type * S::NPOINT;
-        const int px = pt_ % S::PX; pt_ /= S::PX;
-        const int py = pt_ % S::PY; pt_ /= S::PY;
-        const int pz = pt_ % S::PZ;
-        const int pt = pt_ / S::PZ;
+    for (int e = threadIdx.x; e < S::NPOINT; e += S::THREADS) {
+        int r = e;
+        const int px = r % S::PX; r /= S::PX;
+        const int py = r % S::PY; r /= S::PY;
+        const int pz = r % S::PZ;
+        const int pt = r / S::PZ;
+        constexpr int SX = 1, SY = S::GX, SZ = S::GX * S::GY, ST = S::GX * S::GY * S::GZ;
         const int centre = (((D == 4 ? (pt + 1) : 0) * S::GZ + (pz + 1)) * S::GY + (py + 1)) * S::GX + (px + 1);
-        const int mask = p.mask_of_type[type];
-        const int strides[4] = {1, S::GX, S::GX * S::GY, S::GX * S::GY * S::GZ};
-        int axes[4], na = 0;
+        double* dst = deriv + ((pt * S::PZ + pz) * S::PY + py) * S::PXS + px;
+        if (D == 3) {
+            double o[8];
+            stencil_cube(gtile + centre, SX, SY, SZ, o);
 #pragma unroll
-        for (int a = 0; a < D; ++a)
-            if ((mask >> a) & 1) axes[na++] = a;
-        double acc = 0.0, w = 1.0;
-        for (int i = 0; i < na; ++i) w *= 0.5;
-        for (int sgn = 0; sgn < (1 << na); ++sgn) {
-            int off = 0;
-            bool neg = false;
-            for (int i = 0; i < na; ++i) {
-                if ((sgn >> i) & 1) off += strides[axes[i]];
-                else { off -= strides[axes[i]]; neg = !neg; }
+            for (int m = 0; m < 8; ++m) dst[p.type_of_mask[m] * S::TYPE_STRIDE] = o[m];
+        } else {
+            double lo[8], mid[8], hi[8];
+            stencil_cube(gtile + centre - ST, SX, SY, SZ, lo);
+            stencil_cube(gtile + centre, SX, SY, SZ, mid);
+            stencil_cube(gtile + centre + ST, SX, SY, SZ, hi);
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                dst[p.type_of_mask[m] * S::TYPE_STRIDE] = mid[m];
+                dst[p.type_of_mask[m | 8] * S::TYPE_STRIDE] = 0.5 * (hi[m] - lo[m]);
             }
-            const double v = gtile[centre + off];
-            acc += neg ? -v : v;
         }
-        deriv[type * S::TYPE_STRIDE + ((pt * S::PZ + pz) * S::PY + py) * S::PXS + px] = acc * w;
     }
     __syncthreads();
 
     // ---- solve stage (DMMA) ----------------------------------------------------------
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cellx = lane >> 2;              // A-fragment row = cell along x
     const int kq = lane & 3;                  // A-fragment column = corner (cx, cy) within a k-step
     double acc[S::MT][Cfg::NT_W][2];
@@ -134,14 +170,14 @@ build_kernel(const __grid_constant__ CUtensorMap tmap, const BuildParams p) {
         for (int j = 0; j < Cfg::NT_W; ++j) acc[m][j][0] = acc[m][j][1] = 0.0;
 
     constexpr int KS_PER_TYPE = S::NTYPE / 4;     // k-steps per derivative type: 2 (3-D), 4 (4-D)
-    constexpr int NKS = S::NM / 4;
     const int lane_off = (kq >> 1) * S::PXS + cellx + (kq & 1);   // (cy, cx) part of the address
 #pragma unroll 1
     for (int ks = 0; ks < NKS; ++ks) {
-        double bf[Cfg::NT_W];
+        double bn[Cfg::NT_W];                     // next k-step's B fragments (L1/L2) overlap this step's DMMAs
+        const int ksn = (ks + 1 < NKS) ? ks + 1 : ks;
 #pragma unroll
         for (int j = 0; j < Cfg::NT_W; ++j)
-            bf[j] = __ldg(p.bfrag + ((size_t)ks * (S::NM / 8) + warp * Cfg::NT_W + j) * 32 + lane);
+            bn[j] = __ldg(p.bfrag + ((size_t)ksn * (S::NM / 8) + warp * Cfg::NT_W + j) * 32 + lane);
         const int type = ks / KS_PER_TYPE;
         const int chi = ks % KS_PER_TYPE;         // high corner bits: cz (+ 2 ct)
         const double* dbase = deriv + type * S::TYPE_STRIDE;
@@ -163,6 +199,8 @@ build_kernel(const __grid_constant__ CUtensorMap tmap, const BuildParams p) {
 #pragma unroll
             for (int j = 0; j < Cfg::NT_W; ++j) dmma_884(acc[m][j][0], acc[m][j][1], a, bf[j]);
         }
+#pragma unroll
+        for (int j = 0; j < Cfg::NT_W; ++j) bf[j] = bn[j];
     }
 
     // ---- store: C fragment row = cell (lane>>2), columns = coefficients 2*(lane&3)+{0,1} --
@@ -235,10 +273,12 @@ static int get_bfrag(int d, const double** out) {
     return 0;
 }
 
-template <int D>
+static int g_build_variant = 0;
+
+template <typename Cfg>
 static int build_impl(const double* grid, int ncomp, const int64_t* n, double* table, int quirk, cudaStream_t st) {
-    using S = BuildShape<D>;
-    using Cfg = BuildCfg<D>;
+    using S = BuildShape<Cfg>;
+    constexpr int D = Cfg::D;
     EncodeTiledFn encode = get_encode_fn();
     if (!encode) { set_error("arb_build_coeffs: cuTensorMapEncodeTiled not available from the driver"); return 2; }
 
@@ -257,7 +297,7 @@ static int build_impl(const double* grid, int ncomp, const int64_t* n, double* t
     for (int a = D; a < 4; ++a) { p.nc[a] = 1; p.ntile[a] = 1; }
     if (ntiles > 0x7fffffffLL) { set_error("arb_build_coeffs: too many tiles (%lld)", (long long)ntiles); return 1; }
     p.table = table; p.ncomp = ncomp; p.quirk = quirk;
-    for (int r = 0; r < (1 << D); ++r) p.mask_of_type[r] = (unsigned char)deriv_mask(D, r);
+    for (int r = 0; r < (1 << D); ++r) p.type_of_mask[deriv_mask(D, r)] = (unsigned char)r;
     { const int frc = get_bfrag(D, &p.bfrag); if (frc) return frc; }
 
     // TMA needs 16-byte global strides: pad odd nx to even in a scratch copy
@@ -300,7 +340,7 @@ static int build_impl(const double* grid, int ncomp, const int64_t* n, double* t
         return 2;
     }
 
-    auto k = build_kernel<D>;
+    auto k = build_kernel<Cfg>;
     ARB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
     dim3 gridDim((unsigned)ntiles, (unsigned)ncomp, 1);
     k<<<gridDim, S::THREADS, S::SMEM, st>>>(tmap, p);
@@ -320,10 +360,27 @@ int arb_build_coeffs(int d, const double* grid, int ncomp, const int64_t n[4], d
                      void* stream) {
     if (!grid || !table || !n) { arb::set_error("arb_build_coeffs: null pointer"); return 1; }
     if (ncomp < 1 || ncomp > 4) { arb::set_error("arb_build_coeffs: ncomp=%d not in 1..4", ncomp); return 1; }
-    if (d == 3) return arb::build_impl<3>(grid, ncomp, n, table, reference_quirk, (cudaStream_t)stream);
-    if (d == 4) return arb::build_impl<4>(grid, ncomp, n, table, reference_quirk, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int v = arb::g_build_variant;
+    // defaults picked on B200 (profiles/r01_build_configs.log): 3-D 8x4x4 tiles, 4-D 8x2x2x1 tiles
+    if (d == 3) {
+        if (v == 1) return arb::build_impl<arb::Cfg3B>(grid, ncomp, n, table, reference_quirk, st);
+        if (v == 2) return arb::build_impl<arb::Cfg3C>(grid, ncomp, n, table, reference_quirk, st);
+        return arb::build_impl<arb::Cfg3A>(grid, ncomp, n, table, reference_quirk, st);
+    }
+    if (d == 4) {
+        if (v == 1) return arb::build_impl<arb::Cfg4A>(grid, ncomp, n, table, reference_quirk, st);
+        if (v == 2) return arb::build_impl<arb::Cfg4C>(grid, ncomp, n, table, reference_quirk, st);
+        return arb::build_impl<arb::Cfg4B>(grid, ncomp, n, table, reference_quirk, st);
+    }
     arb::set_error("arb_build_coeffs: d=%d not in {3,4}", d);
     return 1;
+}
+
+int arb_set_build_variant(int variant) {
+    const int old = arb::g_build_variant;
+    arb::g_build_variant = variant;
+    return old;
 }
 
 int arb_build_coeffs_3d(const double* grid, int ncomp, int64_t nx, int64_t ny, int64_t nz, double* table,

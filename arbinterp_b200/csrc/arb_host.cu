@@ -3,8 +3,11 @@
 // streams.  Pinned (page-locked) caller buffers are copied directly; pageable ones are staged
 // through pinned ring buffers.  The in-place NaN masking of out-of-volume rows (A.py:350-355)
 // is mirrored on the host from a compact list of masked row numbers, so q is never copied back.
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 #include <vector>
+#include <unistd.h>
 #include "arb_common.cuh"
 
 namespace arb {
@@ -17,6 +20,69 @@ int current_query_variant();
 namespace {
 
 constexpr int NSLOT = 3;
+
+// Staging copies between pageable caller memory and the pinned ring are plain memcpy; one thread
+// moves ~10-25 GB/s, less than the PCIe link, so large copies are split over a few helper threads.
+class CopyPool {
+  public:
+    void copy(void* dst, const void* src, size_t bytes) {
+        if (bytes < (4u << 20)) { memcpy(dst, src, bytes); return; }
+        ensure_started();
+        const int parts = (int)workers_.size() + 1;
+        const size_t step = ((bytes / parts) + 4095) & ~(size_t)4095;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            for (int i = 1; i < parts; ++i) {
+                const size_t off = step * i;
+                if (off >= bytes) break;
+                tasks_.push_back({(char*)dst + off, (const char*)src + off, std::min(step, bytes - off)});
+                ++pending_;
+            }
+        }
+        cv_.notify_all();
+        memcpy(dst, src, std::min(step, bytes));
+        std::unique_lock<std::mutex> lk(m_);
+        done_cv_.wait(lk, [&] { return pending_ == 0; });
+    }
+
+  private:
+    struct Task { char* dst; const char* src; size_t n; };
+    void ensure_started() {
+        if (pid_ == getpid() && !workers_.empty()) return;
+        if (pid_ != getpid()) {                    // forked child: the parent's threads do not exist here
+            workers_.clear(); tasks_.clear(); pending_ = 0;   // (already detached)
+        }
+        pid_ = getpid();
+        unsigned hw = std::thread::hardware_concurrency();
+        const int n = hw >= 16 ? 5 : (hw >= 8 ? 3 : 1);
+        for (int i = 0; i < n; ++i) {
+            workers_.emplace_back([this] {
+                for (;;) {
+                    Task t;
+                    {
+                        std::unique_lock<std::mutex> lk(m_);
+                        cv_.wait(lk, [&] { return !tasks_.empty(); });
+                        t = tasks_.back();
+                        tasks_.pop_back();
+                    }
+                    memcpy(t.dst, t.src, t.n);
+                    {
+                        std::lock_guard<std::mutex> lk(m_);
+                        if (--pending_ == 0) done_cv_.notify_all();
+                    }
+                }
+            });
+            workers_.back().detach();
+        }
+    }
+    std::mutex m_;
+    std::condition_variable cv_, done_cv_;
+    std::vector<Task> tasks_;
+    std::vector<std::thread> workers_;
+    int pending_ = 0;
+    pid_t pid_ = 0;
+};
+CopyPool g_pool;
 
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -111,10 +177,10 @@ int retire(Slot& s, const Call& c) {
     if (!s.busy) return 0;
     ARB_CUDA(cudaEventSynchronize(s.done));
     const int64_t n = s.rows, off = s.off;
-    if (c.comps && !c.comps_pinned) memcpy(c.comps + off * 3, s.h_comps, sizeof(double) * n * 3);
-    if (c.norm && !c.norm_pinned) memcpy(c.norm + off, s.h_norm, sizeof(double) * n);
-    if (c.grad && !c.grad_pinned) memcpy(c.grad + off * c.d, s.h_grad, sizeof(double) * n * c.d);
-    if (c.cell && !c.cell_on_device && !c.cell_pinned) memcpy(c.cell + off, s.h_cell, sizeof(int64_t) * n);
+    if (c.comps && !c.comps_pinned) g_pool.copy(c.comps + off * 3, s.h_comps, sizeof(double) * n * 3);
+    if (c.norm && !c.norm_pinned) g_pool.copy(c.norm + off, s.h_norm, sizeof(double) * n);
+    if (c.grad && !c.grad_pinned) g_pool.copy(c.grad + off * c.d, s.h_grad, sizeof(double) * n * c.d);
+    if (c.cell && !c.cell_on_device && !c.cell_pinned) g_pool.copy(c.cell + off, s.h_cell, sizeof(int64_t) * n);
     const unsigned long long cnt = *s.h_count;
     if (cnt) {
         ARB_CUDA(cudaMemcpyAsync(s.h_rows, s.d_rows, sizeof(int64_t) * cnt, cudaMemcpyDeviceToHost, s.stream));
@@ -165,7 +231,7 @@ extern "C" int arb_query_host(const arb_geom* g, const double* table, int mode, 
         if (rc) return rc;
         const int64_t n = (N - off < chunk_rows) ? (N - off) : chunk_rows;
         const double* src = q_host + off * ldq;
-        if (!c.q_pinned) { memcpy(s.h_q, src, sizeof(double) * n * ldq); src = s.h_q; }
+        if (!c.q_pinned) { g_pool.copy(s.h_q, src, sizeof(double) * n * ldq); src = s.h_q; }
         ARB_CUDA(cudaMemcpyAsync(s.d_q, src, sizeof(double) * n * ldq, cudaMemcpyHostToDevice, s.stream));
         ARB_CUDA(cudaMemsetAsync(s.d_count, 0, sizeof(unsigned long long), s.stream));
         rc = query_device(g, table, mode, s.d_q, n, ldq, s.d_comps, s.d_norm, s.d_grad,

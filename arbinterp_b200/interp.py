@@ -19,6 +19,7 @@ Differences a user can observe, all documented in DESIGN.md:
 from __future__ import annotations
 
 import ctypes
+import os
 import sys
 
 import numpy as np
@@ -283,7 +284,8 @@ class _CubicInterpolator:
         with torch.cuda.device(self._device):
             _lib.check(self._lib.arb_query_host(ctypes.byref(self._cgeom), self._table.data_ptr(), self._mode_code,
                                                 work.ctypes.data, n, work.shape[1], self._ptr(comps),
-                                                self._ptr(norm), self._ptr(grad), cells.data_ptr(), 0),
+                                                self._ptr(norm), self._ptr(grad), cells.data_ptr(),
+                                                int(os.environ.get("ARB_HOST_CHUNK_ROWS", "0"))),
                        "arb_query_host")
         if not direct:
             bad = np.isnan(work[:, :d]).any(axis=1) & ~np.isnan(np.asarray(query[:, :d], dtype=np.float64)).any(axis=1)

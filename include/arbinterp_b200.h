@@ -106,6 +106,8 @@ int arb_query_host(const arb_geom* g, const double* table, int mode, double* q_h
 /* Tuning knob for experiments/benchmarks: selects the query-kernel variant
  * (0 = default).  Returns the previous value. */
 int arb_set_query_variant(int variant);
+/* Same for the tile configuration of the build kernel (0 = default). */
+int arb_set_build_variant(int variant);
 
 #ifdef __cplusplus
 }

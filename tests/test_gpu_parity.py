@@ -104,6 +104,26 @@ def test_golden_coefficient_table(name, d, modes):
         assert np.array_equal(np.isnan(got[:, -1]), np.isnan(ref[:, -1]))
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("name,d,modes", CASES)
+def test_build_tile_configurations(name, d, modes, variant, cuda_lib):
+    """Every tile configuration of the build kernel produces the reference's coefficient table."""
+    g = load_golden(name)
+    mode = modes[-1]
+    kw = {} if mode == "scalar" else {"mode": mode}
+    old = cuda_lib.arb_set_build_variant(variant)
+    try:
+        obj = _cls(d)(g["field"].copy(), "quiet", **kw)
+    finally:
+        cuda_lib.arb_set_build_variant(old)
+    for k in "xyzn":
+        key = f"{mode}_alpha{k}"
+        if key in g.files:
+            ref = g[key]
+            assert_parity(getattr(obj, "alpha" + k)[:, :obj.nc], ref[:, :obj.nc], np.abs(ref[:, :-1]).max(), RTOL,
+                          f"{name} alpha{k} build variant {variant}")
+
+
 @pytest.mark.parametrize("variant", [0, 1, 2, 10, 11, 20, 21, 22, 23])
 @pytest.mark.parametrize("name,d,modes", CASES)
 def test_all_kernel_variants(name, d, modes, variant, cuda_lib):
@@ -296,6 +316,26 @@ def test_device_tensor_path_and_pageable_host_path():
     for a, b in zip(host, outs):
         assert np.array_equal(a, b, equal_nan=True)
     assert np.isnan(qq[7]).all() and cells[7] == obj.nc
+
+
+def test_empty_tiny_and_integer_queries():
+    from arbinterp_b200 import tricubic
+    field = _analytic_field3(12, 11, 10)
+    obj = tricubic(field.copy(), "quiet", mode="both")
+    comps, norms, grads = obj.Query(np.empty((0, 3)))
+    assert comps.shape == (0, 3) and norms.shape == (0, 1) and grads.shape == (0, 3)
+    one = obj.Query(np.array([[0.1, 0.05, 0.7]]))                  # a single ROW is still a range query
+    assert one[0].shape == (1, 3) and one[1].shape == (1, 1) and one[2].shape == (1, 3)
+    # integer arrays: work while nothing has to be NaN-masked, ValueError otherwise (numpy cannot store NaN)
+    qi = np.zeros((4, 3), dtype=np.int64)
+    assert np.isfinite(obj.Query(qi)[1]).all()
+    qi[2, 0] = 50
+    with pytest.raises(ValueError):
+        obj.Query(qi)
+    # Fortran-ordered / strided views go through a contiguous copy and still get their NaN rows back
+    big = np.asfortranarray(np.array([[0.1, 0.05, 0.7, 9.0], [7.0, 0.0, 0.5, 9.0]]))
+    obj.Query(big)
+    assert np.isnan(big[1]).all() and not np.isnan(big[0]).any()
 
 
 def test_upper_edge_and_errors(cuda_lib):

@@ -86,6 +86,7 @@ def main():
     ap.add_argument("--grid3", type=int, default=256)
     ap.add_argument("--grid4", default="48,48,48,32")
     ap.add_argument("--queries", type=int, default=1 << 25)
+    ap.add_argument("--build-variants", default="0,1,2")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
@@ -98,14 +99,18 @@ def main():
             obj = cls(rows, "quiet", mode=mode)
             del rows
             torch.cuda.empty_cache()
-            tb = time_build(obj)
             ncomp = obj.table.shape[1]
             cells = obj.nc
             tab_gb = obj.table.numel() * 8 / 1e9
             flops = cells * ncomp * 2.0 * (4 ** d) ** 2
-            print(f"[build] d={d} mode={mode} grid={shape} cells={cells} C={ncomp} table={tab_gb:.2f} GB: "
-                  f"{tb:.2f} ms  -> {cells * ncomp / tb * 1e3:.3e} cell-comps/s, {tab_gb / tb * 1e3:.0f} GB/s written, "
-                  f"{flops / tb / 1e9:.1f} TFLOP/s dense-equivalent", flush=True)
+            for bv in [int(v) for v in args.build_variants.split(",")]:
+                old = obj._lib.arb_set_build_variant(bv)
+                tb = time_build(obj)
+                obj._lib.arb_set_build_variant(old)
+                print(f"[build] d={d} mode={mode} grid={shape} cells={cells} C={ncomp} table={tab_gb:.2f} GB cfg={bv}: "
+                      f"{tb:.2f} ms  -> {cells * ncomp / tb * 1e3:.3e} cell-comps/s, {tab_gb / tb * 1e3:.0f} GB/s written, "
+                      f"{flops / tb / 1e9:.1f} TFLOP/s dense-equivalent", flush=True)
+            obj._build_table()      # leave the default configuration's table in place
             nq = args.queries if (d == 3 and mode == "norm") else args.queries // 2
             g = torch.Generator(device=dev); g.manual_seed(1)
             q = torch.rand(nq, d, generator=g, dtype=torch.float64, device=dev)
