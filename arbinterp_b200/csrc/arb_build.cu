@@ -18,6 +18,7 @@
 // The 4-D reference matrix carries the A.py:860 off-by-one (row 240 of D is zero and rows
 // 241..255 use the stencil centre of the previous corner); it is reproduced in the gather of
 // step 3, where the quadruple-mixed type reads corner c-1 (and 0 for c = 0).
+#include <cstdlib>
 #include <vector>
 #include <mutex>
 #include "arb_common.cuh"
@@ -340,6 +341,12 @@ static int build_impl(const double* grid, int ncomp, const int64_t* n, double* t
         return 2;
     }
 
+    if (getenv("ARB_DEBUG_TMAP")) {
+        const unsigned long long* w = reinterpret_cast<const unsigned long long*>(&tmap);
+        fprintf(stderr, "[arb] tensor map rank %d box %u %u %u:", rank, box[0], box[1], box[2]);
+        for (int i = 0; i < 16; ++i) fprintf(stderr, " %016llx", w[i]);
+        fprintf(stderr, "\n");
+    }
     auto k = build_kernel<Cfg>;
     ARB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
     dim3 gridDim((unsigned)ntiles, (unsigned)ncomp, 1);
