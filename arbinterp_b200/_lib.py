@@ -17,7 +17,8 @@ MODE_VECTOR, MODE_NORM, MODE_BOTH = 0, 1, 2
 EXPORTED_SYMBOLS = (
     "arb_version", "arb_last_error", "arb_get_matrix",
     "arb_build_coeffs", "arb_build_coeffs_3d", "arb_build_coeffs_4d",
-    "arb_query", "arb_query_host", "arb_set_query_variant", "arb_set_build_variant",
+    "arb_query", "arb_query_host", "arb_query_grid", "arb_query_grid_host",
+    "arb_set_query_variant", "arb_set_build_variant",
 )
 
 
@@ -70,6 +71,10 @@ def load():
     lib.arb_query.argtypes = [ctypes.POINTER(ArbGeom), vp, i32, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp]
     lib.arb_query_host.restype = i32
     lib.arb_query_host.argtypes = [ctypes.POINTER(ArbGeom), vp, i32, vp, i64, i64, vp, vp, vp, vp, i64]
+    lib.arb_query_grid.restype = i32
+    lib.arb_query_grid.argtypes = [ctypes.POINTER(ArbGeom), vp, i64, i32, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp]
+    lib.arb_query_grid_host.restype = i32
+    lib.arb_query_grid_host.argtypes = [ctypes.POINTER(ArbGeom), vp, i64, i32, vp, i64, i64, vp, vp, vp, vp, i64]
     lib.arb_set_query_variant.restype = i32
     lib.arb_set_query_variant.argtypes = [i32]
     lib.arb_set_build_variant.restype = i32

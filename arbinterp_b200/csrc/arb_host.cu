@@ -16,6 +16,9 @@ int query_device(const arb_geom* g, const double* table, int mode, double* q, in
                  double* out_comps, double* out_norm, double* out_grad, int64_t* out_cell, int64_t* masked_rows,
                  unsigned long long* masked_count, cudaStream_t st, int variant);
 int current_query_variant();
+int query_grid_device(const arb_geom* g, const double* grid, int64_t pitch_x, int mode, double* q, int64_t N,
+                      int64_t ldq, double* out_comps, double* out_norm, double* out_grad, int64_t* out_cell,
+                      int64_t* masked_rows, unsigned long long* masked_count, cudaStream_t st);
 
 namespace {
 
@@ -82,7 +85,9 @@ class CopyPool {
     int pending_ = 0;
     pid_t pid_ = 0;
 };
-CopyPool g_pool;
+// Never destroyed: the workers block on the condition variable for the life of the process, and
+// glibc's pthread_cond_destroy would wait for them forever in a static destructor at exit.
+CopyPool& g_pool = *new CopyPool;
 
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -198,9 +203,9 @@ int retire(Slot& s, const Call& c) {
 }  // namespace
 }  // namespace arb
 
-extern "C" int arb_query_host(const arb_geom* g, const double* table, int mode, double* q_host, int64_t N, int64_t ldq,
-                              double* out_comps_host, double* out_norm_host, double* out_grad_host,
-                              int64_t* out_cell_host, int64_t chunk_rows) {
+static int query_host_impl(const arb_geom* g, const double* table, int64_t grid_pitch, int mode, double* q_host,
+                           int64_t N, int64_t ldq, double* out_comps_host, double* out_norm_host,
+                           double* out_grad_host, int64_t* out_cell_host, int64_t chunk_rows) {
     using namespace arb;
     if (!g || !q_host || N < 0) { set_error("arb_query_host: bad arguments"); return 1; }
     if (N == 0) return 0;
@@ -234,9 +239,13 @@ extern "C" int arb_query_host(const arb_geom* g, const double* table, int mode, 
         if (!c.q_pinned) { g_pool.copy(s.h_q, src, sizeof(double) * n * ldq); src = s.h_q; }
         ARB_CUDA(cudaMemcpyAsync(s.d_q, src, sizeof(double) * n * ldq, cudaMemcpyHostToDevice, s.stream));
         ARB_CUDA(cudaMemsetAsync(s.d_count, 0, sizeof(unsigned long long), s.stream));
-        rc = query_device(g, table, mode, s.d_q, n, ldq, s.d_comps, s.d_norm, s.d_grad,
-                          c.cell ? (c.cell_on_device ? c.cell + off : s.d_cell) : nullptr,
-                          s.d_rows, s.d_count, s.stream, current_query_variant());
+        int64_t* cell_dst = c.cell ? (c.cell_on_device ? c.cell + off : s.d_cell) : nullptr;
+        if (grid_pitch > 0)
+            rc = query_grid_device(g, table, grid_pitch, mode, s.d_q, n, ldq, s.d_comps, s.d_norm, s.d_grad, cell_dst,
+                                   s.d_rows, s.d_count, s.stream);
+        else
+            rc = query_device(g, table, mode, s.d_q, n, ldq, s.d_comps, s.d_norm, s.d_grad, cell_dst, s.d_rows,
+                              s.d_count, s.stream, current_query_variant());
         if (rc) return rc;
         if (c.comps)
             ARB_CUDA(cudaMemcpyAsync(c.comps_pinned ? c.comps + off * 3 : s.h_comps, s.d_comps, sizeof(double) * n * 3,
@@ -259,4 +268,19 @@ extern "C" int arb_query_host(const arb_geom* g, const double* table, int mode, 
         if (rc) return rc;
     }
     return 0;
+}
+
+extern "C" int arb_query_host(const arb_geom* g, const double* table, int mode, double* q_host, int64_t N, int64_t ldq,
+                              double* out_comps_host, double* out_norm_host, double* out_grad_host,
+                              int64_t* out_cell_host, int64_t chunk_rows) {
+    return query_host_impl(g, table, 0, mode, q_host, N, ldq, out_comps_host, out_norm_host, out_grad_host,
+                           out_cell_host, chunk_rows);
+}
+
+extern "C" int arb_query_grid_host(const arb_geom* g, const double* grid, int64_t pitch_x, int mode, double* q_host,
+                                   int64_t N, int64_t ldq, double* out_comps_host, double* out_norm_host,
+                                   double* out_grad_host, int64_t* out_cell_host, int64_t chunk_rows) {
+    if (pitch_x <= 0) { arb::set_error("arb_query_grid_host: pitch_x must be positive"); return 1; }
+    return query_host_impl(g, grid, pitch_x, mode, q_host, N, ldq, out_comps_host, out_norm_host, out_grad_host,
+                           out_cell_host, chunk_rows);
 }

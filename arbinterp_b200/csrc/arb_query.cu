@@ -52,6 +52,7 @@ int current_query_variant() { return g_query_variant; }
 template <int D>
 struct Located {
     double frac[D];
+    int idx[D];           // per-axis cell index (valid when ok)
     int64_t cell_global;  // total_cells when the row yields NaN
     int64_t cell_local;   // row of `table`
     bool ok;              // evaluate; otherwise every output is NaN
@@ -80,6 +81,7 @@ __device__ __forceinline__ Located<D> locate(const QueryParams& p, int64_t n) {
         ok &= (ii < p.nc[a]);                  // exact upper edge rounding to n-3: NaN
         lin += ii * mult;
         mult *= p.nc[a];
+        L.idx[a] = (int)ii;
         if (a == D - 1) islow = ii;
     }
     L.masked = masked;
@@ -504,6 +506,143 @@ __global__ void __launch_bounds__(128) query_direct_kernel(const QueryParams p) 
     }
 }
 
+
+// ======================================================================================
+// Table-free path: evaluate straight from the 4x4x4 grid neighbourhood
+// ======================================================================================
+// In 3-D the reference matrix is exactly A = M (x) M (x) M with M the 4x4 Catmull-Rom matrix
+// (SURVEY fact 4), so value = sum_kji f[k][j][i] wz_k(w) wy_j(v) wx_i(u) with the Catmull-Rom
+// weights w(t) = M^T [1,t,t^2,t^3] -- no coefficient table, 64x less memory, no build.  A lane owns
+// (query, component) and asks the TMA unit for the neighbourhood as a tiled box of the grid tensor
+// (cp.async.bulk.tensor, UTMALDG).  fp64 boxes must start on a 16-byte boundary (an odd x start traps
+// with "illegal instruction", tools/micro/tma_dbg.cu), so the box is 6x4x4 starting at the even
+// x <= ix and the x weights are placed at offset ix&1 inside a 6-vector whose other entries are 0.
+// Slots are 768 B apart (TMA needs 128-byte alignment), which would put every lane on the same
+// bank; rows are therefore visited in a per-lane rotated order (j by lane&3, k by (lane>>2)&1) with
+// the y/z weight vectors pre-rotated to match, which makes the LDS.128 stream conflict-free.
+struct GridQueryParams {
+    QueryParams q;
+};
+
+__device__ __forceinline__ void catmull_rom(double t, double (&w)[4], double (&dw)[4]) {
+    const double t2 = t * t, t3 = t2 * t;
+    w[0] = fma(-0.5, t3, fma(1.0, t2, -0.5 * t));
+    w[1] = fma(1.5, t3, fma(-2.5, t2, 1.0));
+    w[2] = fma(-1.5, t3, fma(2.0, t2, 0.5 * t));
+    w[3] = fma(0.5, t3, -0.5 * t2);
+    dw[0] = fma(-1.5, t2, fma(2.0, t, -0.5));
+    dw[1] = fma(4.5, t2, -5.0 * t);
+    dw[2] = fma(-4.5, t2, fma(4.0, t, 0.5));
+    dw[3] = fma(1.5, t2, -t);
+}
+
+template <int MODE, int THREADS>
+__global__ void __launch_bounds__(THREADS) query_grid_kernel(const __grid_constant__ CUtensorMap tmap, const QueryParams p) {
+    constexpr int D = 3;
+    constexpr int C = MODE == 0 ? 3 : (MODE == 1 ? 1 : 4);
+    constexpr uint32_t BYTES = 6 * 4 * 4 * 8;     // 768
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bars[THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint64_t* bar = &bars[wid];
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    const int64_t warp_global = ((int64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * THREADS) >> 5;
+    const int64_t nbatch = (p.N + 31) / 32;
+    const int64_t nitem = nbatch * C;
+    const int rj = lane & 3, rk = (lane >> 2) & 1;     // row rotation of this lane
+    unsigned char* slot = smem + (size_t)threadIdx.x * BYTES;
+    uint32_t phase = 0;
+    for (int64_t item = warp_global; item < nitem; item += nwarps) {
+        const int64_t batch = item / C;
+        const int comp = (int)(item - batch * C);
+        const int64_t n = batch * 32 + lane;
+        Located<D> L;
+        L.ok = false; L.masked = false; L.cell_global = 0; L.cell_local = 0;
+        L.idx[0] = L.idx[1] = L.idx[2] = 0;
+        if (n < p.N) L = locate<D>(p, n);
+        const unsigned fmask = __ballot_sync(0xffffffffu, L.ok);
+        if (lane == 0) mbar_expect_tx(bar, (uint32_t)__popc(fmask) * BYTES);
+        __syncwarp();
+        const int off = L.idx[0] & 1;
+        if (L.ok) tma_load_4d(slot, &tmap, bar, L.idx[0] - off, L.idx[1], L.idx[2], comp);
+        if (comp == 0 && n < p.N) {
+            if (p.out_cell) p.out_cell[n] = L.cell_global;
+            if (L.masked) mask_row_in_place(p, n);
+        }
+        // weights while the box is in flight
+        double wx[4], dwx[4], wy[4], dwy[4], wz[4], dwz[4];
+        catmull_rom(L.frac[0], wx, dwx);
+        catmull_rom(L.frac[1], wy, dwy);
+        catmull_rom(L.frac[2], wz, dwz);
+        double wx6[6], dwx6[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const int s = i - off;     // 0..3 inside the neighbourhood
+            wx6[i] = (s == 0) ? wx[0] : (s == 1) ? wx[1] : (s == 2) ? wx[2] : (s == 3) ? wx[3] : 0.0;
+            dwx6[i] = (s == 0) ? dwx[0] : (s == 1) ? dwx[1] : (s == 2) ? dwx[2] : (s == 3) ? dwx[3] : 0.0;
+        }
+        double wyr[4], dwyr[4], wzr[4], dwzr[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int jj = (j + rj) & 3, kk = (j + rk) & 3;
+            wyr[j] = jj == 0 ? wy[0] : jj == 1 ? wy[1] : jj == 2 ? wy[2] : wy[3];
+            dwyr[j] = jj == 0 ? dwy[0] : jj == 1 ? dwy[1] : jj == 2 ? dwy[2] : dwy[3];
+            wzr[j] = kk == 0 ? wz[0] : kk == 1 ? wz[1] : kk == 2 ? wz[2] : wz[3];
+            dwzr[j] = kk == 0 ? dwz[0] : kk == 1 ? dwz[1] : kk == 2 ? dwz[2] : dwz[3];
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        const bool grad_comp = (MODE == 1) || (MODE == 2 && comp == 3);     // warp-uniform
+        double val = 0.0, gx = 0.0, gy = 0.0, gz = 0.0;
+        if (L.ok) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                double P = 0.0, Px = 0.0, Py = 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int row = 4 * ((k + rk) & 3) + ((j + rj) & 3);
+                    const double2* r = reinterpret_cast<const double2*>(slot + row * 48);
+                    const double2 a = r[0], b = r[1], c = r[2];
+                    double pp = a.x * wx6[0];
+                    pp = fma(a.y, wx6[1], pp); pp = fma(b.x, wx6[2], pp); pp = fma(b.y, wx6[3], pp);
+                    pp = fma(c.x, wx6[4], pp); pp = fma(c.y, wx6[5], pp);
+                    P = fma(wyr[j], pp, P);
+                    if (grad_comp) {
+                        double dp = a.x * dwx6[0];
+                        dp = fma(a.y, dwx6[1], dp); dp = fma(b.x, dwx6[2], dp); dp = fma(b.y, dwx6[3], dp);
+                        dp = fma(c.x, dwx6[4], dp); dp = fma(c.y, dwx6[5], dp);
+                        Px = fma(wyr[j], dp, Px);
+                        Py = fma(dwyr[j], pp, Py);
+                    }
+                }
+                val = fma(wzr[k], P, val);
+                if (grad_comp) {
+                    gx = fma(wzr[k], Px, gx);
+                    gy = fma(wzr[k], Py, gy);
+                    gz = fma(dwzr[k], P, gz);
+                }
+            }
+        }
+        if (n < p.N) {
+            const double nan = qnan();
+            if (!grad_comp) {
+                p.out_comps[n * 3 + comp] = L.ok ? val : nan;
+            } else {
+                p.out_norm[n] = L.ok ? val : nan;
+                p.out_grad[n * 3 + 0] = L.ok ? __ddiv_rn(gx, p.h[0]) : nan;
+                p.out_grad[n * 3 + 1] = L.ok ? __ddiv_rn(gy, p.h[1]) : nan;
+                p.out_grad[n * 3 + 2] = L.ok ? __ddiv_rn(gz, p.h[2]) : nan;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // --------------------------------------------------------------------------------------
 // launchers
 // --------------------------------------------------------------------------------------
@@ -579,40 +718,49 @@ static int dispatch_variant(const QueryParams& p, cudaStream_t st, int variant) 
     }
 }
 
-int query_device(const arb_geom* g, const double* table, int mode, double* q, int64_t N, int64_t ldq,
-                 double* out_comps, double* out_norm, double* out_grad, int64_t* out_cell, int64_t* masked_rows,
-                 unsigned long long* masked_count, cudaStream_t st, int variant) {
-    if (!g || (g->d != 3 && g->d != 4)) { set_error("arb_query: geometry missing or d not in {3,4}"); return 1; }
+static int fill_params(const char* who, const arb_geom* g, bool need_table, const double* table, int mode, double* q,
+                       int64_t N, int64_t ldq, double* out_comps, double* out_norm, double* out_grad, int64_t* out_cell,
+                       int64_t* masked_rows, unsigned long long* masked_count, QueryParams& p) {
+    if (!g || (g->d != 3 && g->d != 4)) { set_error("%s: geometry missing or d not in {3,4}", who); return 1; }
     const int need_c = mode == ARB_MODE_VECTOR ? 3 : (mode == ARB_MODE_NORM ? 1 : (mode == ARB_MODE_BOTH ? 4 : -1));
     if (need_c < 0 || g->ncomp != need_c) {
-        set_error("arb_query: mode %d needs a table with %d components, geometry says %d", mode, need_c, g->ncomp);
+        set_error("%s: mode %d needs %d components, geometry says %d", who, mode, need_c, g->ncomp);
         return 1;
     }
-    if (N < 0 || ldq < g->d) { set_error("arb_query: need N >= 0 and ldq >= d (N=%lld ldq=%lld)", (long long)N, (long long)ldq); return 1; }
-    if (N == 0) return 0;
-    if (!table || !q) { set_error("arb_query: null table or query pointer"); return 1; }
+    if (N < 0 || ldq < g->d) { set_error("%s: need N >= 0 and ldq >= d (N=%lld ldq=%lld)", who, (long long)N, (long long)ldq); return 1; }
+    if (N == 0) return -1;
+    if ((need_table && !table) || !q) { set_error("%s: null table/grid or query pointer", who); return 1; }
     if ((mode != ARB_MODE_NORM && !out_comps) || (mode != ARB_MODE_VECTOR && (!out_norm || !out_grad))) {
-        set_error("arb_query: output pointer missing for mode %d", mode);
+        set_error("%s: output pointer missing for mode %d", who, mode);
         return 1;
     }
-    if (masked_rows && !masked_count) { set_error("arb_query: masked_rows given without masked_count"); return 1; }
-    QueryParams p;
+    if (masked_rows && !masked_count) { set_error("%s: masked_rows given without masked_count", who); return 1; }
     memset(&p, 0, sizeof(p));
     p.table = table; p.q = q; p.N = N; p.ldq = ldq;
     p.out_comps = out_comps; p.out_norm = out_norm; p.out_grad = out_grad; p.out_cell = out_cell;
     p.masked_rows = masked_rows; p.masked_count = masked_count;
     p.total_cells = 1; p.layer_cells = 1;
     for (int a = 0; a < g->d; ++a) {
-        if (g->ncell[a] < 1 || !(g->h[a] > 0.0)) { set_error("arb_query: axis %d has ncell=%lld h=%g", a, (long long)g->ncell[a], g->h[a]); return 1; }
+        if (g->ncell[a] < 1 || !(g->h[a] > 0.0)) { set_error("%s: axis %d has ncell=%lld h=%g", who, a, (long long)g->ncell[a], g->h[a]); return 1; }
         p.mn[a] = g->int_min[a]; p.mx[a] = g->int_max[a]; p.h[a] = g->h[a]; p.nc[a] = g->ncell[a];
         p.total_cells *= g->ncell[a];
         if (a < g->d - 1) p.layer_cells *= g->ncell[a];
     }
     p.slab_lo = g->slab_lo; p.slab_hi = g->slab_hi;
     if (p.slab_lo < 0 || p.slab_hi > g->ncell[g->d - 1] || p.slab_lo >= p.slab_hi) {
-        set_error("arb_query: bad slab [%lld,%lld)", (long long)p.slab_lo, (long long)p.slab_hi);
+        set_error("%s: bad slab [%lld,%lld)", who, (long long)p.slab_lo, (long long)p.slab_hi);
         return 1;
     }
+    return 0;
+}
+
+int query_device(const arb_geom* g, const double* table, int mode, double* q, int64_t N, int64_t ldq,
+                 double* out_comps, double* out_norm, double* out_grad, int64_t* out_cell, int64_t* masked_rows,
+                 unsigned long long* masked_count, cudaStream_t st, int variant) {
+    QueryParams p;
+    const int rc = fill_params("arb_query", g, true, table, mode, q, N, ldq, out_comps, out_norm, out_grad, out_cell,
+                               masked_rows, masked_count, p);
+    if (rc) return rc < 0 ? 0 : rc;
     if (g->d == 3) {
         if (mode == ARB_MODE_VECTOR) return dispatch_variant<3, 3, 0>(p, st, variant);
         if (mode == ARB_MODE_NORM) return dispatch_variant<3, 1, 1>(p, st, variant);
@@ -623,6 +771,62 @@ int query_device(const arb_geom* g, const double* table, int mode, double* q, in
     return dispatch_variant<4, 4, 2>(p, st, variant);
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+template <int MODE>
+static int launch_grid(const CUtensorMap& tm, const QueryParams& p, cudaStream_t st) {
+    constexpr int C = MODE == 0 ? 3 : (MODE == 1 ? 1 : 4);
+    constexpr int THREADS = 128;
+    const size_t smem = (size_t)THREADS * 768;
+    auto k = query_grid_kernel<MODE, THREADS>;
+    ARB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t items = ((p.N + 31) / 32) * C;
+    const int grid = persistent_grid(k, THREADS, smem, (items + THREADS / 32 - 1) / (THREADS / 32));
+    k<<<grid, THREADS, smem, st>>>(tm, p);
+    return check_cuda(cudaGetLastError(), "query_grid_kernel launch");
+}
+
+int query_grid_device(const arb_geom* g, const double* grid, int64_t pitch_x, int mode, double* q, int64_t N,
+                      int64_t ldq, double* out_comps, double* out_norm, double* out_grad, int64_t* out_cell,
+                      int64_t* masked_rows, unsigned long long* masked_count, cudaStream_t st) {
+    QueryParams p;
+    const int rc = fill_params("arb_query_grid", g, true, grid, mode, q, N, ldq, out_comps, out_norm, out_grad,
+                               out_cell, masked_rows, masked_count, p);
+    if (rc) return rc < 0 ? 0 : rc;
+    if (g->d != 3) { set_error("arb_query_grid: only the tricubic (d=3) path has a table-free form"); return 1; }
+    if (g->slab_lo != 0 || g->slab_hi != g->ncell[2]) { set_error("arb_query_grid: slabs are not supported"); return 1; }
+    const int64_t nx = g->ncell[0] + 3, ny = g->ncell[1] + 3, nz = g->ncell[2] + 3;
+    if (pitch_x < nx || (pitch_x & 1) || (reinterpret_cast<uintptr_t>(grid) & 15)) {
+        set_error("arb_query_grid: row pitch must be even and >= nx, grid 16-byte aligned (pitch=%lld nx=%lld)",
+                  (long long)pitch_x, (long long)nx);
+        return 1;
+    }
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess) {
+            set_error("arb_query_grid: cuTensorMapEncodeTiled not available from the driver");
+            return 2;
+        }
+        encode = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    CUtensorMap tm;
+    cuuint64_t gdim[4] = {(cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)nz, (cuuint64_t)g->ncomp};
+    cuuint64_t gstr[3] = {(cuuint64_t)pitch_x * 8, (cuuint64_t)pitch_x * ny * 8, (cuuint64_t)pitch_x * ny * nz * 8};
+    cuuint32_t box[4] = {6, 4, 4, 1}, estr[4] = {1, 1, 1, 1};
+    const CUresult cr = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double*>(grid), gdim, gstr, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { set_error("arb_query_grid: cuTensorMapEncodeTiled failed with CUresult %d", (int)cr); return 2; }
+    if (mode == ARB_MODE_VECTOR) return launch_grid<0>(tm, p, st);
+    if (mode == ARB_MODE_NORM) return launch_grid<1>(tm, p, st);
+    return launch_grid<2>(tm, p, st);
+}
+
 }  // namespace arb
 
 extern "C" {
@@ -631,6 +835,13 @@ int arb_set_query_variant(int variant) {
     const int old = arb::g_query_variant;
     arb::g_query_variant = variant;
     return old;
+}
+
+int arb_query_grid(const arb_geom* g, const double* grid, int64_t pitch_x, int mode, double* q, int64_t N, int64_t ldq,
+                   double* out_comps, double* out_norm, double* out_grad, int64_t* out_cell, int64_t* masked_rows,
+                   unsigned long long* masked_count, void* stream) {
+    return arb::query_grid_device(g, grid, pitch_x, mode, q, N, ldq, out_comps, out_norm, out_grad, out_cell,
+                                  masked_rows, masked_count, (cudaStream_t)stream);
 }
 
 int arb_query(const arb_geom* g, const double* table, int mode, double* q, int64_t N, int64_t ldq, double* out_comps,

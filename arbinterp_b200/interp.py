@@ -14,7 +14,10 @@ Differences a user can observe, all documented in DESIGN.md:
   * a coordinate exactly on the upper edge whose per-axis index rounds to n-3 returns NaN
     (the reference wraps into a neighbouring cell or raises, SURVEY 7.2);
   * ``quiet=True`` is accepted as a keyword as well as the positional string ``'quiet'``;
-  * torch CUDA tensors are accepted as queries and then returned as CUDA tensors.
+  * torch CUDA tensors are accepted as queries and then returned as CUDA tensors;
+  * ``tricubic(..., table=False)`` keeps no coefficient table at all and evaluates every query from
+    its 4x4x4 grid neighbourhood (for fields that change often; CHANGELOG.md:9 of the reference);
+  * ``save(path)`` / ``load(path)`` persist the coefficient table.
 """
 from __future__ import annotations
 
@@ -102,7 +105,42 @@ class _CubicInterpolator:
         self._planes = comp.contiguous()
         del planes
 
+        self._set_geometry_attributes()
+
+        nslow = geo.ncell[d - 1]
+        lo, hi = (0, nslow) if slab is None else (int(slab[0]), int(slab[1]))
+        if not (0 <= lo < hi <= nslow):
+            raise ValueError(f"slab {slab} outside the {nslow} cell layers of the slowest axis")
+        self._slab = (lo, hi)
+        self._table_free = kwargs.get("table", True) is False
+        if self._table_free:
+            if d != 3 or (lo, hi) != (0, nslow):
+                raise ValueError("table=False is available for unsharded tricubic interpolators only "
+                                 "(the 4-D reference matrix is not a Kronecker product, A.py:860)")
+            self._table = None
+            nx = geo.npts[0]
+            self._pitch = nx + (nx & 1)                           # TMA needs 16-byte row strides
+            if self._pitch != nx:
+                self._planes = torch.nn.functional.pad(self._planes, (0, 1)).contiguous()
+            self._make_cgeom()
+        else:
+            self._build_table()
+        self._last_cells = None
+        self.queryInd = None
+
+        self._bind_mode()
+
+    def _bind_mode(self):
+        # bind the mode-specific entry points like the reference does (A.py:27-30, 38-41, ...)
+        mode = self._mode
+        self.Query = {"vector": self.Query1, "norm": self.Query2, "both": self.Query3}[mode]
+        self.sQuery = {"vector": self.sQuery1, "norm": self.sQuery2, "both": self.sQuery3}[mode]
+        self.rQuery = {"vector": self.rQuery1, "norm": self.rQuery2, "both": self.rQuery3}[mode]
+        self.calcCoefficients = self._calc_coefficients_noop
+
+    def _set_geometry_attributes(self):
         # public geometry attributes (A.py:545-568 / 1288-1320)
+        d, geo = self._d, self._geo
         if d == 3:
             self.nPos = np.array(geo.ncell)
         else:
@@ -114,20 +152,90 @@ class _CubicInterpolator:
         self.nc = geo.nc
         self.alphamask = np.ones((self.nc + 1, 1))              # every cell is built (A.py:21-22)
 
-        nslow = geo.ncell[d - 1]
-        lo, hi = (0, nslow) if slab is None else (int(slab[0]), int(slab[1]))
-        if not (0 <= lo < hi <= nslow):
-            raise ValueError(f"slab {slab} outside the {nslow} cell layers of the slowest axis")
-        self._slab = (lo, hi)
-        self._build_table()
+    def _make_cgeom(self):
+        d, geo = self._d, self._geo
+        g = _lib.ArbGeom()
+        g.d, g.ncomp = d, (self._planes.shape[0] if self._table is None else self._table.shape[1])
+        for a in range(4):
+            g.ncell[a] = geo.ncell[a] if a < d else 1
+            g.int_min[a] = geo.int_min[a] if a < d else 0.0
+            g.int_max[a] = geo.int_max[a] if a < d else 0.0
+            g.h[a] = geo.h[a] if a < d else 1.0
+        g.slab_lo, g.slab_hi = self._slab
+        self._cgeom = g
+
+    # ------------------------------------------------------------------ persistence (CHANGELOG.md:9 "save these coefficients to a file")
+    _MAGIC = b"ARBTAB01"
+
+    def save(self, path, chunk_bytes=256 << 20):
+        """Write the coefficient table and everything needed to query it (geometry, mode, slab) to
+        ``path``: 8-byte magic, uint64 header length, JSON header, zero padding to 4096, then the
+        raw little-endian float64 table ``[ncell_local+1][C][4^d]``.  The field itself is not stored."""
+        import json
+        if self._table is None:
+            raise ValueError("a table=False interpolator has no coefficient table to save")
+        geo = self._geo
+        header = {"format": 1, "d": self._d, "mode": self._mode, "scalar_input": self._scalar_input,
+                  "explicit_vector": self._explicit_vector, "reference_quirk": self._reference_quirk,
+                  "npts": list(geo.npts), "h": [float(v).hex() for v in geo.h],
+                  "int_min": [float(v).hex() for v in geo.int_min], "int_max": [float(v).hex() for v in geo.int_max],
+                  "slab": list(self._slab), "table_shape": list(self._table.shape), "dtype": "<f8"}
+        blob = json.dumps(header).encode("utf-8")
+        flat = self._table.reshape(-1)
+        step = max(1, chunk_bytes // 8)
+        with open(path, "wb") as f:
+            f.write(self._MAGIC)
+            f.write(np.uint64(len(blob)).tobytes())
+            f.write(blob)
+            f.write(b"\0" * (-(16 + len(blob)) % 4096))
+            for lo in range(0, flat.numel(), step):
+                flat[lo:lo + step].cpu().numpy().tofile(f)
+
+    @classmethod
+    def load(cls, path, device=None, chunk_bytes=256 << 20):
+        """Rebuild an interpolator from a file written by :meth:`save` -- no ingest, no coefficient build."""
+        import json
+        from .ingest import Geometry
+        with open(path, "rb") as f:
+            if f.read(8) != cls._MAGIC:
+                raise ValueError(f"{path}: not an arbinterp_b200 coefficient file")
+            hlen = int(np.frombuffer(f.read(8), dtype=np.uint64)[0])
+            header = json.loads(f.read(hlen).decode("utf-8"))
+            if header["d"] != cls._d:
+                raise ValueError(f"{path} holds a {header['d']}-D table, {cls.__name__} is {cls._d}-D")
+            f.seek((16 + hlen + 4095) // 4096 * 4096)
+            self = cls.__new__(cls)
+            self.eps = 10 * np.finfo(float).eps
+            self._device = _cuda_device(device)
+            self._lib = _lib.load()
+            self._mode = header["mode"]
+            self._mode_code = {"vector": _lib.MODE_VECTOR, "norm": _lib.MODE_NORM, "both": _lib.MODE_BOTH}[self._mode]
+            self._scalar_input = header["scalar_input"]
+            self._explicit_vector = header["explicit_vector"]
+            self._reference_quirk = header["reference_quirk"]
+            npts = header["npts"]
+            unhex = lambda xs: [float.fromhex(v) for v in xs]
+            self._geo = Geometry(d=cls._d, npts=npts, ncell=[n - 3 for n in npts], h=unhex(header["h"]),
+                                 int_min=unhex(header["int_min"]), int_max=unhex(header["int_max"]))
+            self._slab = tuple(header["slab"])
+            self._planes = None
+            self._table_free = False
+            shape = tuple(header["table_shape"])
+            self._table = torch.empty(shape, dtype=torch.float64, device=self._device)
+            flat = self._table.reshape(-1)
+            step = max(1, chunk_bytes // 8)
+            for lo in range(0, flat.numel(), step):
+                n = min(step, flat.numel() - lo)
+                buf = np.fromfile(f, dtype="<f8", count=n)
+                if buf.size != n:
+                    raise ValueError(f"{path}: truncated table")
+                flat[lo:lo + n].copy_(torch.from_numpy(buf))
+        self._set_geometry_attributes()
+        self._make_cgeom()
         self._last_cells = None
         self.queryInd = None
-
-        # bind the mode-specific entry points like the reference does (A.py:27-30, 38-41, ...)
-        self.Query = {"vector": self.Query1, "norm": self.Query2, "both": self.Query3}[mode]
-        self.sQuery = {"vector": self.sQuery1, "norm": self.sQuery2, "both": self.sQuery3}[mode]
-        self.rQuery = {"vector": self.rQuery1, "norm": self.rQuery2, "both": self.rQuery3}[mode]
-        self.calcCoefficients = self._calc_coefficients_noop
+        self._bind_mode()
+        return self
 
     def _build_table(self):
         d, geo = self._d, self._geo
@@ -148,20 +256,14 @@ class _CubicInterpolator:
             # construction is one-off: finish it here so that queries issued from any stream
             # (arb_query_host uses its own copy/compute streams) see a complete table
             torch.cuda.current_stream(self._device).synchronize()
-        g = _lib.ArbGeom()
-        g.d, g.ncomp = d, ncomp
-        for a in range(4):
-            g.ncell[a] = geo.ncell[a] if a < d else 1
-            g.int_min[a] = geo.int_min[a] if a < d else 0.0
-            g.int_max[a] = geo.int_max[a] if a < d else 0.0
-            g.h[a] = geo.h[a] if a < d else 1.0
-        g.slab_lo, g.slab_hi = lo, hi
-        self._cgeom = g
+        self._make_cgeom()
 
     # ------------------------------------------------------------------ lazily materialised reference attributes
     @property
     def table(self) -> torch.Tensor:
         """Device coefficient table ``[ncell_local+1][C][4^d]`` (cell-major; last row NaN)."""
+        if self._table is None:
+            raise AttributeError("this interpolator was built with table=False and keeps no coefficient table")
         return self._table
 
     @property
@@ -172,6 +274,8 @@ class _CubicInterpolator:
     @property
     def inputfield(self):
         planes = self._planes
+        if planes is None:
+            raise AttributeError("inputfield is unavailable after load(): a coefficient file does not store the field")
         if self._mode in ("norm", "both") and not self._scalar_input:
             raise AttributeError("inputfield is not kept in 'norm'/'both' mode; only the interpolated planes are")
         return sorted_field(planes, self._geo).cpu().numpy()
@@ -191,6 +295,8 @@ class _CubicInterpolator:
         names = self._component_names()
         if name not in names:
             raise AttributeError(f"alpha{name} does not exist in mode '{self._mode}'")
+        if self._table is None:
+            raise AttributeError("alpha* does not exist for a table=False interpolator")
         if self._slab != (0, self._geo.ncell[self._d - 1]):
             raise AttributeError("alpha* views are only available for an unsharded table")
         col = self._table[:, names.index(name), :].T.contiguous().cpu().numpy()   # (4^d, nc+1), like A.py:31
@@ -207,10 +313,15 @@ class _CubicInterpolator:
     alphan = property(lambda self: self._alpha("n"))
 
     def _plane(self, name):
+        if self._planes is None:
+            raise AttributeError("the field planes are not stored in a coefficient file; B* is unavailable after load()")
         names = self._component_names()
         if name not in names:
             raise AttributeError(f"B{name} does not exist in mode '{self._mode}'")
-        return self._planes[names.index(name)].reshape(-1).cpu().numpy()
+        plane = self._planes[names.index(name)]
+        if getattr(self, "_table_free", False):
+            plane = plane[..., :self._geo.npts[0]]
+        return plane.reshape(-1).cpu().numpy()
 
     Bx = property(lambda self: self._plane("x"))
     By = property(lambda self: self._plane("y"))
@@ -261,9 +372,15 @@ class _CubicInterpolator:
         cells = torch.empty(n, dtype=torch.int64, device=self._device)
         with torch.cuda.device(self._device):
             stream = torch.cuda.current_stream(self._device).cuda_stream
-            _lib.check(self._lib.arb_query(ctypes.byref(self._cgeom), self._table.data_ptr(), self._mode_code,
-                                           work.data_ptr(), n, work.shape[1], self._ptr(comps), self._ptr(norm),
-                                           self._ptr(grad), cells.data_ptr(), None, None, stream), "arb_query")
+            if self._table is None:
+                _lib.check(self._lib.arb_query_grid(ctypes.byref(self._cgeom), self._planes.data_ptr(), self._pitch,
+                                                    self._mode_code, work.data_ptr(), n, work.shape[1],
+                                                    self._ptr(comps), self._ptr(norm), self._ptr(grad),
+                                                    cells.data_ptr(), None, None, stream), "arb_query_grid")
+            else:
+                _lib.check(self._lib.arb_query(ctypes.byref(self._cgeom), self._table.data_ptr(), self._mode_code,
+                                               work.data_ptr(), n, work.shape[1], self._ptr(comps), self._ptr(norm),
+                                               self._ptr(grad), cells.data_ptr(), None, None, stream), "arb_query")
         if work is not q:                                        # mirror the in-place NaN rows (A.py:350-355)
             bad = torch.isnan(work[:, :d]).any(dim=1) & ~torch.isnan(q[:, :d].to(self._device)).any(dim=1)
             if bool(bad.any()):
@@ -282,11 +399,17 @@ class _CubicInterpolator:
         comps, norm, grad = self._outputs(n, pinned=True)
         cells = torch.empty(n, dtype=torch.int64, device=self._device)   # stays in HBM; read back lazily
         with torch.cuda.device(self._device):
-            _lib.check(self._lib.arb_query_host(ctypes.byref(self._cgeom), self._table.data_ptr(), self._mode_code,
-                                                work.ctypes.data, n, work.shape[1], self._ptr(comps),
-                                                self._ptr(norm), self._ptr(grad), cells.data_ptr(),
-                                                int(os.environ.get("ARB_HOST_CHUNK_ROWS", "0"))),
-                       "arb_query_host")
+            chunk = int(os.environ.get("ARB_HOST_CHUNK_ROWS", "0"))
+            if self._table is None:
+                _lib.check(self._lib.arb_query_grid_host(ctypes.byref(self._cgeom), self._planes.data_ptr(), self._pitch,
+                                                         self._mode_code, work.ctypes.data, n, work.shape[1],
+                                                         self._ptr(comps), self._ptr(norm), self._ptr(grad),
+                                                         cells.data_ptr(), chunk), "arb_query_grid_host")
+            else:
+                _lib.check(self._lib.arb_query_host(ctypes.byref(self._cgeom), self._table.data_ptr(), self._mode_code,
+                                                    work.ctypes.data, n, work.shape[1], self._ptr(comps),
+                                                    self._ptr(norm), self._ptr(grad), cells.data_ptr(), chunk),
+                           "arb_query_host")
         if not direct:
             bad = np.isnan(work[:, :d]).any(axis=1) & ~np.isnan(np.asarray(query[:, :d], dtype=np.float64)).any(axis=1)
             if bad.any():

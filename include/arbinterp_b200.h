@@ -103,6 +103,19 @@ int arb_query_host(const arb_geom* g, const double* table, int mode, double* q_h
                    double* out_comps_host, double* out_norm_host, double* out_grad_host,
                    int64_t* out_cell_host, int64_t chunk_rows);
 
+/* Table-free tricubic query (d = 3 only): evaluates straight from the 4x4x4 grid neighbourhood
+ * -- no coefficient table, no build, 64x less memory; about half the throughput of arb_query.
+ * It is the reference's lazy path taken to its limit (A.py:376-377 computes a cell's coefficients
+ * on first touch; here nothing is ever stored) and relies on A = M(x)M(x)M being exact in 3-D.
+ *   grid    : device [C][nz][ny][pitch_x] float64, nx = ncell[0]+3 etc.; pitch_x even, >= nx.
+ * Other arguments as arb_query / arb_query_host. */
+int arb_query_grid(const arb_geom* g, const double* grid, int64_t pitch_x, int mode, double* q, int64_t N,
+                   int64_t ldq, double* out_comps, double* out_norm, double* out_grad, int64_t* out_cell,
+                   int64_t* masked_rows, unsigned long long* masked_count, void* stream);
+int arb_query_grid_host(const arb_geom* g, const double* grid, int64_t pitch_x, int mode, double* q_host, int64_t N,
+                        int64_t ldq, double* out_comps_host, double* out_norm_host, double* out_grad_host,
+                        int64_t* out_cell_host, int64_t chunk_rows);
+
 /* Tuning knob for experiments/benchmarks: selects the query-kernel variant
  * (0 = default).  Returns the previous value. */
 int arb_set_query_variant(int variant);

@@ -318,6 +318,73 @@ def test_device_tensor_path_and_pageable_host_path():
     assert np.isnan(qq[7]).all() and cells[7] == obj.nc
 
 
+@pytest.mark.parametrize("name,d,mode", [("tri_12x10x9", 3, "both"), ("quad_8x7x7x6", 4, "norm")])
+def test_save_and_load_coefficients(name, d, mode, tmp_path):
+    """Coefficient-table persistence (reference CHANGELOG.md:9 lists it as future work): a loaded
+    interpolator answers bit-identically without the field, the ingest or the build."""
+    g = load_golden(name)
+    obj = _cls(d)(g["field"].copy(), "quiet", mode=mode)
+    q = g[mode + "_q_in"].copy()
+    ref = obj.Query(q.copy())
+    path = tmp_path / "table.arb"
+    obj.save(str(path), chunk_bytes=1 << 16)
+    back = _cls(d).load(str(path), chunk_bytes=1 << 15)
+    got = back.Query(q.copy())
+    ref = ref if isinstance(ref, tuple) else (ref,)
+    got = got if isinstance(got, tuple) else (got,)
+    for a, b in zip(ref, got):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert np.array_equal(back.queryInds, obj.queryInds) and back.nc == obj.nc
+    assert torch.equal(back.table, obj.table) or bool(torch.isnan(back.table[-1]).all())
+    with pytest.raises(AttributeError):
+        back.Bn if mode != "vector" else back.Bx
+    with pytest.raises(ValueError):
+        _cls(7 - d).load(str(path))
+
+
+@pytest.mark.parametrize("name,modes", [("tri_12x10x9", ["vector", "norm", "both"]), ("tri_scalar_9x8x11", ["scalar"])])
+def test_table_free_path_golden(name, modes):
+    """tricubic(table=False): no coefficient table, every query evaluated from its 4x4x4 neighbourhood
+    (odd nx = 9 exercises the padded TMA pitch).  Same parity bar as the table path."""
+    from arbinterp_b200 import tricubic
+    g = load_golden(name)
+    for mode in modes:
+        kw = {} if mode == "scalar" else {"mode": mode}
+        obj = tricubic(g["field"].copy(), "quiet", table=False, **kw)
+        q = g[mode + "_q_in"].copy()
+        res = obj.Query(q)
+        _check_outputs(res, _golden_ref(g, mode), mode, g["field"], 3, g["h"], f"{name}/{mode}/table-free")
+        assert np.array_equal(q, g[mode + "_q_after"], equal_nan=True)
+        assert np.array_equal(obj.queryInds, g[mode + "_inds"])
+        with pytest.raises(AttributeError):
+            obj.table
+    with pytest.raises(ValueError):
+        from arbinterp_b200 import quadcubic
+        quadcubic(load_golden("quad_8x7x7x6")["field"], "quiet", table=False)
+
+
+@pytest.mark.parametrize("mode", ["vector", "norm", "both"])
+def test_table_free_matches_table_path(mode):
+    from arbinterp_b200 import tricubic
+    rng = np.random.default_rng(77)
+    field = _analytic_field3(37, 26, 23, rng=rng)
+    a = tricubic(field.copy(), "quiet", mode=mode)
+    b = tricubic(field.copy(), "quiet", mode=mode, table=False)
+    q = _uniform_queries(a, 3, 200_000, rng, extra=1)
+    q[::101, 0] = -9.0
+    qa, qb = q.copy(), q.copy()
+    ra, rb = a.Query(qa), b.Query(qb)
+    s_comp, s_norm, s_grad = _scales(field, 3, [a.hx, a.hy, a.hz])
+    ra = ra if isinstance(ra, tuple) else (ra,)
+    rb = rb if isinstance(rb, tuple) else (rb,)
+    _check_outputs(rb, ra, mode, field, 3, [a.hx, a.hy, a.hz], f"table-free vs table {mode}")
+    assert np.array_equal(qa, qb, equal_nan=True) and np.array_equal(a.queryInds, b.queryInds)
+    dev = b.Query(torch.from_numpy(q.copy()).cuda())
+    dev = dev if isinstance(dev, tuple) else (dev,)
+    for x, y in zip(rb, dev):
+        assert np.array_equal(x, y.cpu().numpy(), equal_nan=True)
+
+
 def test_empty_tiny_and_integer_queries():
     from arbinterp_b200 import tricubic
     field = _analytic_field3(12, 11, 10)
@@ -328,6 +395,7 @@ def test_empty_tiny_and_integer_queries():
     assert one[0].shape == (1, 3) and one[1].shape == (1, 1) and one[2].shape == (1, 3)
     # integer arrays: work while nothing has to be NaN-masked, ValueError otherwise (numpy cannot store NaN)
     qi = np.zeros((4, 3), dtype=np.int64)
+    qi[:, 2] = 1                                                  # (0, 0, 1) is inside the volume
     assert np.isfinite(obj.Query(qi)[1]).all()
     qi[2, 0] = 50
     with pytest.raises(ValueError):

@@ -87,6 +87,7 @@ def main():
     ap.add_argument("--grid4", default="48,48,48,32")
     ap.add_argument("--queries", type=int, default=1 << 25)
     ap.add_argument("--build-variants", default="0,1,2")
+    ap.add_argument("--table-free", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
@@ -125,6 +126,32 @@ def main():
                           f"({ALG_BYTES[(d, mode)] * rate / 1e9 / 6458.4:.3f} of measured copy peak)", flush=True)
                 except Exception as e:  # noqa: BLE001
                     print(f"[query] d={d} mode={mode} variant={v}: FAILED {e}", flush=True)
+            if d == 3 and args.table_free:
+                del obj
+                torch.cuda.empty_cache()
+                rows = field_rows(shape, dev)
+                tf = tricubic(rows, "quiet", mode=mode, table=False)
+                del rows
+                comps = torch.empty(q.shape[0], 3, dtype=torch.float64, device=dev) if mode in ("vector", "both") else None
+                norm = torch.empty(q.shape[0], 1, dtype=torch.float64, device=dev) if mode in ("norm", "both") else None
+                grad = torch.empty(q.shape[0], 3, dtype=torch.float64, device=dev) if mode in ("norm", "both") else None
+                cells = torch.empty(q.shape[0], dtype=torch.int64, device=dev)
+                ptr = lambda t: None if t is None else t.data_ptr()
+                st = torch.cuda.current_stream()
+                def launch():
+                    _lib.check(tf._lib.arb_query_grid(ctypes.byref(tf._cgeom), tf._planes.data_ptr(), tf._pitch, tf._mode_code,
+                                                      q.data_ptr(), q.shape[0], q.shape[1], ptr(comps), ptr(norm), ptr(grad),
+                                                      cells.data_ptr(), None, None, st.cuda_stream), "grid")
+                launch(); launch()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize(); e0.record(st)
+                for _ in range(5):
+                    launch()
+                e1.record(st); torch.cuda.synchronize()
+                rate = q.shape[0] * 5 / (e0.elapsed_time(e1) / 1e3)
+                print(f"[query] d=3 mode={mode} TABLE-FREE grid={shape}: {rate:.4e} q/s (grid {tf._planes.numel() * 8 / 1e6:.0f} MB)", flush=True)
+                del tf
+                obj = None
             del obj, q
             torch.cuda.empty_cache()
 
