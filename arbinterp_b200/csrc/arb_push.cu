@@ -1,0 +1,136 @@
+// Fused query + push: particles stay resident in HBM and are advanced by many
+// velocity-Verlet steps of  dv/dt = kappa * grad|B|(x) + g  inside one kernel, the gradient being the
+// quantity the reference's Query2/Query3 return (A.py:452, 519).  This is the application ARBInterp
+// was written for (CHANGELOG.md:22 "simulating particle motion in magnetic fields"; the reference
+// dropped its own trajectory code in 1.8, CHANGELOG.md:8) and what removes the per-step host round trip
+// of a Python loop around Query.
+//
+// One lane per particle.  Each step locates the particle's cell with the reference's arithmetic and
+// evaluates the norm component's tricubic block exactly like query_block_kernel (same TMA bulk copy
+// into the lane's shared-memory slot, same nested Horner).  The slot persists across steps: while a
+// particle stays in its cell no memory traffic is issued at all, so small time steps run at FP64
+// issue rate instead of HBM rate.  Particles that leave the interpolation volume are marked lost:
+// position and velocity become NaN (the Query convention for out-of-volume points).
+#include "arb_device.cuh"
+
+namespace arb {
+
+struct PushParams {
+    QueryParams q;          // geometry + table (q.q etc. unused)
+    double* pos;            // [N][3]
+    double* vel;            // [N][3]
+    double dt, kappa, g[3];
+    int64_t nsteps;
+    unsigned long long* lost;
+    int ncomp;              // table components per cell; the norm block is the last one
+};
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) push_kernel(const PushParams P) {
+    constexpr int D = 3;
+    constexpr uint32_t BYTES = 512, SLOT = 528;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bars[THREADS / 32];
+    const QueryParams& p = P.q;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint64_t* bar = &bars[wid];
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    unsigned char* slot = smem + (size_t)threadIdx.x * SLOT;
+    const int64_t warp_global = ((int64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * THREADS) >> 5;
+    uint32_t phase = 0;
+    const double hdt = 0.5 * P.dt;
+    for (int64_t base = warp_global * 32; base < p.N; base += nwarps * 32) {
+        const int64_t n = base + lane;
+        const bool active = n < p.N;
+        double x[3] = {0, 0, 0}, v[3] = {0, 0, 0};
+        if (active) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { x[a] = P.pos[n * 3 + a]; v[a] = P.vel[n * 3 + a]; }
+        }
+        bool alive = active;
+        int64_t cur_blk = -1;
+        for (int64_t step = 0; step <= P.nsteps; ++step) {
+            Located<D> L;
+            L.ok = false;
+            if (alive) L = locate_coords<D>(p, x);
+            if (alive && !L.ok) {               // left the volume (or NaN): lost from here on
+                alive = false;
+                x[0] = x[1] = x[2] = v[0] = v[1] = v[2] = qnan();
+                if (P.lost) atomicAdd(P.lost, 1ULL);
+            }
+            const int64_t blk = L.cell_local * P.ncomp + (P.ncomp - 1);
+            const bool fetch = alive && (blk != cur_blk);
+            const unsigned fmask = __ballot_sync(0xffffffffu, fetch);
+            if (fmask) {                         // warp-uniform
+                if (lane == 0) mbar_expect_tx(bar, (uint32_t)__popc(fmask) * BYTES);
+                __syncwarp();
+                if (fetch) {
+                    bulk_g2s(slot, p.table + blk * 64, BYTES, bar);
+                    cur_blk = blk;
+                }
+                mbar_wait(bar, phase);
+                phase ^= 1;
+            }
+            double a[3] = {0, 0, 0};
+            if (alive) {
+                double g[5];
+                eval_value_grad<3, true>(reinterpret_cast<const double*>(slot), L.frac, g);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) a[c] = fma(P.kappa, __ddiv_rn(g[1 + c], p.h[c]), P.g[c]);
+            }
+            if (step > 0) {                      // second half kick of the previous step
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[c] = fma(hdt, a[c], v[c]);
+            }
+            if (step == P.nsteps) break;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {        // first half kick + drift
+                v[c] = fma(hdt, a[c], v[c]);
+                x[c] = fma(P.dt, v[c], x[c]);
+            }
+            __syncwarp();
+        }
+        if (active) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { P.pos[n * 3 + a] = x[a]; P.vel[n * 3 + a] = v[a]; }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace arb
+
+extern "C" int arb_push(const arb_geom* g, const double* table, int mode, double* pos, double* vel, int64_t N,
+                        double dt, int64_t nsteps, double kappa, const double* gravity,
+                        unsigned long long* lost_count, void* stream) {
+    using namespace arb;
+    if (mode != ARB_MODE_NORM && mode != ARB_MODE_BOTH) {
+        set_error("arb_push: needs a table with a norm component (mode norm or both), got mode %d", mode);
+        return 1;
+    }
+    if (!pos || !vel || nsteps < 0) { set_error("arb_push: null pos/vel or negative nsteps"); return 1; }
+    PushParams P;
+    memset(&P, 0, sizeof(P));
+    const int rc = fill_params("arb_push", g, true, table, mode, pos, N, 3, nullptr, nullptr, nullptr, nullptr, nullptr,
+                               nullptr, P.q, false);
+    if (rc) return rc < 0 ? 0 : rc;
+    if (g->d != 3) { set_error("arb_push: only d = 3 is implemented"); return 1; }
+    P.pos = pos; P.vel = vel; P.dt = dt; P.kappa = kappa; P.nsteps = nsteps; P.lost = lost_count; P.ncomp = g->ncomp;
+    for (int a = 0; a < 3; ++a) P.g[a] = gravity ? gravity[a] : 0.0;
+    constexpr int THREADS = 128;
+    const size_t smem = (size_t)THREADS * 528;
+    auto k = push_kernel<THREADS>;
+    ARB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, THREADS, smem) != cudaSuccess || occ < 1) occ = 1;
+    int64_t grid = (int64_t)num_sms() * occ;
+    const int64_t need = (N + THREADS - 1) / THREADS;
+    if (need < grid) grid = need;
+    k<<<(unsigned)grid, THREADS, smem, (cudaStream_t)stream>>>(P);
+    return check_cuda(cudaGetLastError(), "push_kernel launch");
+}

@@ -439,6 +439,35 @@ class _CubicInterpolator:
         """Components, magnitude, gradient (A.py:457-521 / 1190-1258)."""
         return self._range(query)
 
+    # ------------------------------------------------------------------ fused query + push
+    def push(self, pos, vel, dt, nsteps, kappa, gravity=None):
+        """Advance particles by ``nsteps`` velocity-Verlet steps of ``dv/dt = kappa * grad(value)(x) + gravity``
+        inside one kernel, where ``grad(value)`` is the gradient ``Query`` returns in 'norm'/'both'/scalar mode
+        (for a magnetic trap: value = |B|, kappa = -mu/m).  ``pos``/``vel``: (N,3) float64 torch CUDA tensors,
+        updated in place (numpy arrays are copied to the GPU and back).  Particles that leave the
+        interpolation volume get NaN position and velocity.  Returns the number of particles lost."""
+        if self._d != 3 or self._mode == "vector" or self._table is None:
+            raise ValueError("push() needs a tricubic interpolator with a coefficient table in 'norm', 'both' or scalar mode")
+        host = not isinstance(pos, torch.Tensor)
+        p = torch.as_tensor(pos, dtype=torch.float64).to(self._device).contiguous() if host else pos
+        v = torch.as_tensor(vel, dtype=torch.float64).to(self._device).contiguous() if host else vel
+        for t in (p, v):
+            if t.dtype != torch.float64 or not t.is_contiguous() or t.dim() != 2 or t.shape[1] != 3 or t.device != self._device:
+                raise ValueError("pos and vel must be contiguous float64 (N,3) tensors on the interpolator's device")
+        if p.shape != v.shape:
+            raise ValueError("pos and vel must have the same shape")
+        lost = torch.zeros(1, dtype=torch.int64, device=self._device)
+        grav = (ctypes.c_double * 3)(*([0.0, 0.0, 0.0] if gravity is None else [float(x) for x in gravity]))
+        with torch.cuda.device(self._device):
+            stream = torch.cuda.current_stream(self._device).cuda_stream
+            _lib.check(self._lib.arb_push(ctypes.byref(self._cgeom), self._table.data_ptr(), self._mode_code,
+                                          p.data_ptr(), v.data_ptr(), p.shape[0], float(dt), int(nsteps), float(kappa),
+                                          ctypes.byref(grav), lost.data_ptr(), stream), "arb_push")
+        if host:
+            np.copyto(pos, p.cpu().numpy())
+            np.copyto(vel, v.cpu().numpy())
+        return int(lost.item())
+
     # ------------------------------------------------------------------ single-point queries
     def _single(self, query):
         """Shared part of sQuery1/2/3 (A.py:213-342 / 916-1062): NaN outside the volume, else one

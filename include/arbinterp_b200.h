@@ -116,6 +116,15 @@ int arb_query_grid_host(const arb_geom* g, const double* grid, int64_t pitch_x, 
                         int64_t ldq, double* out_comps_host, double* out_norm_host, double* out_grad_host,
                         int64_t* out_cell_host, int64_t chunk_rows);
 
+/* Fused query + push: nsteps velocity-Verlet steps of dv/dt = kappa * grad(value)(x) + gravity for N
+ * particles resident in device memory, the gradient being what Query2/Query3 return (A.py:452, 519)
+ * for the table's last (norm / scalar) component.  d = 3, mode NORM or BOTH.
+ *   pos, vel : device [N][3], updated in place; particles that leave the interpolation volume get NaN
+ *              position and velocity (the Query convention) and are counted in *lost_count (device, may be NULL).
+ *   gravity  : host pointer to 3 doubles or NULL. */
+int arb_push(const arb_geom* g, const double* table, int mode, double* pos, double* vel, int64_t N, double dt,
+             int64_t nsteps, double kappa, const double* gravity, unsigned long long* lost_count, void* stream);
+
 /* Tuning knob for experiments/benchmarks: selects the query-kernel variant
  * (0 = default).  Returns the previous value. */
 int arb_set_query_variant(int variant);

@@ -1,0 +1,32 @@
+#!/usr/bin/env python
+"""Small workload touching every kernel (3-D/4-D build, all query modes and variants, table-free path,
+host pipeline) for compute-sanitizer runs.  Sizes are tiny: the sanitizer slows kernels 10-100x."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from arbinterp_b200 import _lib, quadcubic, tricubic
+
+rng = np.random.default_rng(0)
+x = np.linspace(-1, 1, 11); y = np.linspace(0, 1, 10); z = np.linspace(-1, 0, 9); t = np.linspace(0, 1, 7)
+Z, Y, X = [a.ravel() for a in np.meshgrid(z, y, x, indexing="ij")]
+f3 = np.stack([X, Y, Z, np.sin(X) * Y, X * Z, np.cos(Y + Z)], 1)
+T, Z4, Y4, X4 = [a.ravel() for a in np.meshgrid(t, z[:7], y[:8], x[:9], indexing="ij")]
+f4 = np.stack([X4, Y4, Z4, T, np.sin(X4) * T, X4 * Z4, np.cos(Y4 + T)], 1)
+lib = _lib.load()
+for mode in ("vector", "norm", "both"):
+    for table in (True, False):
+        o = tricubic(f3, "quiet", mode=mode, table=table)
+        q = np.stack([rng.uniform(o.xIntMin, o.xIntMax, 700), rng.uniform(o.yIntMin, o.yIntMax * 1.1, 700),
+                      rng.uniform(o.zIntMin, o.zIntMax, 700)], 1)
+        for v in ((0, 1, 2, 10, 20) if table else (0,)):
+            lib.arb_set_query_variant(v)
+            o.Query(q.copy())
+        lib.arb_set_query_variant(0)
+    o4 = quadcubic(f4, "quiet", mode=mode)
+    q4 = np.stack([rng.uniform(o4.xIntMin, o4.xIntMax, 300), rng.uniform(o4.yIntMin, o4.yIntMax, 300),
+                   rng.uniform(o4.zIntMin, o4.zIntMax, 300), rng.uniform(o4.tIntMin, o4.tIntMax * 1.1, 300)], 1)
+    for v in (0, 10):
+        lib.arb_set_query_variant(v)
+        o4.Query(q4.copy())
+    lib.arb_set_query_variant(0)
+print("sanitize target done")
