@@ -203,12 +203,93 @@ int retire(Slot& s, const Call& c) {
 }  // namespace
 }  // namespace arb
 
+// ---------------------------------------------------------------------------------------------------
+// Small batches (the reference's single-point and short line queries, A.py:213-342): latency matters,
+// not overlap.  One pinned + one device scratch block laid out [q | count | comps | norm | grad | cell |
+// rows]: one H2D (q and the zeroed counter), the kernel, one D2H (counter and all outputs), one sync.
+// ---------------------------------------------------------------------------------------------------
+namespace arb {
+namespace {
+constexpr int64_t SMALL_ROWS = 8192;
+
+struct SmallCtx {
+    cudaStream_t stream = nullptr;
+    unsigned char* d = nullptr;
+    unsigned char* h = nullptr;
+    size_t cap = 0;
+    std::mutex mutex;
+};
+SmallCtx g_small[16];
+
+int query_host_small(const arb_geom* g, const double* table, int64_t grid_pitch, int mode, double* q_host, int64_t N,
+                     int64_t ldq, double* comps, double* norm, double* grad, int64_t* cell) {
+    int dev = 0;
+    ARB_CUDA(cudaGetDevice(&dev));
+    SmallCtx& c = g_small[dev & 15];
+    std::lock_guard<std::mutex> lock(c.mutex);
+    const int d = g->d;
+    const size_t o_q = 0, o_count = o_q + sizeof(double) * N * ldq, o_comps = o_count + 8,
+                 o_norm = o_comps + sizeof(double) * N * 3, o_grad = o_norm + sizeof(double) * N,
+                 o_cell = o_grad + sizeof(double) * N * d, o_rows = o_cell + 8 * N, total = o_rows + 8 * N;
+    if (total > c.cap) {
+        if (!c.stream) ARB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        cudaFree(c.d); cudaFreeHost(c.h);
+        c.d = nullptr; c.h = nullptr; c.cap = 0;
+        const size_t want = total < (1u << 20) ? (1u << 20) : total;
+        ARB_CUDA(cudaMalloc(&c.d, want));
+        ARB_CUDA(cudaMallocHost(&c.h, want));
+        c.cap = want;
+    }
+    memcpy(c.h + o_q, q_host, sizeof(double) * N * ldq);
+    *reinterpret_cast<unsigned long long*>(c.h + o_count) = 0ULL;
+    ARB_CUDA(cudaMemcpyAsync(c.d, c.h, o_count + 8, cudaMemcpyHostToDevice, c.stream));
+    const bool cell_dev = is_device(cell);
+    int64_t* d_cell = cell ? (cell_dev ? cell : reinterpret_cast<int64_t*>(c.d + o_cell)) : nullptr;
+    double* dq = reinterpret_cast<double*>(c.d + o_q);
+    int rc;
+    if (grid_pitch > 0)
+        rc = query_grid_device(g, table, grid_pitch, mode, dq, N, ldq, reinterpret_cast<double*>(c.d + o_comps),
+                               reinterpret_cast<double*>(c.d + o_norm), reinterpret_cast<double*>(c.d + o_grad), d_cell,
+                               reinterpret_cast<int64_t*>(c.d + o_rows),
+                               reinterpret_cast<unsigned long long*>(c.d + o_count), c.stream);
+    else
+        rc = query_device(g, table, mode, dq, N, ldq, reinterpret_cast<double*>(c.d + o_comps),
+                          reinterpret_cast<double*>(c.d + o_norm), reinterpret_cast<double*>(c.d + o_grad), d_cell,
+                          reinterpret_cast<int64_t*>(c.d + o_rows), reinterpret_cast<unsigned long long*>(c.d + o_count),
+                          c.stream, current_query_variant());
+    if (rc) return rc;
+    const size_t back_end = (cell && !cell_dev) ? o_rows : o_cell;
+    ARB_CUDA(cudaMemcpyAsync(c.h + o_count, c.d + o_count, back_end - o_count, cudaMemcpyDeviceToHost, c.stream));
+    ARB_CUDA(cudaStreamSynchronize(c.stream));
+    if (comps) memcpy(comps, c.h + o_comps, sizeof(double) * N * 3);
+    if (norm) memcpy(norm, c.h + o_norm, sizeof(double) * N);
+    if (grad) memcpy(grad, c.h + o_grad, sizeof(double) * N * d);
+    if (cell && !cell_dev) memcpy(cell, c.h + o_cell, 8 * N);
+    const unsigned long long cnt = *reinterpret_cast<unsigned long long*>(c.h + o_count);
+    if (cnt) {
+        ARB_CUDA(cudaMemcpyAsync(c.h + o_rows, c.d + o_rows, 8 * cnt, cudaMemcpyDeviceToHost, c.stream));
+        ARB_CUDA(cudaStreamSynchronize(c.stream));
+        const int64_t* rows = reinterpret_cast<const int64_t*>(c.h + o_rows);
+        const double nan = __builtin_nan("");
+        for (unsigned long long i = 0; i < cnt; ++i)
+            for (int64_t k = 0; k < ldq; ++k) q_host[rows[i] * ldq + k] = nan;
+    }
+    return 0;
+}
+}  // namespace
+}  // namespace arb
+
 static int query_host_impl(const arb_geom* g, const double* table, int64_t grid_pitch, int mode, double* q_host,
                            int64_t N, int64_t ldq, double* out_comps_host, double* out_norm_host,
                            double* out_grad_host, int64_t* out_cell_host, int64_t chunk_rows) {
     using namespace arb;
     if (!g || !q_host || N < 0) { set_error("arb_query_host: bad arguments"); return 1; }
     if (N == 0) return 0;
+    if (N <= SMALL_ROWS && chunk_rows <= 0)
+        return query_host_small(g, table, grid_pitch, mode, q_host, N, ldq,
+                                (mode != ARB_MODE_NORM) ? out_comps_host : nullptr,
+                                (mode != ARB_MODE_VECTOR) ? out_norm_host : nullptr,
+                                (mode != ARB_MODE_VECTOR) ? out_grad_host : nullptr, out_cell_host);
     if (chunk_rows <= 0) chunk_rows = 1 << 20;
     if (chunk_rows > N) chunk_rows = N;
     int dev = 0;

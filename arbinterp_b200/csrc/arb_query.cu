@@ -482,10 +482,21 @@ __global__ void __launch_bounds__(THREADS) query_grid_kernel(const __grid_consta
 // --------------------------------------------------------------------------------------
 // launchers
 // --------------------------------------------------------------------------------------
+// Per-kernel, per-device launch set-up (dynamic shared-memory opt-in + occupancy) is done once and
+// cached: it costs several microseconds per call, which matters for small batches.
+struct LaunchCache { int occ[16]; };
+
 template <typename K>
-static int persistent_grid(K kernel, int threads, size_t smem, int64_t work_blocks) {
-    int occ = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem) != cudaSuccess || occ < 1) occ = 1;
+static int persistent_grid(K kernel, int threads, size_t smem, int64_t work_blocks, LaunchCache& cache) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    int& occ = cache.occ[dev & 15];
+    if (occ == 0) {
+        if (smem > 0) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int o = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kernel, threads, smem) != cudaSuccess || o < 1) o = 1;
+        occ = o;
+    }
     int64_t g = (int64_t)num_sms() * occ;
     if (work_blocks < g) g = work_blocks;
     return (int)(g < 1 ? 1 : g);
@@ -497,7 +508,8 @@ static int launch_coop(const QueryParams& p, cudaStream_t st) {
     constexpr int THREADS = 256;
     const int64_t per_block = (int64_t)(THREADS / G) * U;
     auto k = query_coop_kernel<D, C, MODE, U>;
-    const int grid = persistent_grid(k, THREADS, 0, (p.N + per_block - 1) / per_block);
+    static LaunchCache cache = {};
+    const int grid = persistent_grid(k, THREADS, 0, (p.N + per_block - 1) / per_block, cache);
     k<<<grid, THREADS, 0, st>>>(p);
     return check_cuda(cudaGetLastError(), "query_coop_kernel launch");
 }
@@ -507,8 +519,8 @@ static int launch_bulk(const QueryParams& p, cudaStream_t st) {
     constexpr int NM = (D == 3) ? 64 : 256;
     const size_t smem = (size_t)THREADS * (C * NM * 8 + 16);
     auto k = query_bulk_kernel<D, C, MODE, THREADS>;
-    ARB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = persistent_grid(k, THREADS, smem, (p.N + THREADS - 1) / THREADS);
+    static LaunchCache cache = {};
+    const int grid = persistent_grid(k, THREADS, smem, (p.N + THREADS - 1) / THREADS, cache);
     k<<<grid, THREADS, smem, st>>>(p);
     return check_cuda(cudaGetLastError(), "query_bulk_kernel launch");
 }
@@ -519,9 +531,9 @@ static int launch_block(const QueryParams& p, cudaStream_t st) {
     constexpr int QPW = (D == 4) ? 8 : 32;
     const size_t smem = (size_t)THREADS * 528;
     auto k = query_block_kernel<D, MODE, THREADS, DEDUP>;
-    ARB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static LaunchCache cache = {};
     const int64_t items = ((p.N + QPW - 1) / QPW) * C;
-    const int grid = persistent_grid(k, THREADS, smem, (items + THREADS / 32 - 1) / (THREADS / 32));
+    const int grid = persistent_grid(k, THREADS, smem, (items + THREADS / 32 - 1) / (THREADS / 32), cache);
     k<<<grid, THREADS, smem, st>>>(p);
     return check_cuda(cudaGetLastError(), "query_block_kernel launch");
 }
@@ -529,7 +541,8 @@ static int launch_block(const QueryParams& p, cudaStream_t st) {
 template <int D, int C, int MODE>
 static int launch_direct(const QueryParams& p, cudaStream_t st) {
     auto k = query_direct_kernel<D, C, MODE>;
-    const int grid = persistent_grid(k, 128, 0, (p.N + 127) / 128);
+    static LaunchCache cache = {};
+    const int grid = persistent_grid(k, 128, 0, (p.N + 127) / 128, cache);
     k<<<grid, 128, 0, st>>>(p);
     return check_cuda(cudaGetLastError(), "query_direct_kernel launch");
 }
@@ -617,9 +630,9 @@ static int launch_grid(const CUtensorMap& tm, const QueryParams& p, cudaStream_t
     constexpr int THREADS = 128;
     const size_t smem = (size_t)THREADS * 768;
     auto k = query_grid_kernel<MODE, THREADS>;
-    ARB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static LaunchCache cache = {};
     const int64_t items = ((p.N + 31) / 32) * C;
-    const int grid = persistent_grid(k, THREADS, smem, (items + THREADS / 32 - 1) / (THREADS / 32));
+    const int grid = persistent_grid(k, THREADS, smem, (items + THREADS / 32 - 1) / (THREADS / 32), cache);
     k<<<grid, THREADS, smem, st>>>(tm, p);
     return check_cuda(cudaGetLastError(), "query_grid_kernel launch");
 }

@@ -396,6 +396,8 @@ class _CubicInterpolator:
         direct = query.dtype == np.float64 and query.flags.c_contiguous and query.flags.writeable
         work = query if direct else np.ascontiguousarray(query, dtype=np.float64).copy()
         n = work.shape[0]
+        if n <= self._SMALL_ROWS:
+            return self._range_host_small(query, work, direct)
         comps, norm, grad = self._outputs(n, pinned=True)
         cells = torch.empty(n, dtype=torch.int64, device=self._device)   # stays in HBM; read back lazily
         with torch.cuda.device(self._device):
@@ -416,6 +418,34 @@ class _CubicInterpolator:
                 query[np.where(bad)[0]] = np.nan                 # A.py:350-355 (raises for int arrays, as there)
         self._last_cells = cells
         return tuple(None if t is None else t.numpy() for t in (comps, norm, grad))
+
+    _SMALL_ROWS = 8192        # same threshold as SMALL_ROWS in csrc/arb_host.cu
+
+    def _range_host_small(self, query, work, direct):
+        """Latency path for short batches and single points: plain numpy outputs, one H2D, one kernel, one
+        D2H inside the library -- no pinned allocations, no stream ring."""
+        d, mode, n = self._d, self._mode, work.shape[0]
+        comps = np.empty((n, 3)) if mode != "norm" else None
+        norm = np.empty((n, 1)) if mode != "vector" else None
+        grad = np.empty((n, d)) if mode != "vector" else None
+        cells = np.empty(n, dtype=np.int64)
+        ptr = lambda a: None if a is None else a.ctypes.data
+        if torch.cuda.current_device() != self._device.index:
+            torch.cuda.set_device(self._device)
+        args = (ctypes.byref(self._cgeom), self._planes.data_ptr() if self._table is None else self._table.data_ptr())
+        if self._table is None:
+            rc = self._lib.arb_query_grid_host(*args, self._pitch, self._mode_code, work.ctypes.data, n, work.shape[1],
+                                               ptr(comps), ptr(norm), ptr(grad), cells.ctypes.data, 0)
+        else:
+            rc = self._lib.arb_query_host(*args, self._mode_code, work.ctypes.data, n, work.shape[1],
+                                          ptr(comps), ptr(norm), ptr(grad), cells.ctypes.data, 0)
+        _lib.check(rc, "arb_query_host")
+        if not direct:
+            bad = np.isnan(work[:, :d]).any(axis=1) & ~np.isnan(np.asarray(query[:, :d], dtype=np.float64)).any(axis=1)
+            if bad.any():
+                query[np.where(bad)[0]] = np.nan
+        self._last_cells = cells
+        return comps, norm, grad
 
     def _range(self, query):
         if isinstance(query, torch.Tensor):
@@ -481,7 +511,7 @@ class _CubicInterpolator:
             if q[a] < geo.int_min[a] or q[a] > geo.int_max[a]:   # A.py:215, 918
                 return None
         res = self._range_host(q[:d].reshape(1, d).copy())
-        self.queryInd = int(self._last_cells[0].item())         # A.py:231-232
+        self.queryInd = int(self._last_cells[0])                # A.py:231-232
         return res
 
     def sQuery1(self, query):
