@@ -5,7 +5,7 @@
 // dropped its own trajectory code in 1.8, CHANGELOG.md:8) and what removes the per-step host round trip
 // of a Python loop around Query.
 //
-// One lane per particle.  Each step locates the particle's cell with the reference's arithmetic and
+// One lane per particle (four in 4-D).  Each step locates the particle's cell with the reference's arithmetic and
 // evaluates the norm component's tricubic block exactly like query_block_kernel (same TMA bulk copy
 // into the lane's shared-memory slot, same nested Horner).  The slot persists across steps: while a
 // particle stays in its cell no memory traffic is issued at all, so small time steps run at FP64
@@ -17,7 +17,7 @@ namespace arb {
 
 struct PushParams {
     QueryParams q;          // geometry + table (q.q etc. unused)
-    double* pos;            // [N][3]
+    double* pos;            // [N][D] (D = 4: x, y, z and the particle's own time)
     double* vel;            // [N][3]
     double dt, kappa, g[3];
     int64_t nsteps;
@@ -25,14 +25,21 @@ struct PushParams {
     int ncomp;              // table components per cell; the norm block is the last one
 };
 
-template <int THREADS>
+// D = 3: one lane per particle.  D = 4 (time-dependent field): the norm component's 256 coefficients are
+// four tricubic blocks alpha[.., l]; four adjacent lanes own (particle, l), each evaluates its block in
+// (u, v, w) and the spatial gradient is the s^l-weighted sum over the four lanes (as in
+// query_block_kernel); all four lanes carry the particle state redundantly and update it identically.
+// pos is [N][D] (the 4th coordinate is the particle's own time and advances by dt per step), vel [N][3].
+template <int D, int THREADS>
 __global__ void __launch_bounds__(THREADS) push_kernel(const PushParams P) {
-    constexpr int D = 3;
+    constexpr int SL = (D == 4) ? 4 : 1;
+    constexpr int PPW = 32 / SL;                 // particles per warp pass
     constexpr uint32_t BYTES = 512, SLOT = 528;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bars[THREADS / 32];
     const QueryParams& p = P.q;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int pi = lane / SL, sl = lane % SL;
     uint64_t* bar = &bars[wid];
     if (lane == 0) {
         mbar_init(bar, 1);
@@ -44,13 +51,15 @@ __global__ void __launch_bounds__(THREADS) push_kernel(const PushParams P) {
     const int64_t nwarps = ((int64_t)gridDim.x * THREADS) >> 5;
     uint32_t phase = 0;
     const double hdt = 0.5 * P.dt;
-    for (int64_t base = warp_global * 32; base < p.N; base += nwarps * 32) {
-        const int64_t n = base + lane;
+    for (int64_t base = warp_global * PPW; base < p.N; base += nwarps * PPW) {
+        const int64_t n = base + pi;
         const bool active = n < p.N;
-        double x[3] = {0, 0, 0}, v[3] = {0, 0, 0};
+        double x[D], v[3] = {0, 0, 0};
+#pragma unroll
+        for (int a = 0; a < D; ++a) x[a] = active ? P.pos[n * D + a] : 0.0;
         if (active) {
 #pragma unroll
-            for (int a = 0; a < 3; ++a) { x[a] = P.pos[n * 3 + a]; v[a] = P.vel[n * 3 + a]; }
+            for (int a = 0; a < 3; ++a) v[a] = P.vel[n * 3 + a];
         }
         bool alive = active;
         int64_t cur_blk = -1;
@@ -60,10 +69,11 @@ __global__ void __launch_bounds__(THREADS) push_kernel(const PushParams P) {
             if (alive) L = locate_coords<D>(p, x);
             if (alive && !L.ok) {               // left the volume (or NaN): lost from here on
                 alive = false;
-                x[0] = x[1] = x[2] = v[0] = v[1] = v[2] = qnan();
-                if (P.lost) atomicAdd(P.lost, 1ULL);
+#pragma unroll
+                for (int a = 0; a < 3; ++a) x[a] = v[a] = qnan();
+                if (P.lost && sl == 0) atomicAdd(P.lost, 1ULL);
             }
-            const int64_t blk = L.cell_local * P.ncomp + (P.ncomp - 1);
+            const int64_t blk = (L.cell_local * P.ncomp + (P.ncomp - 1)) * SL + sl;
             const bool fetch = alive && (blk != cur_blk);
             const unsigned fmask = __ballot_sync(0xffffffffu, fetch);
             if (fmask) {                         // warp-uniform
@@ -76,10 +86,19 @@ __global__ void __launch_bounds__(THREADS) push_kernel(const PushParams P) {
                 mbar_wait(bar, phase);
                 phase ^= 1;
             }
+            double g[5] = {0, 0, 0, 0, 0};
+            if (alive) eval_value_grad<3, true>(reinterpret_cast<const double*>(slot), L.frac, g);
+            if (D == 4) {
+                const double w = alive ? pow_sel(L.frac[D - 1], sl) : 0.0;
+#pragma unroll
+                for (int c = 1; c <= 3; ++c) {
+                    g[c] *= w;
+                    g[c] += __shfl_xor_sync(0xffffffffu, g[c], 1);
+                    g[c] += __shfl_xor_sync(0xffffffffu, g[c], 2);
+                }
+            }
             double a[3] = {0, 0, 0};
             if (alive) {
-                double g[5];
-                eval_value_grad<3, true>(reinterpret_cast<const double*>(slot), L.frac, g);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) a[c] = fma(P.kappa, __ddiv_rn(g[1 + c], p.h[c]), P.g[c]);
             }
@@ -93,14 +112,34 @@ __global__ void __launch_bounds__(THREADS) push_kernel(const PushParams P) {
                 v[c] = fma(hdt, a[c], v[c]);
                 x[c] = fma(P.dt, v[c], x[c]);
             }
+            if (D == 4) x[3] += P.dt;
             __syncwarp();
         }
-        if (active) {
+        if (active && sl == 0) {
 #pragma unroll
-            for (int a = 0; a < 3; ++a) { P.pos[n * 3 + a] = x[a]; P.vel[n * 3 + a] = v[a]; }
+            for (int a = 0; a < D; ++a) P.pos[n * D + a] = x[a];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) P.vel[n * 3 + a] = v[a];
         }
         __syncwarp();
     }
+}
+
+template <int D>
+static int launch_push(const PushParams& P, int64_t N, cudaStream_t st) {
+    constexpr int THREADS = 128;
+    constexpr int PPW = (D == 4) ? 8 : 32;
+    const size_t smem = (size_t)THREADS * 528;
+    auto k = push_kernel<D, THREADS>;
+    ARB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, THREADS, smem) != cudaSuccess || occ < 1) occ = 1;
+    int64_t grid = (int64_t)num_sms() * occ;
+    const int64_t per_block = (int64_t)(THREADS / 32) * PPW;
+    const int64_t need = (N + per_block - 1) / per_block;
+    if (need < grid) grid = need;
+    k<<<(unsigned)grid, THREADS, smem, st>>>(P);
+    return check_cuda(cudaGetLastError(), "push_kernel launch");
 }
 
 }  // namespace arb
@@ -116,21 +155,11 @@ extern "C" int arb_push(const arb_geom* g, const double* table, int mode, double
     if (!pos || !vel || nsteps < 0) { set_error("arb_push: null pos/vel or negative nsteps"); return 1; }
     PushParams P;
     memset(&P, 0, sizeof(P));
-    const int rc = fill_params("arb_push", g, true, table, mode, pos, N, 3, nullptr, nullptr, nullptr, nullptr, nullptr,
-                               nullptr, P.q, false);
+    const int rc = fill_params("arb_push", g, true, table, mode, pos, N, g ? g->d : 3, nullptr, nullptr, nullptr, nullptr,
+                               nullptr, nullptr, P.q, false);
     if (rc) return rc < 0 ? 0 : rc;
-    if (g->d != 3) { set_error("arb_push: only d = 3 is implemented"); return 1; }
     P.pos = pos; P.vel = vel; P.dt = dt; P.kappa = kappa; P.nsteps = nsteps; P.lost = lost_count; P.ncomp = g->ncomp;
     for (int a = 0; a < 3; ++a) P.g[a] = gravity ? gravity[a] : 0.0;
-    constexpr int THREADS = 128;
-    const size_t smem = (size_t)THREADS * 528;
-    auto k = push_kernel<THREADS>;
-    ARB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, THREADS, smem) != cudaSuccess || occ < 1) occ = 1;
-    int64_t grid = (int64_t)num_sms() * occ;
-    const int64_t need = (N + THREADS - 1) / THREADS;
-    if (need < grid) grid = need;
-    k<<<(unsigned)grid, THREADS, smem, (cudaStream_t)stream>>>(P);
-    return check_cuda(cudaGetLastError(), "push_kernel launch");
+    if (g->d == 3) return launch_push<3>(P, N, (cudaStream_t)stream);
+    return launch_push<4>(P, N, (cudaStream_t)stream);
 }

@@ -473,19 +473,21 @@ class _CubicInterpolator:
     def push(self, pos, vel, dt, nsteps, kappa, gravity=None):
         """Advance particles by ``nsteps`` velocity-Verlet steps of ``dv/dt = kappa * grad(value)(x) + gravity``
         inside one kernel, where ``grad(value)`` is the gradient ``Query`` returns in 'norm'/'both'/scalar mode
-        (for a magnetic trap: value = |B|, kappa = -mu/m).  ``pos``/``vel``: (N,3) float64 torch CUDA tensors,
-        updated in place (numpy arrays are copied to the GPU and back).  Particles that leave the
-        interpolation volume get NaN position and velocity.  Returns the number of particles lost."""
-        if self._d != 3 or self._mode == "vector" or self._table is None:
-            raise ValueError("push() needs a tricubic interpolator with a coefficient table in 'norm', 'both' or scalar mode")
+        (for a magnetic trap: value = |B|, kappa = -mu/m).  ``pos``: (N,d), ``vel``: (N,3) float64 torch CUDA
+        tensors, updated in place (numpy arrays are copied to the GPU and back); for a quadcubic
+        (time-dependent) field the 4th column of ``pos`` is each particle's own time and advances by ``dt``
+        per step.  Particles that leave the interpolation volume get NaN position and velocity.
+        Returns the number of particles lost."""
+        if self._mode == "vector" or self._table is None or self._slab != (0, self._geo.ncell[self._d - 1]):
+            raise ValueError("push() needs an unsharded coefficient table in 'norm', 'both' or scalar mode")
         host = not isinstance(pos, torch.Tensor)
         p = torch.as_tensor(pos, dtype=torch.float64).to(self._device).contiguous() if host else pos
         v = torch.as_tensor(vel, dtype=torch.float64).to(self._device).contiguous() if host else vel
-        for t in (p, v):
-            if t.dtype != torch.float64 or not t.is_contiguous() or t.dim() != 2 or t.shape[1] != 3 or t.device != self._device:
-                raise ValueError("pos and vel must be contiguous float64 (N,3) tensors on the interpolator's device")
-        if p.shape != v.shape:
-            raise ValueError("pos and vel must have the same shape")
+        for t, w in ((p, self._d), (v, 3)):
+            if t.dtype != torch.float64 or not t.is_contiguous() or t.dim() != 2 or t.shape[1] != w or t.device != self._device:
+                raise ValueError(f"pos must be (N,{self._d}) and vel (N,3): contiguous float64 on the interpolator's device")
+        if p.shape[0] != v.shape[0]:
+            raise ValueError("pos and vel must have the same number of rows")
         lost = torch.zeros(1, dtype=torch.int64, device=self._device)
         grav = (ctypes.c_double * 3)(*([0.0, 0.0, 0.0] if gravity is None else [float(x) for x in gravity]))
         with torch.cuda.device(self._device):

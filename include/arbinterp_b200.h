@@ -118,8 +118,9 @@ int arb_query_grid_host(const arb_geom* g, const double* grid, int64_t pitch_x, 
 
 /* Fused query + push: nsteps velocity-Verlet steps of dv/dt = kappa * grad(value)(x) + gravity for N
  * particles resident in device memory, the gradient being what Query2/Query3 return (A.py:452, 519)
- * for the table's last (norm / scalar) component.  d = 3, mode NORM or BOTH.
- *   pos, vel : device [N][3], updated in place; particles that leave the interpolation volume get NaN
+ * for the table's last (norm / scalar) component; mode NORM or BOTH.  For d = 4 (time-dependent field) pos
+ * carries each particle's own time as 4th coordinate, which advances by dt per step.
+ *   pos : device [N][d], vel : device [N][3], updated in place; particles that leave the interpolation volume get NaN
  *              position and velocity (the Query convention) and are counted in *lost_count (device, may be NULL).
  *   gravity  : host pointer to 3 doubles or NULL. */
 int arb_push(const arb_geom* g, const double* table, int mode, double* pos, double* vel, int64_t N, double dt,
