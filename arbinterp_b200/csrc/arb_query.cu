@@ -148,10 +148,8 @@ __global__ void __launch_bounds__(256) query_coop_kernel(const QueryParams p) {
                 }
                 idx += up ? half : 0;
             }
-            constexpr int LOGNVP = NVP == 1 ? 0 : (NVP == 2 ? 1 : (NVP == 4 ? 2 : (NVP == 8 ? 3 : 4)));
 #pragma unroll
             for (int m = NVP; m < G; m <<= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], m);
-            (void)LOGNVP;
             if (n[u] < p.N) {
                 if (l < NVP && idx < NV) store_output<D, MODE>(p, n[u], idx, L[u].ok ? v[0] : qnan());
                 if (l == G - 1) {

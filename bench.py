@@ -108,6 +108,24 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this rank to the CPU cores NVML reports as local to its GPU, so the pinned host buffers of the
+    end-to-end leg are allocated on (and copied from) the NUMA node the GPU's PCIe root hangs off."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1]
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"{len(allowed)} cores [{allowed[0]}..{allowed[-1]}]"
+    except Exception:
+        return None
+    return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -277,6 +295,7 @@ def run_b200(args):
     dist = None
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    affinity = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         import torch.distributed as dist_mod
         dist_mod.init_process_group("nccl", device_id=device)
@@ -390,6 +409,7 @@ def run_b200(args):
 
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
+    parity = None
     if world == 1 and not args.no_cpu:
         ncpu = n
         ora = make_cpu_oracle(ncpu, args.mode)
@@ -398,6 +418,20 @@ def run_b200(args):
         cpu = {"value": rate, "unit": "queries/s", "cores": 1, "kind": "port",
                "sample": f"{args.cpu_sample} warm queries (second pass, coefficients cached) through the numpy oracle "
                          f"on a {ncpu}^3 grid of the same analytic field, single process"}
+        # full-size parity on the same sample (oracle as the checker): indices exact, values within 1e-12 scaled
+        ref = ora.query(qc.copy())
+        ref = ref if isinstance(ref, tuple) else (ref,)
+        got = obj.Query(qc.copy())
+        got = got if isinstance(got, tuple) else (got,)
+        scale = max(float(np.abs(v).max()) for v in ora.values.values())
+        worst = 0.0
+        for a, b in zip(got, ref):
+            sc = scale / np.array(ora.geo.h)[None, :] if b.shape[1] == d and args.mode != "vector" and a is got[-1] else scale
+            worst = max(worst, float(np.max(np.abs(a - b) / np.maximum(np.abs(b), sc))))
+        parity = {"n": int(len(qc)), "max_scaled_err": worst, "tolerance": 1e-12,
+                  "indices_equal": bool(np.array_equal(obj.queryInds, ora.query_inds)),
+                  "checker": "oracle/arb_oracle.py (numpy restatement, bit-equal to the live reference on tests/golden)"}
+        assert parity["indices_equal"] and worst <= 1e-12, f"parity failure in bench: {parity}"
 
     peak, peak_src = measured_peak()
     alg = ALG_BYTES[(d, args.mode)]
@@ -414,12 +448,14 @@ def run_b200(args):
                    "cache": "inputs larger than L2 (query batch %.1f GB, table %.1f GB vs 126 MB L2)" %
                             (q.numel() * 8 / 1e9, obj.table.numel() * 8 / 1e9),
                    "parallelism": f"replicated table, queries sharded x{world}",
-                   "variant": args.variant if args.variant is not None else 0, "build_s": t_build},
+                   "variant": args.variant if args.variant is not None else 0, "build_s": t_build,
+                   "cpu_affinity": affinity},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (traffic_per_query * Q) if traffic_per_query else None,
                      "kernel": "query kernel (arb_query)", "alg_bytes_per_query": alg,
                      "avg_launch_ms": avg_ms, "peak_source": peak_src},
         "cpu_baseline": cpu,
+        "parity": parity,
         "e2e": e2e,
         "gpu_launches": args.steps * world,
         "clocks": clocks,
