@@ -300,6 +300,12 @@ def test_device_tensor_path_and_pageable_host_path():
         assert isinstance(b, torch.Tensor) and b.is_cuda
         assert np.array_equal(a, b.cpu().numpy(), equal_nan=True)
     assert torch.isnan(qd[7]).all()
+    # page-locked caller buffers are copied without staging; the in-place NaN rows still land in them
+    qp = torch.from_numpy(q.copy()).pin_memory().numpy()
+    pinned = obj.Query(qp)
+    for a, b in zip(host, pinned):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert np.isnan(qp[7]).all() and np.array_equal(qp[8], q[8])
     # float32 / non-contiguous input goes through a float64 copy; NaN rows are still written back
     q32 = q.astype(np.float32)
     r32 = obj.Query(q32)
