@@ -279,6 +279,20 @@ int query_host_small(const arb_geom* g, const double* table, int64_t grid_pitch,
 }  // namespace
 }  // namespace arb
 
+namespace arb {
+namespace {
+// error exit of the pipelined path: nothing may stay in flight that still points at this call's buffers
+int abandon(HostCtx& ctx, int rc) {
+    for (int i = 0; i < NSLOT; ++i) {
+        if (ctx.slot[i].stream) cudaStreamSynchronize(ctx.slot[i].stream);
+        ctx.slot[i].busy = false;
+    }
+    cudaGetLastError();
+    return rc;
+}
+}  // namespace
+}  // namespace arb
+
 static int query_host_impl(const arb_geom* g, const double* table, int64_t grid_pitch, int mode, double* q_host,
                            int64_t N, int64_t ldq, double* out_comps_host, double* out_norm_host,
                            double* out_grad_host, int64_t* out_cell_host, int64_t chunk_rows) {
@@ -310,16 +324,21 @@ static int query_host_impl(const arb_geom* g, const double* table, int64_t grid_
     c.grad_pinned = is_pinned(c.grad); c.cell_pinned = is_pinned(c.cell);
     c.cell_on_device = is_device(c.cell);
 
+#define ARB_CUDA_OR_ABANDON(expr)                                  \
+    do {                                                            \
+        int _rc = ::arb::check_cuda((expr), #expr);                 \
+        if (_rc) return abandon(ctx, _rc);                          \
+    } while (0)
     int64_t chunk = 0;
     for (int64_t off = 0; off < N; off += chunk_rows, ++chunk) {
         Slot& s = ctx.slot[chunk % NSLOT];
         rc = retire(s, c);
-        if (rc) return rc;
+        if (rc) return abandon(ctx, rc);
         const int64_t n = (N - off < chunk_rows) ? (N - off) : chunk_rows;
         const double* src = q_host + off * ldq;
         if (!c.q_pinned) { g_pool.copy(s.h_q, src, sizeof(double) * n * ldq); src = s.h_q; }
-        ARB_CUDA(cudaMemcpyAsync(s.d_q, src, sizeof(double) * n * ldq, cudaMemcpyHostToDevice, s.stream));
-        ARB_CUDA(cudaMemsetAsync(s.d_count, 0, sizeof(unsigned long long), s.stream));
+        ARB_CUDA_OR_ABANDON(cudaMemcpyAsync(s.d_q, src, sizeof(double) * n * ldq, cudaMemcpyHostToDevice, s.stream));
+        ARB_CUDA_OR_ABANDON(cudaMemsetAsync(s.d_count, 0, sizeof(unsigned long long), s.stream));
         int64_t* cell_dst = c.cell ? (c.cell_on_device ? c.cell + off : s.d_cell) : nullptr;
         if (grid_pitch > 0)
             rc = query_grid_device(g, table, grid_pitch, mode, s.d_q, n, ldq, s.d_comps, s.d_norm, s.d_grad, cell_dst,
@@ -327,26 +346,26 @@ static int query_host_impl(const arb_geom* g, const double* table, int64_t grid_
         else
             rc = query_device(g, table, mode, s.d_q, n, ldq, s.d_comps, s.d_norm, s.d_grad, cell_dst, s.d_rows,
                               s.d_count, s.stream, current_query_variant());
-        if (rc) return rc;
+        if (rc) return abandon(ctx, rc);
         if (c.comps)
-            ARB_CUDA(cudaMemcpyAsync(c.comps_pinned ? c.comps + off * 3 : s.h_comps, s.d_comps, sizeof(double) * n * 3,
+            ARB_CUDA_OR_ABANDON(cudaMemcpyAsync(c.comps_pinned ? c.comps + off * 3 : s.h_comps, s.d_comps, sizeof(double) * n * 3,
                                      cudaMemcpyDeviceToHost, s.stream));
         if (c.norm)
-            ARB_CUDA(cudaMemcpyAsync(c.norm_pinned ? c.norm + off : s.h_norm, s.d_norm, sizeof(double) * n,
+            ARB_CUDA_OR_ABANDON(cudaMemcpyAsync(c.norm_pinned ? c.norm + off : s.h_norm, s.d_norm, sizeof(double) * n,
                                      cudaMemcpyDeviceToHost, s.stream));
         if (c.grad)
-            ARB_CUDA(cudaMemcpyAsync(c.grad_pinned ? c.grad + off * c.d : s.h_grad, s.d_grad, sizeof(double) * n * c.d,
+            ARB_CUDA_OR_ABANDON(cudaMemcpyAsync(c.grad_pinned ? c.grad + off * c.d : s.h_grad, s.d_grad, sizeof(double) * n * c.d,
                                      cudaMemcpyDeviceToHost, s.stream));
         if (c.cell && !c.cell_on_device)
-            ARB_CUDA(cudaMemcpyAsync(c.cell_pinned ? c.cell + off : s.h_cell, s.d_cell, sizeof(int64_t) * n,
+            ARB_CUDA_OR_ABANDON(cudaMemcpyAsync(c.cell_pinned ? c.cell + off : s.h_cell, s.d_cell, sizeof(int64_t) * n,
                                      cudaMemcpyDeviceToHost, s.stream));
-        ARB_CUDA(cudaMemcpyAsync(s.h_count, s.d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
-        ARB_CUDA(cudaEventRecord(s.done, s.stream));
+        ARB_CUDA_OR_ABANDON(cudaMemcpyAsync(s.h_count, s.d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+        ARB_CUDA_OR_ABANDON(cudaEventRecord(s.done, s.stream));
         s.busy = true; s.off = off; s.rows = n;
     }
     for (int i = 0; i < NSLOT; ++i) {
         rc = retire(ctx.slot[i], c);
-        if (rc) return rc;
+        if (rc) return abandon(ctx, rc);
     }
     return 0;
 }
