@@ -230,6 +230,8 @@ class OracleInterp:
             # sorted cell ids + coefficient columns; the arithmetic is unchanged.
             self._cells = np.zeros(0, dtype=np.int64)
             self._cols = {k: np.zeros((self.nmono, 0)) for k in self.values}
+            self._have = np.zeros(nc + 1, dtype=bool)
+            self._have[-1] = True
 
     @classmethod
     def from_planes(cls, axes, values, mode, scalar_input=False, reference_quirk=True, dense=False):
@@ -254,6 +256,8 @@ class OracleInterp:
         else:
             self._cells = np.zeros(0, dtype=np.int64)
             self._cols = {k: np.zeros((self.nmono, 0)) for k in self.values}
+            self._have = np.zeros(nc + 1, dtype=bool)
+            self._have[-1] = True
         return self
 
     # ---- coefficients ------------------------------------------------------------
@@ -272,10 +276,15 @@ class OracleInterp:
         return out
 
     def calc_coefficients(self, cells, exact_gemv=False, chunk=8192):
-        cells = np.unique(np.asarray(cells, dtype=np.int64))
+        cells = np.asarray(cells, dtype=np.int64)
+        # the reference's cheap "already there?" test first (A.py:376: alphamask[queryInds] == 0)
+        have = self.alphamask if self.dense else self._have
+        cells = cells[~have[cells]]
+        if len(cells) == 0:
+            return
+        cells = np.unique(cells)
         cells = cells[cells < self.geo.nc]
         if self.dense:
-            cells = cells[~self.alphamask[cells]]
             for lo in range(0, len(cells), chunk):
                 c = cells[lo:lo + chunk]
                 cols = self._coeff_columns(c, exact_gemv)
@@ -290,6 +299,7 @@ class OracleInterp:
                     cols = self._coeff_columns(new[lo:lo + chunk], exact_gemv)
                     for k in cols:
                         parts[k].append(cols[k])
+                self._have[new] = True
                 allc = np.concatenate([self._cells, new])
                 order = np.argsort(allc, kind="stable")
                 self._cells = allc[order]
