@@ -353,8 +353,14 @@ class OracleInterp:
             vec = np.transpose(np.array([np.ones(N), u, u ** 2, u ** 3]))
             dvec = np.transpose(np.array([np.zeros(N), np.ones(N), 2 * u, 3 * u ** 2]))
             reps_inner, reps_outer = 4 ** a, 4 ** (d - 1 - a)
-            val.append(np.tile(np.repeat(vec, reps_inner, axis=1), reps_outer))
-            der.append(np.tile(np.repeat(dvec, reps_inner, axis=1), reps_outer))
+
+            def expand(m):      # np.tile(np.repeat(m, inner, axis=1), outer) without the no-op copies
+                if reps_inner > 1:
+                    m = np.repeat(m, reps_inner, axis=1)
+                return np.tile(m, reps_outer) if reps_outer > 1 else m
+
+            val.append(expand(vec))
+            der.append(expand(dvec))
         return val, der
 
     @staticmethod
