@@ -172,6 +172,48 @@ def test_golden_single_point_queries(name, d, modes):
                 obj.Query(far)
 
 
+def test_example_script_flow_through_dropin_import_path(tmp_path):
+    """Configs 1/2/4: the reference example scripts' flow (CSV field -> tricubic/quadcubic -> single point
+    + 20-point line; scalar, then vector mode='both') on synthetic stand-in fields, checked against the oracle."""
+    import importlib.util
+    import os
+    from conftest import ROOT
+    from oracle.arb_oracle import OracleInterp
+
+    def load(name):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "examples", name + ".py"))
+        mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+        return mod
+
+    make, runner = load("make_example_fields"), load("run_examples")
+    folder = str(tmp_path / "ExampleFields")
+    make.main(folder)
+    from arbinterp_b200 import quadcubic, tricubic
+    from arbinterp_b200.io import load_field_csv
+    for cls, d, stem in ((tricubic, 3, "3D"), (quadcubic, 4, "4D")):
+        out = runner.run(cls, d, folder, stem)
+        coords = np.zeros((20, d))
+        for a in range(3):
+            coords[:, a] = np.linspace(-2e-3, 2e-3, 20)
+        if d == 4:
+            coords[:, 3] = np.linspace(-3e-6, 3e-6, 20)
+        fs = load_field_csv(os.path.join(folder, f"Example{stem}ScalarField.csv"))
+        fv = load_field_csv(os.path.join(folder, f"Example{stem}VectorField.csv"))
+        n_ref, g_ref = OracleInterp(fs, d).query(coords.copy())
+        ora = OracleInterp(fv, d, mode="both")
+        c_ref, n2_ref, g2_ref = ora.query(coords.copy())
+        h = np.array(ora.geo.h)
+        s = np.abs(fs[:, d]).max()
+        assert not np.isnan(n_ref).any(), "the example line must lie inside the stand-in volume"
+        assert_parity(out["scalar_line"][0], n_ref, s, RTOL, stem + " scalar line norms")
+        assert_parity(out["scalar_line"][1], g_ref, s / h[None, :], RTOL, stem + " scalar line grads")
+        assert_parity(out["vector_line"][0], c_ref, np.abs(fv[:, d:]).max(axis=0)[None, :], RTOL, stem + " comps")
+        assert_parity(out["vector_line"][1], n2_ref, s, RTOL, stem + " norms")
+        assert_parity(out["vector_line"][2], g2_ref, s / h[None, :], RTOL, stem + " grads")
+        assert_parity(out["scalar_single"][0], n_ref[3, 0], s, RTOL, stem + " single norm")
+        assert_parity(out["vector_single"][0], c_ref[3], np.abs(fv[:, d:]).max(axis=0), RTOL, stem + " single comps")
+
+
 def test_norm_plane_bit_exact_on_gpu():
     """Bn = ||(Bx,By,Bz)|| (A.py:58, 74): same products, same sum order, IEEE sqrt -> identical bits."""
     from arbinterp_b200.ingest import ingest_field, norm_plane

@@ -77,6 +77,17 @@ def test_ingest_warns_on_irregular_spacing():
         ingest_field(load_golden("tri_12x10x9")["field"], 3)   # linspace grids pass
 
 
+def test_csv_loader_matches_genfromtxt(tmp_path):
+    """arbinterp_b200.io.load_field_csv == np.genfromtxt(delimiter=',') on the reference's file format."""
+    from arbinterp_b200.io import load_field_csv, save_field_csv
+    g = load_golden("tri_12x10x9")
+    path = str(tmp_path / "field.csv")
+    save_field_csv(path, g["field"])
+    a = load_field_csv(path)
+    assert a.dtype == np.float64 and a.flags.c_contiguous
+    assert np.array_equal(a, np.genfromtxt(path, delimiter=",")) and np.array_equal(a, g["field"])   # %.18e round-trips
+
+
 # ----------------------------------------------------------------------------------------- C-ABI
 def _declared_functions():
     text = open(os.path.join(ROOT, "include", "arbinterp_b200.h")).read()
