@@ -42,6 +42,28 @@ class FieldError(ValueError):
     pass
 
 
+@dataclass
+class IngestedField:
+    """Result of :func:`ingest_field`, accepted by the ``tricubic`` / ``quadcubic`` constructors in place of
+    the raw rows (multi-GPU construction ingests once and broadcasts this, see ``sharding``)."""
+    planes: torch.Tensor       # [ncols-d][n_{d-1}]..[n_0] raw value planes
+    geo: Geometry
+
+    @property
+    def ncols(self) -> int:
+        return self.geo.d + int(self.planes.shape[0])
+
+
+def geometry_from_axes(axes) -> Geometry:
+    """Geometry from the sorted distinct coordinates per axis -- the same expressions as in
+    :func:`ingest_field` (A.py:541-556), so every rank derives bit-identical numbers from broadcast axes."""
+    d = len(axes)
+    npts = [int(a.numel()) for a in axes]
+    h = [float(torch.abs(a[0] - a[1])) for a in axes]
+    return Geometry(d=d, npts=npts, ncell=[n - 3 for n in npts], h=h, int_min=[float(a[1]) for a in axes],
+                    int_max=[float(a[-2]) for a in axes], axes=list(axes))
+
+
 def ingest_field(field, d: int, device=None, spacing_rtol: float = 1e-6):
     """Return ``(planes, geometry)``.
 

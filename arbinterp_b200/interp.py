@@ -29,7 +29,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .ingest import ingest_field, norm_plane, sorted_field
+from .ingest import IngestedField, ingest_field, norm_plane, sorted_field
 
 __version__ = "1.8"   # API level of the reference this mirrors (A.py:6)
 
@@ -57,15 +57,19 @@ class _CubicInterpolator:
         d = self._d
         self.eps = 10 * np.finfo(float).eps                      # A.py:11 (never used there either)
         quiet = ("quiet" in args) or bool(kwargs.get("quiet", False))
-        shape = getattr(field, "shape", None)
-        if shape is None or len(shape) != 2 or shape[1] not in (d + 1, d + 3):
+        pre = field if isinstance(field, IngestedField) else None
+        shape = (0, pre.ncols) if pre is not None else getattr(field, "shape", None)
+        if shape is None or len(shape) != 2 or shape[1] not in (d + 1, d + 3) or (pre is not None and pre.geo.d != d):
             sys.exit(f"--- Input not shaped as expected - should be N x {d + 1} or N x {d + 3} ---")  # A.py:104, 723
         self._device = _cuda_device(kwargs.get("device"))
         self._lib = _lib.load()
         slab = kwargs.get("slab")                                # (lo, hi) cell layers of the slowest axis
         self._reference_quirk = not bool(kwargs.get("fixed_d4", False))
 
-        planes, geo = ingest_field(field, d, device=self._device)
+        if pre is not None:
+            planes, geo = pre.planes.to(self._device), pre.geo
+        else:
+            planes, geo = ingest_field(field, d, device=self._device)
         self._geo = geo
         scalar = shape[1] == d + 1
         banner = None

@@ -2,8 +2,9 @@
 broadcast and query routing.  Nothing here is on the per-query compute path -- a rank's queries are
 evaluated by its local table with no collective; the only exchanges are
 
-  * construction: one broadcast of the raw field (NCCL over NVLink), after which every rank
-    builds its replica or its slab locally (cheaper than moving a 25-400 GB table), and
+  * construction: the source rank ingests the rows once; the dense value planes (+ axes) are broadcast
+    over NCCL/NVLink and every rank builds its replica or its slab locally (cheaper than moving a
+    25-400 GB table), and
   * slab-sharded tables only: one all-to-all that moves each query row to the rank owning its
     slowest-axis cell layer, and one that returns the result rows.
 
@@ -97,6 +98,35 @@ def broadcast_field(field, src: int = 0, device=None, group=None) -> torch.Tenso
     return t
 
 
+def broadcast_ingested(field, d: int, src: int = 0, device=None, group=None):
+    """Construction-time replicate, done right: rank ``src`` ingests the raw rows once (sort-free grid
+    indexing + scatter into dense planes), then the per-axis coordinates and the dense value planes are
+    broadcast (NCCL over NVLink) -- 1/(d+C) .. 1/2 of the raw rows' bytes, and no rank repeats the ingest.
+    Returns an :class:`~arbinterp_b200.ingest.IngestedField` on every rank; geometry is derived from the
+    broadcast axes with the same expressions everywhere, so it is bit-identical across ranks."""
+    import torch.distributed as dist
+    from .ingest import IngestedField, geometry_from_axes, ingest_field
+    rank = dist.get_rank(group)
+    meta = torch.zeros(2 + d, dtype=torch.int64, device=device)
+    if rank == src:
+        planes, geo = ingest_field(field, d, device=device)
+        meta[0], meta[1] = 1, planes.shape[0]
+        meta[2:] = torch.tensor(geo.npts, dtype=torch.int64)
+        axes = torch.cat(geo.axes).contiguous()
+    dist.broadcast(meta, src=src, group=group)
+    ncomp, npts = int(meta[1]), [int(v) for v in meta[2:]]
+    if rank != src:
+        axes = torch.empty(sum(npts), dtype=torch.float64, device=device)
+        planes = torch.empty([ncomp] + npts[::-1], dtype=torch.float64, device=device)
+    dist.broadcast(axes, src=src, group=group)
+    dist.broadcast(planes, src=src, group=group)
+    per_axis, off = [], 0
+    for n in npts:
+        per_axis.append(axes[off:off + n].clone())
+        off += n
+    return IngestedField(planes=planes, geo=geometry_from_axes(per_axis))
+
+
 class SlabShardedInterp:
     """A tricubic/quadcubic whose coefficient table is sharded over the ranks by slowest-axis
     slabs (config 5: 96^3 x 64 'both' = 402 GB over 8 GPUs).  ``Query`` takes this rank's rows and
@@ -107,9 +137,9 @@ class SlabShardedInterp:
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         device = kwargs.get("device") or torch.device("cuda", torch.cuda.current_device())
-        full = broadcast_field(field, src=src, device=device, group=group)
         d = cls._d
-        n_slow = int(torch.unique(full[:, d - 1]).numel()) - 3
+        full = broadcast_ingested(field, d, src=src, device=device, group=group)
+        n_slow = full.geo.ncell[d - 1]
         self.slabs = plan_slabs(n_slow, self.world)
         lo, hi = self.slabs[self.rank]
         if hi == lo:

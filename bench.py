@@ -307,12 +307,10 @@ def run_b200(args):
     # ---- construction (untimed): rank 0 makes the field, NCCL broadcast, every rank builds its replica
     n = args.grid
     t0 = time.perf_counter()
-    if rank == 0:
-        _, rows = analytic_field_rows(torch, n, device)
-    else:
-        rows = torch.empty(n ** 3, 6, dtype=torch.float64, device=device)
+    rows = analytic_field_rows(torch, n, device)[1] if rank == 0 else None
     if dist is not None:
-        dist.broadcast(rows, src=0)
+        from arbinterp_b200.sharding import broadcast_ingested
+        rows = broadcast_ingested(rows, 3, src=0, device=device)     # ingest once, NCCL-broadcast the planes
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     obj = tricubic(rows, "quiet", mode=args.mode)

@@ -215,6 +215,32 @@ def _routing_worker(rank, world, port, field, q_all, out_dir):
     dist.destroy_process_group()
 
 
+def _bcast_worker(rank, world, port, field, out_dir):
+    import torch.distributed as dist
+    from arbinterp_b200.sharding import broadcast_ingested
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    got = broadcast_ingested(field if rank == 0 else None, 4, src=0)
+    g = got.geo
+    np.savez(os.path.join(out_dir, f"ing{rank}.npz"), planes=got.planes.numpy(), h=g.h, lo=g.int_min, hi=g.int_max, npts=g.npts)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_broadcast_ingested_world2_gloo(tmp_path):
+    """Ingest once on rank 0, broadcast axes + dense planes: every rank ends up with the planes and the
+    bit-identical geometry a local ingest of the raw rows would give."""
+    import torch.multiprocessing as mp
+    g = load_golden("quad_8x7x7x6")
+    mp.spawn(_bcast_worker, args=(2, _free_port(), g["field"], str(tmp_path)), nprocs=2, join=True)
+    planes, geo = ingest_field(g["field"], 4)
+    for rank in range(2):
+        z = np.load(tmp_path / f"ing{rank}.npz")
+        assert np.array_equal(z["planes"], planes.numpy()) and list(z["npts"]) == geo.npts
+        assert list(z["h"]) == geo.h and list(z["lo"]) == geo.int_min and list(z["hi"]) == geo.int_max
+
+
 def test_query_routing_world2_gloo(tmp_path):
     """World-size-2 exchange on CPU: every row reaches the rank owning its t-layer and the results
     come back in the caller's order, identical to a single-process evaluation."""
