@@ -163,3 +163,37 @@ extern "C" int arb_push(const arb_geom* g, const double* table, int mode, double
     if (g->d == 3) return launch_push<3>(P, N, (cudaStream_t)stream);
     return launch_push<4>(P, N, (cudaStream_t)stream);
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Row permutation for the slab-sharded routing path (sharding.exchange_and_query): query rows are 24/32
+// bytes and result rows 24..64 bytes; torch's row-gather kernel moves them at ~60 GB/s (one tiny block
+// per row), which cost more than the NVLink exchange itself.  One thread per double keeps it at HBM speed.
+// ---------------------------------------------------------------------------------------------------
+namespace arb {
+template <bool SCATTER>
+__global__ void permute_rows_kernel(double* __restrict__ dst, const double* __restrict__ src,
+                                    const int64_t* __restrict__ order, int64_t n, int width) {
+    const int64_t total = n * width;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = e / width;
+        const int col = (int)(e - row * width);
+        const int64_t other = order[row];
+        if (SCATTER) dst[other * width + col] = src[e];
+        else dst[e] = src[other * width + col];
+    }
+}
+}  // namespace arb
+
+extern "C" int arb_permute_rows(double* dst, const double* src, const int64_t* order, int64_t n, int width,
+                                int scatter, void* stream) {
+    using namespace arb;
+    if (n < 0 || width < 1 || (n > 0 && (!dst || !src || !order))) { set_error("arb_permute_rows: bad arguments"); return 1; }
+    if (n == 0) return 0;
+    const int64_t total = n * width;
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    if (scatter) permute_rows_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dst, src, order, n, width);
+    else permute_rows_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dst, src, order, n, width);
+    return check_cuda(cudaGetLastError(), "permute_rows_kernel launch");
+}

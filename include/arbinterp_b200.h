@@ -126,6 +126,12 @@ int arb_query_grid_host(const arb_geom* g, const double* grid, int64_t pitch_x, 
 int arb_push(const arb_geom* g, const double* table, int mode, double* pos, double* vel, int64_t N, double dt,
              int64_t nsteps, double kappa, const double* gravity, unsigned long long* lost_count, void* stream);
 
+/* Row permutation used by the slab-sharded routing path (no counterpart in the single-process reference):
+ * gather  (scatter == 0): dst[i][:] = src[order[i]][:];  scatter (scatter != 0): dst[order[i]][:] = src[i][:].
+ * Rows are `width` doubles; all pointers are device pointers. */
+int arb_permute_rows(double* dst, const double* src, const int64_t* order, int64_t n, int width, int scatter,
+                     void* stream);
+
 /* Tuning knob for experiments/benchmarks: selects the query-kernel variant
  * (0 = default).  Returns the previous value. */
 int arb_set_query_variant(int variant);

@@ -93,6 +93,13 @@ def main():
                   float((norm[:, 0] - want).abs().max()),
                   float(((grad - gradP(x, y, z, t)).abs() * torch.tensor(g.h, device=dev)).max()))
         worst = max(worst, err)
+    if os.environ.get("ARB_PROFILE_ROUTING") and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            obj.Query(q); torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=22, max_name_column_width=60), flush=True)
+    elif os.environ.get("ARB_PROFILE_ROUTING"):
+        obj.Query(q); torch.cuda.synchronize()
     w = torch.tensor([worst], dtype=torch.float64, device=dev)
     dist.all_reduce(w, op=dist.ReduceOp.MAX)
     tb = torch.tensor([table_gb], dtype=torch.float64, device=dev)
