@@ -29,12 +29,12 @@ namespace arb {
 // coefficients each) for all MT m-tiles, so a thread holds MT*NT_W*2 FP64 accumulators.  Smaller
 // tiles trade halo re-reads (served by L2) for more resident warps per SM, which is what keeps the
 // DMMA pipe busy while other CTAs are in their TMA / stencil / store phases.
-struct Cfg3A { static constexpr int D = 3, TX = 8, TY = 4, TZ = 4, TT = 1, WARPS = 4, NT_W = 2, MINB = 3; };
-struct Cfg3B { static constexpr int D = 3, TX = 8, TY = 4, TZ = 2, TT = 1, WARPS = 4, NT_W = 2, MINB = 5; };
-struct Cfg3C { static constexpr int D = 3, TX = 8, TY = 2, TZ = 2, TT = 1, WARPS = 4, NT_W = 2, MINB = 6; };
-struct Cfg4A { static constexpr int D = 4, TX = 8, TY = 2, TZ = 2, TT = 2, WARPS = 8, NT_W = 4, MINB = 1; };
-struct Cfg4B { static constexpr int D = 4, TX = 8, TY = 2, TZ = 2, TT = 1, WARPS = 8, NT_W = 4, MINB = 2; };
-struct Cfg4C { static constexpr int D = 4, TX = 8, TY = 2, TZ = 1, TT = 1, WARPS = 8, NT_W = 4, MINB = 3; };
+struct Cfg3A { static constexpr int D = 3, TX = 8, TY = 4, TZ = 4, TT = 1, WARPS = 4, NT_W = 2, MINB = 3, MINB_KRON = 6; };
+struct Cfg3B { static constexpr int D = 3, TX = 8, TY = 4, TZ = 2, TT = 1, WARPS = 4, NT_W = 2, MINB = 5, MINB_KRON = 6; };
+struct Cfg3C { static constexpr int D = 3, TX = 8, TY = 2, TZ = 2, TT = 1, WARPS = 4, NT_W = 2, MINB = 6, MINB_KRON = 8; };
+struct Cfg4A { static constexpr int D = 4, TX = 8, TY = 2, TZ = 2, TT = 2, WARPS = 8, NT_W = 4, MINB = 1, MINB_KRON = 3; };
+struct Cfg4B { static constexpr int D = 4, TX = 8, TY = 2, TZ = 2, TT = 1, WARPS = 8, NT_W = 4, MINB = 2, MINB_KRON = 3; };
+struct Cfg4C { static constexpr int D = 4, TX = 8, TY = 2, TZ = 1, TT = 1, WARPS = 8, NT_W = 4, MINB = 3, MINB_KRON = 4; };
 
 template <typename Cfg>
 struct BuildShape {
@@ -62,6 +62,7 @@ struct BuildParams {
     int ncomp;
     int quirk;
     unsigned char type_of_mask[16];   // derivative-axis bitmask -> b-vector type index (A.py:118-125 order)
+    unsigned long long type_nibbles;  // the same map packed 4 bits per mask (register-only lookup)
 };
 
 // Central differences of one grid point over its 3x3x3 neighbourhood, all 8 axis subsets at once:
@@ -223,6 +224,222 @@ build_kernel(const __grid_constant__ CUtensorMap tmap, const BuildParams p) {
     }
 }
 
+// ======================================================================================
+// Kronecker-factored solve (build variant 3)
+// ======================================================================================
+// inv(B) is a Kronecker product of the 1-D cubic Hermite inverse H (4x4, integer):
+//     alpha[kl][ji] = sum_{s_hi, s_lo} G_hi[kl][s_hi] * G_lo[ji][s_lo] * b[s_hi][s_lo]
+// with "lo" = the (x, y) pair, "hi" = z (3-D) or the (z, t) pair (4-D), s_a = 2*(differentiated along a)
+// + (corner bit along a), G_lo[i+4j][sx+4sy] = H[i][sx] H[j][sy] and G_hi likewise.  The solve then is two
+// batched dense contractions with 4x4 / 16x16 blocks instead of one with a 64x64 / 256x256 block:
+//   step A  U[cell][kl][s_lo]  = sum_{s_hi} b[cell][s_hi][s_lo] * G_hi^T      rows (cell, s_lo), K = s_hi
+//   step B  alpha[cell][kl][ji] = sum_{s_lo} U[cell][kl][s_lo]  * G_lo^T      rows (cell, kl),   K = s_lo
+// 6 DMMAs per 3-D cell instead of 16, 32 per 4-D cell instead of 256, no inv(B) traffic at all (the
+// fragments of G_hi and G_lo are built from H in registers), ~40 registers per thread.  After the stencil
+// stage the warps are independent: each owns a share of the tile's cells and a private U buffer, so the
+// solve needs no block-level barrier.  Same b-vector gather as the dense kernel (including the A.py:860
+// quirk), same table layout, results equal to round-off (different summation order).
+__constant__ double c_H[16] = {1, 0, 0, 0, 0, 0, 1, 0, -3, 3, -2, -1, 2, -2, 1, 1};   // H[i][s], s = (f0, f1, f0', f1')
+
+template <typename Cfg>
+struct KronShape {
+    using S = BuildShape<Cfg>;
+    static constexpr int D = Cfg::D;
+    static constexpr int NHI = (D == 3) ? 4 : 16;          // size of the "hi" index (k or (k,l))
+    static constexpr int GC = (D == 3) ? 4 : 1;            // cells per warp pass
+    static constexpr int KS_A = NHI / 4, NT_A = (NHI + 7) / 8;
+    static constexpr int MT_A = GC * 2;                    // 16 s_lo rows per cell
+    static constexpr int MT_B = GC * NHI / 8;
+    static constexpr int US = 16;                          // s_lo pitch of U; columns are XOR-swizzled by the row
+    static constexpr int U_PER_WARP = GC * NHI * US;
+    static constexpr int NCELL = Cfg::TX * Cfg::TY * Cfg::TZ * Cfg::TT;
+    // Derivative fields are stored by dm = fx | fz<<1 | fy<<2 | ft<<3 with a pitch == 4 (mod 16) doubles: the 16
+    // lanes of a half-warp of a step-A gather differ in (fx, bit_x, fz, bit_z) only, and dm*KTS + bit_x +
+    // bit_z*(PY*PXS) then hits 16 distinct 8-byte bank pairs (PY*PXS == 2 or 14 mod 16 for the tiles used).
+    static constexpr int KTS = ((S::TYPE_STRIDE + 11) / 16) * 16 + 4;
+    static constexpr int DERIV_K = KTS * S::NTYPE;
+    static_assert(KTS >= S::TYPE_STRIDE, "padded pitch too small");
+    static constexpr size_t SMEM = (size_t)(S::GRID_ELEMS + DERIV_K + Cfg::WARPS * U_PER_WARP) * 8 + 128;
+};
+
+template <typename Cfg>
+__global__ void __launch_bounds__(BuildShape<Cfg>::THREADS, Cfg::MINB_KRON)
+build_kron_kernel(const __grid_constant__ CUtensorMap tmap, const BuildParams p) {
+    using S = BuildShape<Cfg>;
+    using K = KronShape<Cfg>;
+    constexpr int D = Cfg::D;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* gtile = reinterpret_cast<double*>(smem_raw);
+    double* deriv = gtile + S::GRID_ELEMS;
+    double* ubase = deriv + K::DERIV_K;
+    __shared__ uint64_t bar;
+
+    int64_t tl = blockIdx.x;
+    const int64_t tx = tl % p.ntile[0]; tl /= p.ntile[0];
+    const int64_t ty = tl % p.ntile[1]; tl /= p.ntile[1];
+    const int64_t tz = (D == 4) ? tl % p.ntile[2] : tl;
+    const int64_t tt = (D == 4) ? tl / p.ntile[2] : 0;
+    const int comp = blockIdx.y;
+    const int x0 = (int)(tx * Cfg::TX), y0 = (int)(ty * Cfg::TY), z0 = (int)(tz * Cfg::TZ), t0 = (int)(tt * Cfg::TT);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+        mbar_expect_tx(&bar, S::GRID_ELEMS * 8);
+        if (D == 3) tma_load_4d(gtile, &tmap, &bar, x0, y0, z0, comp);
+        else tma_load_5d(gtile, &tmap, &bar, x0, y0, z0, t0, comp);
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+
+    // ---- stencil stage: one thread per corner point, all 2^D derivative types in registers ----
+    // corner point (px,py,pz,pt) of the tile sits at grid-tile coordinate (+1,+1,+1,+1)
+    for (int e = threadIdx.x; e < S::NPOINT; e += S::THREADS) {
+        int r = e;
+        const int px = r % S::PX; r /= S::PX;
+        const int py = r % S::PY; r /= S::PY;
+        const int pz = r % S::PZ;
+        const int pt = r / S::PZ;
+        constexpr int SX = 1, SY = S::GX, SZ = S::GX * S::GY, ST = S::GX * S::GY * S::GZ;
+        const int centre = (((D == 4 ? (pt + 1) : 0) * S::GZ + (pz + 1)) * S::GY + (py + 1)) * S::GX + (px + 1);
+        double* dst = deriv + ((pt * S::PZ + pz) * S::PY + py) * S::PXS + px;
+        if (D == 3) {
+            double o[8];
+            stencil_cube(gtile + centre, SX, SY, SZ, o);
+#pragma unroll
+            for (int m = 0; m < 8; ++m) dst[((m & 1) | (((m >> 2) & 1) << 1) | (((m >> 1) & 1) << 2)) * K::KTS] = o[m];
+        } else {
+            double lo[8], mid[8], hi[8];
+            stencil_cube(gtile + centre - ST, SX, SY, SZ, lo);
+            stencil_cube(gtile + centre, SX, SY, SZ, mid);
+            stencil_cube(gtile + centre + ST, SX, SY, SZ, hi);
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const int dm = (m & 1) | (((m >> 2) & 1) << 1) | (((m >> 1) & 1) << 2);
+                dst[dm * K::KTS] = mid[m];
+                dst[(dm | 8) * K::KTS] = 0.5 * (hi[m] - lo[m]);
+            }
+        }
+    }
+    __syncthreads();
+
+
+    // ---- constant fragments (B operands): element [k = 4*ks + q][n = 8*nt + r], q = lane&3, r = lane>>2 ----
+    const int q = lane & 3, r = lane >> 2;
+    double bA[K::KS_A][K::NT_A], bB[4][2];
+#pragma unroll
+    for (int ks = 0; ks < K::KS_A; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < K::NT_A; ++nt) {
+            const int shi = 4 * ks + q, kl = 8 * nt + r;             // G_hi[kl][s_hi]
+            double v = (kl < K::NHI) ? c_H[(kl & 3) * 4 + (shi & 3)] : 0.0;
+            if (D == 4) v *= c_H[((kl >> 2) & 3) * 4 + (shi >> 2)];
+            bA[ks][nt] = v;
+        }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            const int slo = 4 * ks + q, ji = 8 * nt + r;             // G_lo[ji][s_lo]
+            bB[ks][nt] = c_H[(ji & 3) * 4 + (slo & 3)] * c_H[(ji >> 2) * 4 + (slo >> 2)];
+        }
+
+    // ---- per-lane gather offsets of the b-vector element [s_hi = 4ks + q][s_lo = 8*half + r] ----
+    // s = 2*flag + bit per axis; type = type_of_mask[flags]; the point is the cell corner + bits
+    int lo_off[2], lo_mask[2], lo_c[2];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int slo = 8 * half + r, sx = slo & 3, sy = slo >> 2;
+        lo_mask[half] = (sx >> 1) | ((sy >> 1) << 2);             // dm bit layout: fx | fz<<1 | fy<<2 | ft<<3
+        lo_off[half] = (sy & 1) * S::PXS + (sx & 1);
+        lo_c[half] = (sx & 1) | ((sy & 1) << 1);
+    }
+    int hi_off[K::KS_A], hi_mask[K::KS_A], hi_c[K::KS_A];
+#pragma unroll
+    for (int ks = 0; ks < K::KS_A; ++ks) {
+        const int shi = 4 * ks + q, sz = shi & 3, st = shi >> 2;
+        hi_mask[ks] = ((sz >> 1) << 1) | ((st >> 1) << 3);
+        hi_off[ks] = ((st & 1) * S::PZ + (sz & 1)) * S::PY * S::PXS;
+        hi_c[ks] = ((sz & 1) << 2) | ((st & 1) << 3);
+    }
+    double* U = ubase + warp * K::U_PER_WARP;
+
+    for (int g = warp; g < K::NCELL / K::GC; g += Cfg::WARPS) {
+        const int c0 = g * K::GC;
+        // ---- step A: rows (cell, s_lo), K = s_hi, N = kl ----
+#pragma unroll
+        for (int ma = 0; ma < K::MT_A; ++ma) {
+            const int ci = c0 + (ma >> 1), half = ma & 1;
+            const int cx = ci % Cfg::TX, cy = (ci / Cfg::TX) % Cfg::TY, cz = (ci / (Cfg::TX * Cfg::TY)) % Cfg::TZ,
+                      ct = ci / (Cfg::TX * Cfg::TY * Cfg::TZ);
+            const int cell_off = ((ct * S::PZ + cz) * S::PY + cy) * S::PXS + cx;
+            double acc[K::NT_A][2];
+#pragma unroll
+            for (int nt = 0; nt < K::NT_A; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < K::KS_A; ++ks) {
+                const int mask = lo_mask[half] | hi_mask[ks];
+                double a;
+                if (D == 4 && p.quirk && mask == 15) {
+                    // A.py:860: b[240 + c] = stencil at corner c-1, b[240] = 0
+                    const int c = (lo_c[half] | hi_c[ks]) - 1;
+                    const int off = (((c >> 3) & 1) * S::PZ + ((c >> 2) & 1)) * S::PY * S::PXS + ((c >> 1) & 1) * S::PXS + (c & 1);
+                    a = (c < 0) ? 0.0 : deriv[15 * K::KTS + cell_off + off];
+                } else {
+                    a = deriv[mask * K::KTS + cell_off + lo_off[half] + hi_off[ks]];
+                }
+#pragma unroll
+                for (int nt = 0; nt < K::NT_A; ++nt) dmma_884(acc[nt][0], acc[nt][1], a, bA[ks][nt]);
+            }
+            // C[row = s_lo = 8*half + r][col = kl = 8*nt + 2q + {0,1}]  ->  U[cell][kl][s_lo ^ swz(kl)].
+            // swz(kl) = 4*((kl ^ kl>>1) & 3) makes both this store (lanes differ in q and r) and the step-B
+            // load (lanes differ in kl = row and in s_lo & 3) hit 16 distinct bank pairs per half-warp.
+#pragma unroll
+            for (int nt = 0; nt < K::NT_A; ++nt) {
+                const int kl = 8 * nt + 2 * q;
+                if (kl < K::NHI) {
+                    double* dst = U + ((ma >> 1) * K::NHI + kl) * K::US;
+                    const int col = 8 * half + r;
+                    dst[col ^ (4 * ((kl ^ (kl >> 1)) & 3))] = acc[nt][0];
+                    dst[K::US + (col ^ (4 * (((kl + 1) ^ ((kl + 1) >> 1)) & 3)))] = acc[nt][1];
+                }
+            }
+        }
+        __syncwarp();
+        // ---- step B: rows (cell, kl), K = s_lo, N = ji ----
+#pragma unroll
+        for (int mb = 0; mb < K::MT_B; ++mb) {
+            const int R = mb * 8 + r;                         // row within the group
+            const int cg = R / K::NHI, kl = R % K::NHI;
+            double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+            const double* urow = U + (cg * K::NHI + kl) * K::US;
+            const int swz = 4 * ((kl ^ (kl >> 1)) & 3);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const double a = urow[(4 * ks + q) ^ swz];
+                dmma_884(acc[0][0], acc[0][1], a, bB[ks][0]);
+                dmma_884(acc[1][0], acc[1][1], a, bB[ks][1]);
+            }
+            const int ci = c0 + cg;
+            const int64_t gx = x0 + ci % Cfg::TX, gy = y0 + (ci / Cfg::TX) % Cfg::TY,
+                          gz = z0 + (ci / (Cfg::TX * Cfg::TY)) % Cfg::TZ, gt = t0 + ci / (Cfg::TX * Cfg::TY * Cfg::TZ);
+            bool ok = (gx < p.nc[0]) && (gy < p.nc[1]) && (gz < p.nc[2]);
+            int64_t cell = gx + p.nc[0] * (gy + p.nc[1] * gz);
+            if (D == 4) {
+                ok = ok && (gt < p.nc[3]);
+                cell += p.nc[0] * p.nc[1] * p.nc[2] * gt;
+            }
+            if (ok) {
+                double* dst = p.table + (cell * p.ncomp + comp) * S::NM + kl * 16 + 2 * q;
+                stg_stream_d2(dst, acc[0][0], acc[0][1]);
+                stg_stream_d2(dst + 8, acc[1][0], acc[1][1]);
+            }
+        }
+        __syncwarp();
+    }
+}
+
 __global__ void fill_nan_kernel(double* p, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = __longlong_as_double(0x7ff8000000000000LL);
@@ -276,7 +493,7 @@ static int get_bfrag(int d, const double** out) {
 
 static int g_build_variant = 0;
 
-template <typename Cfg>
+template <typename Cfg, bool KRON = false>
 static int build_impl(const double* grid, int ncomp, const int64_t* n, double* table, int quirk, cudaStream_t st) {
     using S = BuildShape<Cfg>;
     constexpr int D = Cfg::D;
@@ -298,7 +515,10 @@ static int build_impl(const double* grid, int ncomp, const int64_t* n, double* t
     for (int a = D; a < 4; ++a) { p.nc[a] = 1; p.ntile[a] = 1; }
     if (ntiles > 0x7fffffffLL) { set_error("arb_build_coeffs: too many tiles (%lld)", (long long)ntiles); return 1; }
     p.table = table; p.ncomp = ncomp; p.quirk = quirk;
-    for (int r = 0; r < (1 << D); ++r) p.type_of_mask[deriv_mask(D, r)] = (unsigned char)r;
+    for (int r = 0; r < (1 << D); ++r) {
+        p.type_of_mask[deriv_mask(D, r)] = (unsigned char)r;
+        p.type_nibbles |= (unsigned long long)r << (4 * deriv_mask(D, r));
+    }
     { const int frc = get_bfrag(D, &p.bfrag); if (frc) return frc; }
 
     // TMA needs 16-byte global strides: pad odd nx to even in a scratch copy
@@ -347,10 +567,16 @@ static int build_impl(const double* grid, int ncomp, const int64_t* n, double* t
         for (int i = 0; i < 16; ++i) fprintf(stderr, " %016llx", w[i]);
         fprintf(stderr, "\n");
     }
-    auto k = build_kernel<Cfg>;
-    ARB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
     dim3 gridDim((unsigned)ntiles, (unsigned)ncomp, 1);
-    k<<<gridDim, S::THREADS, S::SMEM, st>>>(tmap, p);
+    if (KRON) {
+        auto k = build_kron_kernel<Cfg>;
+        ARB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KronShape<Cfg>::SMEM));
+        k<<<gridDim, S::THREADS, KronShape<Cfg>::SMEM, st>>>(tmap, p);
+    } else {
+        auto k = build_kernel<Cfg>;
+        ARB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
+        k<<<gridDim, S::THREADS, S::SMEM, st>>>(tmap, p);
+    }
     ARB_CUDA(cudaGetLastError());
     const int64_t tail = (int64_t)ncomp * S::NM;
     fill_nan_kernel<<<(unsigned)((tail + 255) / 256), 256, 0, st>>>(table + ncell * tail, tail);
@@ -369,16 +595,21 @@ int arb_build_coeffs(int d, const double* grid, int ncomp, const int64_t n[4], d
     if (ncomp < 1 || ncomp > 4) { arb::set_error("arb_build_coeffs: ncomp=%d not in 1..4", ncomp); return 1; }
     cudaStream_t st = (cudaStream_t)stream;
     const int v = arb::g_build_variant;
-    // defaults picked on B200 (profiles/r01_build_configs.log): 3-D 8x4x4 tiles, 4-D 8x2x2x1 tiles
+    // variant 0 (default): Kronecker-factored solve (build_kron_kernel); 1-3: the dense 4^d x 4^d contraction
+    // with different tiles (1 = its best); 4: Kronecker with the smaller tile.  profiles/r01_build_configs.log
     if (d == 3) {
-        if (v == 1) return arb::build_impl<arb::Cfg3B>(grid, ncomp, n, table, reference_quirk, st);
-        if (v == 2) return arb::build_impl<arb::Cfg3C>(grid, ncomp, n, table, reference_quirk, st);
-        return arb::build_impl<arb::Cfg3A>(grid, ncomp, n, table, reference_quirk, st);
+        if (v == 1) return arb::build_impl<arb::Cfg3A>(grid, ncomp, n, table, reference_quirk, st);
+        if (v == 2) return arb::build_impl<arb::Cfg3B>(grid, ncomp, n, table, reference_quirk, st);
+        if (v == 3) return arb::build_impl<arb::Cfg3C>(grid, ncomp, n, table, reference_quirk, st);
+        if (v == 4) return arb::build_impl<arb::Cfg3B, true>(grid, ncomp, n, table, reference_quirk, st);
+        return arb::build_impl<arb::Cfg3A, true>(grid, ncomp, n, table, reference_quirk, st);
     }
     if (d == 4) {
-        if (v == 1) return arb::build_impl<arb::Cfg4A>(grid, ncomp, n, table, reference_quirk, st);
-        if (v == 2) return arb::build_impl<arb::Cfg4C>(grid, ncomp, n, table, reference_quirk, st);
-        return arb::build_impl<arb::Cfg4B>(grid, ncomp, n, table, reference_quirk, st);
+        if (v == 1) return arb::build_impl<arb::Cfg4B>(grid, ncomp, n, table, reference_quirk, st);
+        if (v == 2) return arb::build_impl<arb::Cfg4A>(grid, ncomp, n, table, reference_quirk, st);
+        if (v == 3) return arb::build_impl<arb::Cfg4C>(grid, ncomp, n, table, reference_quirk, st);
+        if (v == 4) return arb::build_impl<arb::Cfg4B, true>(grid, ncomp, n, table, reference_quirk, st);
+        return arb::build_impl<arb::Cfg4A, true>(grid, ncomp, n, table, reference_quirk, st);
     }
     arb::set_error("arb_build_coeffs: d=%d not in {3,4}", d);
     return 1;
