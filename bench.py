@@ -47,7 +47,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=1_000_000)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--other-modes", action="store_true", help="also time vector/both (device-resident)")
+    ap.add_argument("--other-modes", action="store_true", help="(default at N=1) also time vector/both, device-resident")
+    ap.add_argument("--no-other-modes", action="store_true", help="skip the vector/both lines")
     return ap.parse_args()
 
 
@@ -352,7 +353,7 @@ def run_b200(args):
 
     # ---- other modes (device-resident), optional
     others = {}
-    if args.other_modes and rank == 0 and world == 1:
+    if not args.no_other_modes and rank == 0 and world == 1:
         del obj, outs
         torch.cuda.empty_cache()
         for m in ("vector", "both"):
@@ -366,7 +367,10 @@ def run_b200(args):
             outs2 = alloc_outputs(torch, m, d, Q2, device)
             el, per = time_device(torch, lib, o2, m, d, q[:Q2], outs2, cells[:Q2], args.steps, args.warmup)
             rate = Q2 * args.steps / el
-            others[m] = {"value": rate, "unit": "queries/s", "alg_gbs": ALG_BYTES[(d, m)] * rate / 1e9}
+            others[m] = {"value": rate, "unit": "queries/s", "alg_bytes_per_query": ALG_BYTES[(d, m)],
+                         "achieved_gbs": ALG_BYTES[(d, m)] * rate / 1e9,
+                         "frac_of_measured_hbm": ALG_BYTES[(d, m)] * rate / 1e9 / measured_peak()[0],
+                         "queries_per_step": Q2, "table_gb": o2.table.numel() * 8 / 1e9}
             del o2, outs2
             torch.cuda.empty_cache()
         _, rows = analytic_field_rows(torch, n, device)

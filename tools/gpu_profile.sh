@@ -3,7 +3,7 @@ mkdir -p gpurun_out
 python tools/fp64_peak.py > gpurun_out/fp64_peak.txt 2>&1
 # (a) launch list of the bench command
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu --queries 16777216 --e2e-queries 2097152 > gpurun_out/bench_under_ncu.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-cpu --no-other-modes --queries 16777216 --e2e-queries 2097152 > gpurun_out/bench_under_ncu.log 2>&1
 # (b) full capture of the query kernel (norm), (c) of the build kernel
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:query_block -s 1 -c 1 -o gpurun_out/prof_query_norm \
     python tools/profile_target.py --mode norm > gpurun_out/prof_query.log 2>&1
