@@ -11,13 +11,14 @@
 //      unit-cell coordinates, the rows of D, A.py:129-173 / 762-876) are evaluated at every
 //      cell-corner point of the tile and kept in shared memory.  A cell's b-vector is a gather
 //      of 2^d corners x 2^d types from these fields, so it is never materialised.
-//   3. solve stage: alpha^T[cells x 4^d] = b^T[cells x 4^d] * inv(B)^T on the FP64 tensor cores
-//      (mma.sync m8n8k4 f64, SASS DMMA).  inv(B) is integer (|entries| <= 27 / 81) and is read as
-//      pre-swizzled fragments from a small L1/L2-resident buffer; accumulators stay in
-//      registers and go straight to the cell-major table with 16-byte stores.
+//   3. solve stage: alpha = inv(B) b on the FP64 tensor cores (mma.sync m8n8k4 f64, SASS DMMA), either
+//      as ONE dense contraction alpha^T[cells x 4^d] = b^T * inv(B)^T (build_kernel; inv(B) is integer,
+//      |entries| <= 27 / 81, read as pre-swizzled fragments from an L1/L2-resident buffer) or, by default,
+//      as TWO small dense contractions that exploit inv(B) = G_hi (x) G_lo (build_kron_kernel, below).
+//      Accumulators stay in registers and go straight to the cell-major table with 16-byte stores.
 // The 4-D reference matrix carries the A.py:860 off-by-one (row 240 of D is zero and rows
-// 241..255 use the stencil centre of the previous corner); it is reproduced in the gather of
-// step 3, where the quadruple-mixed type reads corner c-1 (and 0 for c = 0).
+// 241..255 use the stencil centre of the previous corner); it is reproduced in the b-vector gather,
+// where the quadruple-mixed type reads corner c-1 (and 0 for c = 0).
 #include <cstdlib>
 #include <vector>
 #include <mutex>
