@@ -402,7 +402,16 @@ class _CubicInterpolator:
         n = work.shape[0]
         if n <= self._SMALL_ROWS:
             return self._range_host_small(query, work, direct)
-        comps, norm, grad = self._outputs(n, pinned=True)
+        # page-locked outputs let the D2H copies land directly; beyond a few GB pinning itself becomes the cost
+        # (and can fail), so very large results are ordinary arrays staged through the library's pinned ring
+        pinned = n * 8 * (3 + 1 + d) <= self._PIN_LIMIT_BYTES
+        if pinned:
+            comps, norm, grad = self._outputs(n, pinned=True)
+        else:
+            mode = self._mode
+            comps = torch.from_numpy(np.empty((n, 3))) if mode in ("vector", "both") else None
+            norm = torch.from_numpy(np.empty((n, 1))) if mode in ("norm", "both") else None
+            grad = torch.from_numpy(np.empty((n, d))) if mode in ("norm", "both") else None
         cells = torch.empty(n, dtype=torch.int64, device=self._device)   # stays in HBM; read back lazily
         with torch.cuda.device(self._device):
             chunk = int(os.environ.get("ARB_HOST_CHUNK_ROWS", "0"))
@@ -424,6 +433,7 @@ class _CubicInterpolator:
         return tuple(None if t is None else t.numpy() for t in (comps, norm, grad))
 
     _SMALL_ROWS = 8192        # same threshold as SMALL_ROWS in csrc/arb_host.cu
+    _PIN_LIMIT_BYTES = 4 << 30
 
     def _range_host_small(self, query, work, direct):
         """Latency path for short batches and single points: plain numpy outputs, one H2D, one kernel, one

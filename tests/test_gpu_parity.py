@@ -348,6 +348,15 @@ def test_device_tensor_path_and_pageable_host_path():
     for a, b in zip(host, pinned):
         assert np.array_equal(a, b, equal_nan=True)
     assert np.isnan(qp[7]).all() and np.array_equal(qp[8], q[8])
+    # results too large to pin come back as ordinary arrays staged through the library's ring
+    old_limit = type(obj)._PIN_LIMIT_BYTES
+    type(obj)._PIN_LIMIT_BYTES = 1024
+    try:
+        unpinned = obj.Query(q.copy())
+    finally:
+        type(obj)._PIN_LIMIT_BYTES = old_limit
+    for a, b in zip(host, unpinned):
+        assert np.array_equal(a, b, equal_nan=True)
     # float32 / non-contiguous input goes through a float64 copy; NaN rows are still written back
     q32 = q.astype(np.float32)
     r32 = obj.Query(q32)
