@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(THREADS) query_bulk_kernel(const QueryParams p
 // other.  DEDUP: lanes of a warp that want the same block elect one leader to fetch it and read
 // the leader's slot (warp-level binning by cell; free for clustered queries such as particle
 // bunches, one MATCH instruction of overhead for random ones).
-template <int D, int MODE, int THREADS, bool DEDUP>
+template <int D, int MODE, int THREADS, bool DEDUP, bool LOOPC = false>
 __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams p) {
     constexpr int C = MODE == 0 ? 3 : (MODE == 1 ? 1 : 4);
     constexpr int SL = (D == 4) ? 4 : 1;          // tricubic blocks per component
@@ -261,15 +261,19 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
     const int64_t warp_global = ((int64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * THREADS) >> 5;
     const int64_t nbatch = (p.N + QPW - 1) / QPW;
-    const int64_t nitem = nbatch * C;
+    // LOOPC: a work item is a batch and its components are fetched one after the other (one locate per
+    // query); otherwise (batch, component) pairs are separate items (more independent items in flight).
+    const int64_t nitem = LOOPC ? nbatch : nbatch * C;
     uint32_t phase = 0;
     for (int64_t item = warp_global; item < nitem; item += nwarps) {
-        const int64_t batch = item / C;
-        const int comp = (int)(item - batch * C);
+        const int64_t batch = LOOPC ? item : item / C;
         const int64_t n = batch * QPW + qi;
         Located<D> L;
         L.ok = false; L.masked = false; L.cell_global = 0; L.cell_local = 0;
         if (n < p.N) L = locate<D>(p, n);
+#pragma unroll 1
+      for (int ci = 0; ci < (LOOPC ? C : 1); ++ci) {
+        const int comp = LOOPC ? ci : (int)(item - batch * C);
         const int64_t blk = (L.cell_local * C + comp) * SL + sl;      // 512-byte block number in the table
         int src_lane = lane;
         bool fetch = L.ok;
@@ -322,6 +326,7 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
             }
         }
         __syncwarp();   // every lane is done with the slots before the next item's copies land
+      }
     }
 }
 
@@ -523,14 +528,14 @@ static int launch_bulk(const QueryParams& p, cudaStream_t st) {
     return check_cuda(cudaGetLastError(), "query_bulk_kernel launch");
 }
 
-template <int D, int MODE, int THREADS, bool DEDUP>
+template <int D, int MODE, int THREADS, bool DEDUP, bool LOOPC = false>
 static int launch_block(const QueryParams& p, cudaStream_t st) {
     constexpr int C = MODE == 0 ? 3 : (MODE == 1 ? 1 : 4);
     constexpr int QPW = (D == 4) ? 8 : 32;
     const size_t smem = (size_t)THREADS * 528;
-    auto k = query_block_kernel<D, MODE, THREADS, DEDUP>;
+    auto k = query_block_kernel<D, MODE, THREADS, DEDUP, LOOPC>;
     static LaunchCache cache = {};
-    const int64_t items = ((p.N + QPW - 1) / QPW) * C;
+    const int64_t items = ((p.N + QPW - 1) / QPW) * (LOOPC ? 1 : C);
     const int grid = persistent_grid(k, THREADS, smem, (items + THREADS / 32 - 1) / (THREADS / 32), cache);
     k<<<grid, THREADS, smem, st>>>(p);
     return check_cuda(cudaGetLastError(), "query_block_kernel launch");
@@ -561,7 +566,12 @@ static int dispatch_variant(const QueryParams& p, cudaStream_t st, int variant) 
         case 21: return launch_block<D, MODE, 64, true>(p, st);
         case 22: return launch_block<D, MODE, 192, true>(p, st);
         case 23: return launch_block<D, MODE, 384, true>(p, st);
-        default: return launch_block<D, MODE, 128, true>(p, st);
+        case 30: return launch_block<D, MODE, 128, true, true>(p, st);
+        default:
+            // 4-D: one locate per query and its components fetched in turn (+8 % in 'both');
+            // 3-D: (batch, component) items are independent (profiles/r01_variant_sweep.log)
+            if constexpr (D == 4) return launch_block<D, MODE, 128, true, true>(p, st);
+            else return launch_block<D, MODE, 128, true, false>(p, st);
     }
 }
 

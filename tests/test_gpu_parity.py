@@ -124,7 +124,7 @@ def test_build_tile_configurations(name, d, modes, variant, cuda_lib):
                           f"{name} alpha{k} build variant {variant}")
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 10, 11, 20, 21, 22, 23])
+@pytest.mark.parametrize("variant", [0, 1, 2, 10, 11, 20, 21, 22, 23, 30])
 @pytest.mark.parametrize("name,d,modes", CASES)
 def test_all_kernel_variants(name, d, modes, variant, cuda_lib):
     g = load_golden(name)
