@@ -304,15 +304,6 @@ static int query_host_impl(const arb_geom* g, const double* table, int64_t grid_
                                 (mode != ARB_MODE_NORM) ? out_comps_host : nullptr,
                                 (mode != ARB_MODE_VECTOR) ? out_norm_host : nullptr,
                                 (mode != ARB_MODE_VECTOR) ? out_grad_host : nullptr, out_cell_host);
-    if (chunk_rows <= 0) chunk_rows = 1 << 20;
-    if (chunk_rows > N) chunk_rows = N;
-    int dev = 0;
-    ARB_CUDA(cudaGetDevice(&dev));
-    HostCtx& ctx = g_ctx[dev & 15];
-    std::lock_guard<std::mutex> lock(ctx.mutex);
-    int rc = ensure_capacity(ctx, chunk_rows, ldq);
-    if (rc) return rc;
-
     Call c;
     c.g = g; c.mode = mode; c.d = g->d; c.q = q_host; c.ldq = ldq;
     c.comps = (mode != ARB_MODE_NORM) ? out_comps_host : nullptr;
@@ -323,6 +314,24 @@ static int query_host_impl(const arb_geom* g, const double* table, int64_t grid_
     c.comps_pinned = is_pinned(c.comps); c.norm_pinned = is_pinned(c.norm);
     c.grad_pinned = is_pinned(c.grad); c.cell_pinned = is_pinned(c.cell);
     c.cell_on_device = is_device(c.cell);
+    if (chunk_rows <= 0) {
+        // measured optima (profiles/r01_e2e_chunk_sweep.log, r01_midsize_chunks.log): 1 Mi rows when every
+        // buffer is page-locked, 256 Ki when something is staged through the ring (the staging memcpy then
+        // overlaps the copies), and never fewer than ~6 chunks so that mid-size batches pipeline at all
+        const bool all_pinned = c.q_pinned && c.comps_pinned && c.norm_pinned && c.grad_pinned &&
+                                (c.cell_pinned || c.cell_on_device);
+        const int64_t base = all_pinned ? (1 << 20) : (1 << 18);
+        int64_t sixth = (N + 5) / 6;
+        if (sixth < 65536) sixth = 65536;
+        chunk_rows = sixth < base ? sixth : base;
+    }
+    if (chunk_rows > N) chunk_rows = N;
+    int dev = 0;
+    ARB_CUDA(cudaGetDevice(&dev));
+    HostCtx& ctx = g_ctx[dev & 15];
+    std::lock_guard<std::mutex> lock(ctx.mutex);
+    int rc = ensure_capacity(ctx, chunk_rows, ldq);
+    if (rc) return rc;
 
 #define ARB_CUDA_OR_ABANDON(expr)                                  \
     do {                                                            \
