@@ -7,10 +7,12 @@
 // full-line reads in flight per SM; the FP64 arithmetic (about 70-150 DFMA per query) is
 // 10-20 % of the issue budget at roofline.
 //
-// Variants (arb_set_query_variant):
+// Variants (arb_set_query_variant; everything but 0 is kept as a measured baseline, see
+// profiles/r01_variant_sweep.log):
 //   0  BLOCK: default, see query_block_kernel below (TMA block gather, one lane per 64-coefficient
-//             block, all modes and both dimensionalities).
-//   10 COOP : G = 8 (3-D) / 32 (4-D) lanes share one query; lane l issues four 16-byte loads
+//             block, all modes and both dimensionalities).  20-23: the same with other CTA sizes /
+//             without warp de-duplication; 30: components looped inside a work item (the 4-D default).
+//   10/11 COOP : G = 8 (3-D) / 32 (4-D) lanes share one query; lane l issues four 16-byte loads
 //             that are contiguous across the group (one full 128 B line per group and
 //             instruction), evaluates its 8 coefficients and the partial sums are combined
 //             with a reduce-scatter over shuffles.  No shared memory, any block size.
@@ -46,7 +48,7 @@ __device__ __forceinline__ void store_output(const QueryParams& p, int64_t n, in
 }
 
 // ======================================================================================
-// Variant 0: cooperative sub-warp gather
+// Variants 10/11: cooperative sub-warp gather
 // ======================================================================================
 template <int D, int C, int MODE, int U>
 __global__ void __launch_bounds__(256) query_coop_kernel(const QueryParams p) {
