@@ -282,6 +282,8 @@ class _CubicInterpolator:
             raise AttributeError("inputfield is unavailable after load(): a coefficient file does not store the field")
         if self._mode in ("norm", "both") and not self._scalar_input:
             raise AttributeError("inputfield is not kept in 'norm'/'both' mode; only the interpolated planes are")
+        if getattr(self, "_table_free", False):
+            planes = planes[..., :self._geo.npts[0]]              # drop the TMA pitch padding
         return sorted_field(planes, self._geo).cpu().numpy()
 
     @property

@@ -415,6 +415,8 @@ def test_table_free_path_golden(name, modes):
         assert np.array_equal(obj.queryInds, g[mode + "_inds"])
         with pytest.raises(AttributeError):
             obj.table
+        if mode in ("vector", "scalar"):
+            assert np.array_equal(obj.inputfield, g["sorted_field"])      # padded pitch is not visible
     with pytest.raises(ValueError):
         from arbinterp_b200 import quadcubic
         quadcubic(load_golden("quad_8x7x7x6")["field"], "quiet", table=False)
