@@ -70,7 +70,9 @@ def analytic_field_rows(torch, n, device):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle-reason samples DURING the timed region (B200_PROFILING.md).  NVML is polled every
+    5 ms from a thread (the timed region of the default run is ~60 ms, too short for `nvidia-smi -lms`);
+    nvidia-smi is the fallback when pynvml is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -78,35 +80,68 @@ class ClockSampler(threading.Thread):
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.gpu = gpu_index
-        self.rows = []
+        self.samples = []          # (sm_mhz, set of reasons)
+        self.max_mhz = None
         self.proc = None
+        self._halt = threading.Event()
+        self.source = None
+
+    def _run_nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        names = (("hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                 ("hw_thermal_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                 ("sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap"))
+        bits = [(n, getattr(pynvml, a)) for n, a in names if hasattr(pynvml, a)]
+        self.source = "nvml"
+        while not self._halt.is_set():
+            mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+            mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            self.samples.append((mhz, {n for n, b in bits if mask & b}))
+            time.sleep(0.005)
+
+    def _run_smi(self):
+        self.source = "nvidia-smi"
+        self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+        for line in self.proc.stdout:
+            r = [c.strip() for c in line.split(",")]
+            try:
+                reasons = {n for n, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                                            ("sw_power_cap", 8)) if r[col].lower().startswith("active")}
+                self.samples.append((float(r[1]), reasons))
+                self.max_mhz = float(r[2])
+            except (ValueError, IndexError):
+                continue
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
+            self._run_nvml()
         except Exception:
-            pass
+            try:
+                self._run_smi()
+            except Exception:
+                pass
+
+    def wait_first_sample(self, timeout=5.0):
+        t0 = time.perf_counter()
+        while not self.samples and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
 
     def stop(self):
+        self._halt.set()
         if self.proc:
             self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
-                                  ("sw_power_cap", 8)):
-                    if r[col].lower().startswith("active"):
-                        reasons.add(name)
-            except (ValueError, IndexError):
-                continue
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        busy = sorted(sm)[len(sm) // 2:]
-        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0, "source": self.source}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = set().union(*[s[1] for s in self.samples])
+        busy = sm[len(sm) // 2:]                      # the upper half: samples taken under load
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons),
+                "samples": len(sm), "source": self.source}
 
 
 def bind_to_gpu_numa_node(gpu_index):
@@ -339,7 +374,8 @@ def run_b200(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
+        sampler.wait_first_sample()
+        sampler.samples.clear()                       # keep only what is sampled from the warm-up on
     elapsed, per_launch = time_device(torch, lib, obj, args.mode, d, q, outs, cells, args.steps, args.warmup, dist)
     clocks = sampler.stop() if rank == 0 else None
     if dist is not None:
