@@ -673,3 +673,16 @@ def test_full_size_4d_quirk_detector():
             fixed = quadcubic(field, "quiet", fixed_d4=True)
             n2, _ = fixed.Query(q.copy())
             assert np.max(np.abs(n2[:, 0] - fun(*q.T))) < 1e-12
+
+
+def test_randomised_parity_stress():
+    """40 random (shape, spacing, mode, table/table-free, build variant, query variant) cases against the oracle
+    (tools/stress_parity.py; 200 cases were run for profiles/r01_stress_parity.log)."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "stress_parity.py"), "--cases", "40", "--seed", "7"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "0 failures" in out.stdout
