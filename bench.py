@@ -245,7 +245,7 @@ def run_reference(args):
     global _PARENT_ORACLE
     os.environ["OMP_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = "1"
     cores = len(os.sched_getaffinity(0))
-    procs = max(1, min(cores, 64))
+    procs = max(1, min(cores, 256))
     per = max(20_000, min(200_000, args.cpu_sample // 5))
     n = args.grid
     t0 = time.perf_counter()
