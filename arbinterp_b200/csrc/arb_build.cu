@@ -23,6 +23,7 @@
 #include <vector>
 #include <mutex>
 #include "arb_common.cuh"
+#include "arb_build_sep.cuh"
 
 namespace arb {
 
@@ -441,6 +442,100 @@ build_kron_kernel(const __grid_constant__ CUtensorMap tmap, const BuildParams p)
     }
 }
 
+
+// ======================================================================================
+// Separable build on the FP64 pipe (build variants 5..7; phases in arb_build_sep.cuh)
+// ======================================================================================
+// 3-D: one CTA = one tile of 8 x TY x TZ cells of one component.  TMA stages the grid tile, then the x, y
+// and z passes of the 1-D line transform run back to back; the z pass writes the table.
+template <typename S3, int MINB>
+__global__ void __launch_bounds__(S3::THREADS, MINB)
+build_sep3_kernel(const __grid_constant__ CUtensorMap tmap, const sep::SepParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* g = reinterpret_cast<double*>(smem_raw);
+    double* X = g + S3::G_ELEMS;
+    double* Y = X + S3::X_ELEMS;
+    __shared__ uint64_t bar;
+
+    int64_t tl = blockIdx.x;
+    const int64_t tx = tl % p.ntile[0]; tl /= p.ntile[0];
+    const int64_t ty = tl % p.ntile[1];
+    const int64_t tz = tl / p.ntile[1];
+    const int comp = blockIdx.y;
+    const int x0 = (int)(tx * 8), y0 = (int)(ty * S3::TY), z0 = (int)(tz * S3::TZ);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+        mbar_expect_tx(&bar, S3::G_ELEMS * 8);
+        tma_load_4d(g, &tmap, &bar, x0, y0, z0, comp);
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    sep::pass_x(g, X, S3::NROW, tid, S3::THREADS);
+    __syncthreads();
+    sep::pass_y(X, Y, S3::GZ, S3::TY, tid, S3::THREADS);
+    __syncthreads();
+    S3::pass_z_emit(Y, p, x0, y0, z0, comp, tid, S3::THREADS);
+}
+
+// 4-D: one CTA = one column of 8 x 2 x 2 cells of one component, marching over p.lt cell layers along t.
+// Grid planes arrive through a two-deep TMA pipeline (one mbarrier per buffer); every plane is transformed
+// along x, y, z once, and the fused z/t phase emits the layer the plane completes.
+__global__ void __launch_bounds__(sep::Sep4::THREADS, 2)
+build_sep4_kernel(const __grid_constant__ CUtensorMap tmap, const sep::SepParams p) {
+    using S4 = sep::Sep4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* base = reinterpret_cast<double*>(smem_raw);
+    double* plane = base + S4::OFF_PLANE;
+    double* X = base + S4::OFF_X;
+    double* wx = base + S4::OFF_WX;
+    double* Y = base + S4::OFF_Y;
+    double* ring = base + S4::OFF_RING;
+    double* w3ring = base + S4::OFF_W3;
+    double* delta = base + S4::OFF_DELTA;
+    __shared__ uint64_t bar[2];
+
+    int64_t tl = blockIdx.x;
+    const int64_t tx = tl % p.ntile[0]; tl /= p.ntile[0];
+    const int64_t ty = tl % p.ntile[1];
+    const int64_t tz = tl / p.ntile[1];
+    const int comp = blockIdx.y;
+    const int x0 = (int)(tx * 8), y0 = (int)(ty * S4::TY), z0 = (int)(tz * S4::TZ);
+    const int64_t t0 = (int64_t)blockIdx.z * p.lt;                 // first cell layer of this CTA
+    const int nlayer = (int)((p.nc[3] - t0 < p.lt) ? (p.nc[3] - t0) : p.lt);
+    const int nstep = nlayer + 3;                                  // grid planes t0 .. t0 + nlayer + 2
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        fence_mbar_init();
+        for (int b = 0; b < 2; ++b) {
+            mbar_expect_tx(&bar[b], S4::PLANE * 8);
+            tma_load_5d(plane + b * S4::PLANE_PITCH, &tmap, &bar[b], x0, y0, z0, (int)t0 + b, comp);
+        }
+    }
+    __syncthreads();
+    for (int s = 0; s < nstep; ++s) {
+        const int b = s & 1;
+        mbar_wait(&bar[b], (s >> 1) & 1);
+        S4::phase_a(plane + b * S4::PLANE_PITCH, X, wx, p.quirk, tid, S4::THREADS);
+        __syncthreads();
+        if (tid == 0 && s + 2 < nstep) {           // buffer b is free again: fetch plane s + 2
+            fence_proxy_async();
+            mbar_expect_tx(&bar[b], S4::PLANE * 8);
+            tma_load_5d(plane + b * S4::PLANE_PITCH, &tmap, &bar[b], x0, y0, z0, (int)t0 + s + 2, comp);
+        }
+        S4::phase_b(X, Y, wx, w3ring + (s & 3) * S4::W3, p.quirk, tid, S4::THREADS);
+        __syncthreads();
+        if (p.quirk && s >= 3) {
+            S4::phase_d(w3ring, delta, s, tid, S4::THREADS);
+            __syncthreads();
+        }
+        S4::phase_e(Y, ring, delta, p, s, x0, y0, z0, t0 + s - 3, comp, tid, S4::THREADS);
+    }
+}
+
 __global__ void fill_nan_kernel(double* p, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = __longlong_as_double(0x7ff8000000000000LL);
@@ -494,13 +589,77 @@ static int get_bfrag(int d, const double** out) {
 
 static int g_build_variant = 0;
 
+// Tensor map over the grid [C][nt][nz][ny][nx] (x fastest) with the given box; TMA needs 16-byte global
+// strides, so an odd nx is padded to even in a stream-ordered scratch copy (`padded`, freed by the caller
+// after the launch).  Out-of-range box elements are zero-filled.
+struct GridMap {
+    CUtensorMap tmap;
+    double* padded = nullptr;
+};
+
+static int make_grid_map(int D, const double* grid, int ncomp, const int64_t* n, const cuuint32_t* box_dims,
+                         cudaStream_t st, GridMap* out) {
+    EncodeTiledFn encode = get_encode_fn();
+    if (!encode) { set_error("arb_build_coeffs: cuTensorMapEncodeTiled not available from the driver"); return 2; }
+    const double* src = grid;
+    int64_t pitch = n[0];
+    int64_t rows = ncomp;
+    for (int a = 1; a < D; ++a) rows *= n[a];
+    if (n[0] & 1) {
+        pitch = n[0] + 1;
+        ARB_CUDA(cudaMallocAsync(&out->padded, sizeof(double) * pitch * rows, st));
+        ARB_CUDA(cudaMemsetAsync(out->padded, 0, sizeof(double) * pitch * rows, st));
+        ARB_CUDA(cudaMemcpy2DAsync(out->padded, pitch * 8, grid, n[0] * 8, n[0] * 8, rows, cudaMemcpyDeviceToDevice, st));
+        src = out->padded;
+    }
+    if ((reinterpret_cast<uintptr_t>(src) & 15) != 0) {
+        if (out->padded) cudaFreeAsync(out->padded, st);
+        out->padded = nullptr;
+        set_error("arb_build_coeffs: grid pointer must be 16-byte aligned");
+        return 1;
+    }
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t box[5], estr[5];
+    const int rank = D + 1;
+    gdim[0] = (cuuint64_t)n[0];
+    int64_t stride = pitch * 8;
+    for (int a = 1; a < D; ++a) { gdim[a] = (cuuint64_t)n[a]; gstr[a - 1] = (cuuint64_t)stride; stride *= n[a]; }
+    gdim[D] = (cuuint64_t)ncomp; gstr[D - 1] = (cuuint64_t)stride;
+    for (int a = 0; a < D; ++a) box[a] = box_dims[a];
+    box[D] = 1;
+    for (int a = 0; a < rank; ++a) estr[a] = 1;
+    CUresult cr = encode(&out->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, rank, const_cast<double*>(src), gdim, gstr, box,
+                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        if (out->padded) cudaFreeAsync(out->padded, st);
+        out->padded = nullptr;
+        set_error("arb_build_coeffs: cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+        return 2;
+    }
+    if (getenv("ARB_DEBUG_TMAP")) {
+        const unsigned long long* w = reinterpret_cast<const unsigned long long*>(&out->tmap);
+        fprintf(stderr, "[arb] tensor map rank %d box %u %u %u:", rank, box[0], box[1], box[2]);
+        for (int i = 0; i < 16; ++i) fprintf(stderr, " %016llx", w[i]);
+        fprintf(stderr, "\n");
+    }
+    return 0;
+}
+
+// NaN sentinel row behind the last cell (A.py:45, 57, 70) and release of the padded scratch copy
+static int finish_build(int D, int ncomp, int64_t ncell, double* table, GridMap* gm, cudaStream_t st) {
+    const int64_t tail = (int64_t)ncomp * (1 << (2 * D));
+    fill_nan_kernel<<<(unsigned)((tail + 255) / 256), 256, 0, st>>>(table + ncell * tail, tail);
+    ARB_CUDA(cudaGetLastError());
+    if (gm->padded) ARB_CUDA(cudaFreeAsync(gm->padded, st));
+    gm->padded = nullptr;
+    return 0;
+}
+
 template <typename Cfg, bool KRON = false>
 static int build_impl(const double* grid, int ncomp, const int64_t* n, double* table, int quirk, cudaStream_t st) {
     using S = BuildShape<Cfg>;
     constexpr int D = Cfg::D;
-    EncodeTiledFn encode = get_encode_fn();
-    if (!encode) { set_error("arb_build_coeffs: cuTensorMapEncodeTiled not available from the driver"); return 2; }
-
     BuildParams p;
     memset(&p, 0, sizeof(p));
     int64_t ncell = 1;
@@ -522,68 +681,89 @@ static int build_impl(const double* grid, int ncomp, const int64_t* n, double* t
     }
     { const int frc = get_bfrag(D, &p.bfrag); if (frc) return frc; }
 
-    // TMA needs 16-byte global strides: pad odd nx to even in a scratch copy
-    const double* src = grid;
-    double* padded = nullptr;
-    int64_t pitch = n[0];
-    int64_t rows = ncomp;
-    for (int a = 1; a < D; ++a) rows *= n[a];
-    if (n[0] & 1) {
-        pitch = n[0] + 1;
-        ARB_CUDA(cudaMallocAsync(&padded, sizeof(double) * pitch * rows, st));
-        ARB_CUDA(cudaMemsetAsync(padded, 0, sizeof(double) * pitch * rows, st));
-        ARB_CUDA(cudaMemcpy2DAsync(padded, pitch * 8, grid, n[0] * 8, n[0] * 8, rows, cudaMemcpyDeviceToDevice, st));
-        src = padded;
-    }
-    if ((reinterpret_cast<uintptr_t>(src) & 15) != 0) {
-        if (padded) cudaFreeAsync(padded, st);
-        set_error("arb_build_coeffs: grid pointer must be 16-byte aligned");
-        return 1;
-    }
+    GridMap gm;
+    const cuuint32_t box[4] = {S::GX, S::GY, S::GZ, S::GT};
+    { const int rc = make_grid_map(D, grid, ncomp, n, box, st, &gm); if (rc) return rc; }
 
-    CUtensorMap tmap;
-    cuuint64_t gdim[5], gstr[4];
-    cuuint32_t box[5], estr[5];
-    const int rank = D + 1;
-    gdim[0] = (cuuint64_t)n[0];
-    int64_t stride = pitch * 8;
-    for (int a = 1; a < D; ++a) { gdim[a] = (cuuint64_t)n[a]; gstr[a - 1] = (cuuint64_t)stride; stride *= n[a]; }
-    gdim[D] = (cuuint64_t)ncomp; gstr[D - 1] = (cuuint64_t)stride;
-    box[0] = S::GX; box[1] = S::GY; box[2] = S::GZ;
-    if (D == 4) box[3] = S::GT;
-    box[D] = 1;
-    for (int a = 0; a < rank; ++a) estr[a] = 1;
-    CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, rank, const_cast<double*>(src), gdim, gstr, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (cr != CUDA_SUCCESS) {
-        if (padded) cudaFreeAsync(padded, st);
-        set_error("arb_build_coeffs: cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
-        return 2;
-    }
-
-    if (getenv("ARB_DEBUG_TMAP")) {
-        const unsigned long long* w = reinterpret_cast<const unsigned long long*>(&tmap);
-        fprintf(stderr, "[arb] tensor map rank %d box %u %u %u:", rank, box[0], box[1], box[2]);
-        for (int i = 0; i < 16; ++i) fprintf(stderr, " %016llx", w[i]);
-        fprintf(stderr, "\n");
-    }
     dim3 gridDim((unsigned)ntiles, (unsigned)ncomp, 1);
     if (KRON) {
         auto k = build_kron_kernel<Cfg>;
         ARB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KronShape<Cfg>::SMEM));
-        k<<<gridDim, S::THREADS, KronShape<Cfg>::SMEM, st>>>(tmap, p);
+        k<<<gridDim, S::THREADS, KronShape<Cfg>::SMEM, st>>>(gm.tmap, p);
     } else {
         auto k = build_kernel<Cfg>;
         ARB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
-        k<<<gridDim, S::THREADS, S::SMEM, st>>>(tmap, p);
+        k<<<gridDim, S::THREADS, S::SMEM, st>>>(gm.tmap, p);
     }
     ARB_CUDA(cudaGetLastError());
-    const int64_t tail = (int64_t)ncomp * S::NM;
-    fill_nan_kernel<<<(unsigned)((tail + 255) / 256), 256, 0, st>>>(table + ncell * tail, tail);
-    ARB_CUDA(cudaGetLastError());
-    if (padded) ARB_CUDA(cudaFreeAsync(padded, st));
+    return finish_build(D, ncomp, ncell, table, &gm, st);
+}
+
+static int sep_params(int D, int ncomp, const int64_t* n, double* table, int quirk, const int* tdim,
+                      sep::SepParams* p, int64_t* ncell, int64_t* ntiles) {
+    memset(p, 0, sizeof(*p));
+    *ncell = 1;
+    *ntiles = 1;
+    for (int a = 0; a < D; ++a) {
+        if (n[a] < 4) { set_error("arb_build_coeffs: axis %d has %lld points, need >= 4", a, (long long)n[a]); return 1; }
+        p->nc[a] = n[a] - 3;
+        *ncell *= p->nc[a];
+        if (a < 3) {
+            p->ntile[a] = (p->nc[a] + tdim[a] - 1) / tdim[a];
+            *ntiles *= p->ntile[a];
+        }
+    }
+    for (int a = D; a < 4; ++a) p->nc[a] = 1;
+    if (*ntiles > 0x7fffffffLL) { set_error("arb_build_coeffs: too many tiles (%lld)", (long long)*ntiles); return 1; }
+    p->table = table; p->ncomp = ncomp; p->quirk = quirk;
     return 0;
+}
+
+template <int TY, int TZ, int THREADS, int MINB>
+static int build_sep3_impl(const double* grid, int ncomp, const int64_t* n, double* table, cudaStream_t st) {
+    using S3 = sep::Sep3<TY, TZ, THREADS>;
+    sep::SepParams p;
+    int64_t ncell, ntiles;
+    const int tdim[3] = {8, TY, TZ};
+    { const int rc = sep_params(3, ncomp, n, table, 0, tdim, &p, &ncell, &ntiles); if (rc) return rc; }
+    GridMap gm;
+    const cuuint32_t box[4] = {sep::GX, S3::GY, S3::GZ, 1};
+    { const int rc = make_grid_map(3, grid, ncomp, n, box, st, &gm); if (rc) return rc; }
+    auto k = build_sep3_kernel<S3, MINB>;
+    ARB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S3::SMEM));
+    k<<<dim3((unsigned)ntiles, (unsigned)ncomp, 1), THREADS, S3::SMEM, st>>>(gm.tmap, p);
+    ARB_CUDA(cudaGetLastError());
+    return finish_build(3, ncomp, ncell, table, &gm, st);
+}
+
+// layers_per_cta <= 0: long marches, cut only as far as needed to fill the GPU with a few waves of CTAs
+static int build_sep4_impl(const double* grid, int ncomp, const int64_t* n, double* table, int quirk,
+                           int layers_per_cta, cudaStream_t st) {
+    using S4 = sep::Sep4;
+    sep::SepParams p;
+    int64_t ncell, ntiles;
+    const int tdim[3] = {8, S4::TY, S4::TZ};
+    { const int rc = sep_params(4, ncomp, n, table, quirk, tdim, &p, &ncell, &ntiles); if (rc) return rc; }
+    int64_t lt = layers_per_cta;
+    if (lt <= 0) {
+        const int64_t want = 8LL * 2 * num_sms();              // CTAs for ~8 waves at 2 CTAs per SM
+        int64_t chunks = (want + ntiles * ncomp - 1) / (ntiles * ncomp);
+        const int64_t max_chunks = (p.nc[3] + 5) / 6;            // keep marches >= 6 layers (3 planes of run-in each)
+        if (chunks > max_chunks) chunks = max_chunks;
+        if (chunks < 1) chunks = 1;
+        lt = (p.nc[3] + chunks - 1) / chunks;
+    }
+    if (lt > p.nc[3]) lt = p.nc[3];
+    p.lt = (int)lt;
+    const int64_t nchunk = (p.nc[3] + lt - 1) / lt;
+    if (nchunk > 65535) { set_error("arb_build_coeffs: too many t chunks (%lld)", (long long)nchunk); return 1; }
+    GridMap gm;
+    const cuuint32_t box[4] = {sep::GX, S4::GY, S4::GZ, 1};
+    { const int rc = make_grid_map(4, grid, ncomp, n, box, st, &gm); if (rc) return rc; }
+    ARB_CUDA(cudaFuncSetAttribute(build_sep4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S4::SMEM));
+    build_sep4_kernel<<<dim3((unsigned)ntiles, (unsigned)ncomp, (unsigned)nchunk), S4::THREADS, S4::SMEM, st>>>(gm.tmap, p);
+    ARB_CUDA(cudaGetLastError());
+    return finish_build(4, ncomp, ncell, table, &gm, st);
 }
 
 }  // namespace arb
@@ -599,6 +779,10 @@ int arb_build_coeffs(int d, const double* grid, int ncomp, const int64_t n[4], d
     // variant 0 (default): Kronecker-factored solve (build_kron_kernel); 1-3: the dense 4^d x 4^d contraction
     // with different tiles (1 = its best); 4: Kronecker with the smaller tile.  profiles/r01_build_configs.log
     if (d == 3) {
+        if (v == 5) return arb::build_sep3_impl<4, 4, 128, 4>(grid, ncomp, n, table, st);
+        if (v == 6) return arb::build_sep3_impl<4, 8, 256, 2>(grid, ncomp, n, table, st);
+        if (v == 7) return arb::build_sep3_impl<4, 4, 256, 2>(grid, ncomp, n, table, st);
+        if (v == 8) return arb::build_sep3_impl<2, 4, 128, 6>(grid, ncomp, n, table, st);
         if (v == 1) return arb::build_impl<arb::Cfg3A>(grid, ncomp, n, table, reference_quirk, st);
         if (v == 2) return arb::build_impl<arb::Cfg3B>(grid, ncomp, n, table, reference_quirk, st);
         if (v == 3) return arb::build_impl<arb::Cfg3C>(grid, ncomp, n, table, reference_quirk, st);
@@ -606,6 +790,10 @@ int arb_build_coeffs(int d, const double* grid, int ncomp, const int64_t n[4], d
         return arb::build_impl<arb::Cfg3A, true>(grid, ncomp, n, table, reference_quirk, st);
     }
     if (d == 4) {
+        if (v == 5) return arb::build_sep4_impl(grid, ncomp, n, table, reference_quirk, 0, st);
+        if (v == 6) return arb::build_sep4_impl(grid, ncomp, n, table, reference_quirk, 8, st);
+        if (v == 7) return arb::build_sep4_impl(grid, ncomp, n, table, reference_quirk, 1 << 20, st);
+        if (v == 8) return arb::build_sep4_impl(grid, ncomp, n, table, reference_quirk, 3, st);
         if (v == 1) return arb::build_impl<arb::Cfg4B>(grid, ncomp, n, table, reference_quirk, st);
         if (v == 2) return arb::build_impl<arb::Cfg4A>(grid, ncomp, n, table, reference_quirk, st);
         if (v == 3) return arb::build_impl<arb::Cfg4C>(grid, ncomp, n, table, reference_quirk, st);

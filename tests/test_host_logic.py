@@ -116,6 +116,24 @@ def test_exact_matrices_against_reference_fixtures():
         assert np.array_equal(hermite_matrix(d), B)
 
 
+def test_separable_build_phases_on_host(tmp_path):
+    """The phases of the separable build kernels (arb_build_sep.cuh, __host__ __device__) run thread by thread
+    on the CPU and reproduce A f for every cell, in 3-D and in 4-D with and without the A.py:860 quirk."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "sep_host_emul")
+    subprocess.run([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", exe,
+                    os.path.join(ROOT, "tests", "host_emul", "sep_host_emul.cu"),
+                    os.path.join(ROOT, "arbinterp_b200", "csrc", "arb_core.cu")], check=True, timeout=600)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    errs = [float(x) for x in re.findall(r"max scaled error ([0-9.eE+-]+)", out.stdout)]
+    assert out.returncode == 0, out.stdout
+    assert len(errs) >= 10 and max(errs) <= 1e-12
+
+
 def test_argument_validation_without_gpu():
     lib = _lib.load()
     g = _lib.ArbGeom()
