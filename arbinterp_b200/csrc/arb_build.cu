@@ -458,10 +458,11 @@ build_sep3_kernel(const __grid_constant__ CUtensorMap tmap, const sep::SepParams
     __shared__ uint64_t bar;
 
     int64_t tl = blockIdx.x;
+    int comp = blockIdx.y;
+    if (p.comp_fast) { comp = (int)(tl % p.ncomp); tl /= p.ncomp; }
     const int64_t tx = tl % p.ntile[0]; tl /= p.ntile[0];
     const int64_t ty = tl % p.ntile[1];
     const int64_t tz = tl / p.ntile[1];
-    const int comp = blockIdx.y;
     const int x0 = (int)(tx * 8), y0 = (int)(ty * S3::TY), z0 = (int)(tz * S3::TZ);
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -481,7 +482,9 @@ build_sep3_kernel(const __grid_constant__ CUtensorMap tmap, const sep::SepParams
 
 // 4-D: one CTA = one column of 8 x 2 x 2 cells of one component, marching over p.lt cell layers along t.
 // Grid planes arrive through a two-deep TMA pipeline (one mbarrier per buffer); every plane is transformed
-// along x, y, z once, and the fused z/t phase emits the layer the plane completes.
+// along x, y, z once, and the fused z/t phase emits the layer the plane completes.  Software pipeline: iteration
+// s runs {x pass of plane s+1, first half of emit(s)} | barrier | {y pass of plane s+1, second half of emit(s)} |
+// barrier, so the latency-bound passes always share an interval with table stores (Y and delta are double-buffered).
 __global__ void __launch_bounds__(sep::Sep4::THREADS, 2)
 build_sep4_kernel(const __grid_constant__ CUtensorMap tmap, const sep::SepParams p) {
     using S4 = sep::Sep4;
@@ -489,7 +492,6 @@ build_sep4_kernel(const __grid_constant__ CUtensorMap tmap, const sep::SepParams
     double* base = reinterpret_cast<double*>(smem_raw);
     double* plane = base + S4::OFF_PLANE;
     double* X = base + S4::OFF_X;
-    double* wx = base + S4::OFF_WX;
     double* Y = base + S4::OFF_Y;
     double* ring = base + S4::OFF_RING;
     double* w3ring = base + S4::OFF_W3;
@@ -497,42 +499,53 @@ build_sep4_kernel(const __grid_constant__ CUtensorMap tmap, const sep::SepParams
     __shared__ uint64_t bar[2];
 
     int64_t tl = blockIdx.x;
+    int comp = blockIdx.y;
+    if (p.comp_fast) { comp = (int)(tl % p.ncomp); tl /= p.ncomp; }
     const int64_t tx = tl % p.ntile[0]; tl /= p.ntile[0];
     const int64_t ty = tl % p.ntile[1];
     const int64_t tz = tl / p.ntile[1];
-    const int comp = blockIdx.y;
     const int x0 = (int)(tx * 8), y0 = (int)(ty * S4::TY), z0 = (int)(tz * S4::TZ);
     const int64_t t0 = (int64_t)blockIdx.z * p.lt;                 // first cell layer of this CTA
     const int nlayer = (int)((p.nc[3] - t0 < p.lt) ? (p.nc[3] - t0) : p.lt);
     const int nstep = nlayer + 3;                                  // grid planes t0 .. t0 + nlayer + 2
     const int tid = threadIdx.x;
+    auto fetch = [&](int q) {                                      // plane q -> buffer q & 1 (one thread)
+        mbar_expect_tx(&bar[q & 1], S4::PLANE * 8);
+        tma_load_5d(plane + (q & 1) * S4::PLANE_PITCH, &tmap, &bar[q & 1], x0, y0, z0, (int)t0 + q, comp);
+    };
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
         fence_mbar_init();
-        for (int b = 0; b < 2; ++b) {
-            mbar_expect_tx(&bar[b], S4::PLANE * 8);
-            tma_load_5d(plane + b * S4::PLANE_PITCH, &tmap, &bar[b], x0, y0, z0, (int)t0 + b, comp);
-        }
+        fetch(0);
+        fetch(1);
     }
     __syncthreads();
+    // prologue: plane 0 through the x and y passes
+    mbar_wait(&bar[0], 0);
+    S4::phase_a(plane, X, w3ring, p.quirk, tid, S4::THREADS);
+    __syncthreads();
+    if (tid == 0) { fence_proxy_async(); fetch(2); }              // nstep >= 4 always
+    S4::phase_b(X, Y, w3ring, delta, 0, p.quirk, tid, S4::THREADS);
+    __syncthreads();
     for (int s = 0; s < nstep; ++s) {
-        const int b = s & 1;
-        mbar_wait(&bar[b], (s >> 1) & 1);
-        S4::phase_a(plane + b * S4::PLANE_PITCH, X, wx, p.quirk, tid, S4::THREADS);
-        __syncthreads();
-        if (tid == 0 && s + 2 < nstep) {           // buffer b is free again: fetch plane s + 2
-            fence_proxy_async();
-            mbar_expect_tx(&bar[b], S4::PLANE * 8);
-            tma_load_5d(plane + b * S4::PLANE_PITCH, &tmap, &bar[b], x0, y0, z0, (int)t0 + s + 2, comp);
+        const int q = s + 1;                                       // plane whose x/y passes ride along
+        const bool more = q < nstep;
+        const double* Ys = Y + (s & 1) * S4::Y_ELEMS;
+        const double* ds = delta + (s & 1) * S4::DELTA_ELEMS;
+        if (more) {
+            mbar_wait(&bar[q & 1], (q >> 1) & 1);
+            S4::phase_a(plane + (q & 1) * S4::PLANE_PITCH, X, w3ring + (q & 3) * S4::W3_PITCH, p.quirk, tid, S4::THREADS);
         }
-        S4::phase_b(X, Y, wx, w3ring + (s & 3) * S4::W3, p.quirk, tid, S4::THREADS);
+        S4::phase_e(Ys, ring, ds, p, s, x0, y0, z0, t0 + s - 3, comp, 0, S4::NTASK_E / 2, tid, S4::THREADS);
         __syncthreads();
-        if (p.quirk && s >= 3) {
-            S4::phase_d(w3ring, delta, s, tid, S4::THREADS);
-            __syncthreads();
+        if (more) {
+            if (tid == 0 && q + 2 < nstep) { fence_proxy_async(); fetch(q + 2); }
+            S4::phase_b(X, Y + (q & 1) * S4::Y_ELEMS, w3ring, delta + (q & 1) * S4::DELTA_ELEMS, q, p.quirk, tid,
+                        S4::THREADS);
         }
-        S4::phase_e(Y, ring, delta, p, s, x0, y0, z0, t0 + s - 3, comp, tid, S4::THREADS);
+        S4::phase_e(Ys, ring, ds, p, s, x0, y0, z0, t0 + s - 3, comp, S4::NTASK_E / 2, S4::NTASK_E, tid, S4::THREADS);
+        __syncthreads();
     }
 }
 
@@ -720,7 +733,8 @@ static int sep_params(int D, int ncomp, const int64_t* n, double* table, int qui
 }
 
 template <int TY, int TZ, int THREADS, int MINB>
-static int build_sep3_impl(const double* grid, int ncomp, const int64_t* n, double* table, cudaStream_t st) {
+static int build_sep3_impl(const double* grid, int ncomp, const int64_t* n, double* table, int comp_fast,
+                           cudaStream_t st) {
     using S3 = sep::Sep3<TY, TZ, THREADS>;
     sep::SepParams p;
     int64_t ncell, ntiles;
@@ -731,14 +745,16 @@ static int build_sep3_impl(const double* grid, int ncomp, const int64_t* n, doub
     { const int rc = make_grid_map(3, grid, ncomp, n, box, st, &gm); if (rc) return rc; }
     auto k = build_sep3_kernel<S3, MINB>;
     ARB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S3::SMEM));
-    k<<<dim3((unsigned)ntiles, (unsigned)ncomp, 1), THREADS, S3::SMEM, st>>>(gm.tmap, p);
+    p.comp_fast = comp_fast && ntiles * ncomp <= 0x7fffffffLL;
+    const dim3 blocks = p.comp_fast ? dim3((unsigned)(ntiles * ncomp), 1, 1) : dim3((unsigned)ntiles, (unsigned)ncomp, 1);
+    k<<<blocks, THREADS, S3::SMEM, st>>>(gm.tmap, p);
     ARB_CUDA(cudaGetLastError());
     return finish_build(3, ncomp, ncell, table, &gm, st);
 }
 
 // layers_per_cta <= 0: long marches, cut only as far as needed to fill the GPU with a few waves of CTAs
 static int build_sep4_impl(const double* grid, int ncomp, const int64_t* n, double* table, int quirk,
-                           int layers_per_cta, cudaStream_t st) {
+                           int layers_per_cta, int comp_fast, cudaStream_t st) {
     using S4 = sep::Sep4;
     sep::SepParams p;
     int64_t ncell, ntiles;
@@ -761,7 +777,10 @@ static int build_sep4_impl(const double* grid, int ncomp, const int64_t* n, doub
     const cuuint32_t box[4] = {sep::GX, S4::GY, S4::GZ, 1};
     { const int rc = make_grid_map(4, grid, ncomp, n, box, st, &gm); if (rc) return rc; }
     ARB_CUDA(cudaFuncSetAttribute(build_sep4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S4::SMEM));
-    build_sep4_kernel<<<dim3((unsigned)ntiles, (unsigned)ncomp, (unsigned)nchunk), S4::THREADS, S4::SMEM, st>>>(gm.tmap, p);
+    p.comp_fast = comp_fast && ntiles * ncomp <= 0x7fffffffLL;
+    const dim3 blocks = p.comp_fast ? dim3((unsigned)(ntiles * ncomp), 1, (unsigned)nchunk)
+                                    : dim3((unsigned)ntiles, (unsigned)ncomp, (unsigned)nchunk);
+    build_sep4_kernel<<<blocks, S4::THREADS, S4::SMEM, st>>>(gm.tmap, p);
     ARB_CUDA(cudaGetLastError());
     return finish_build(4, ncomp, ncell, table, &gm, st);
 }
@@ -779,10 +798,10 @@ int arb_build_coeffs(int d, const double* grid, int ncomp, const int64_t n[4], d
     // variant 0 (default): Kronecker-factored solve (build_kron_kernel); 1-3: the dense 4^d x 4^d contraction
     // with different tiles (1 = its best); 4: Kronecker with the smaller tile.  profiles/r01_build_configs.log
     if (d == 3) {
-        if (v == 5) return arb::build_sep3_impl<4, 4, 128, 4>(grid, ncomp, n, table, st);
-        if (v == 6) return arb::build_sep3_impl<4, 8, 256, 2>(grid, ncomp, n, table, st);
-        if (v == 7) return arb::build_sep3_impl<4, 4, 256, 2>(grid, ncomp, n, table, st);
-        if (v == 8) return arb::build_sep3_impl<2, 4, 128, 6>(grid, ncomp, n, table, st);
+        if (v == 5) return arb::build_sep3_impl<4, 4, 128, 4>(grid, ncomp, n, table, 0, st);
+        if (v == 6) return arb::build_sep3_impl<4, 4, 128, 4>(grid, ncomp, n, table, 1, st);
+        if (v == 7) return arb::build_sep3_impl<4, 8, 256, 2>(grid, ncomp, n, table, 1, st);
+        if (v == 8) return arb::build_sep3_impl<2, 4, 128, 6>(grid, ncomp, n, table, 1, st);
         if (v == 1) return arb::build_impl<arb::Cfg3A>(grid, ncomp, n, table, reference_quirk, st);
         if (v == 2) return arb::build_impl<arb::Cfg3B>(grid, ncomp, n, table, reference_quirk, st);
         if (v == 3) return arb::build_impl<arb::Cfg3C>(grid, ncomp, n, table, reference_quirk, st);
@@ -790,10 +809,10 @@ int arb_build_coeffs(int d, const double* grid, int ncomp, const int64_t n[4], d
         return arb::build_impl<arb::Cfg3A, true>(grid, ncomp, n, table, reference_quirk, st);
     }
     if (d == 4) {
-        if (v == 5) return arb::build_sep4_impl(grid, ncomp, n, table, reference_quirk, 0, st);
-        if (v == 6) return arb::build_sep4_impl(grid, ncomp, n, table, reference_quirk, 8, st);
-        if (v == 7) return arb::build_sep4_impl(grid, ncomp, n, table, reference_quirk, 1 << 20, st);
-        if (v == 8) return arb::build_sep4_impl(grid, ncomp, n, table, reference_quirk, 3, st);
+        if (v == 5) return arb::build_sep4_impl(grid, ncomp, n, table, reference_quirk, 0, 0, st);
+        if (v == 6) return arb::build_sep4_impl(grid, ncomp, n, table, reference_quirk, 0, 1, st);
+        if (v == 7) return arb::build_sep4_impl(grid, ncomp, n, table, reference_quirk, 8, 1, st);
+        if (v == 8) return arb::build_sep4_impl(grid, ncomp, n, table, reference_quirk, 3, 1, st);
         if (v == 1) return arb::build_impl<arb::Cfg4B>(grid, ncomp, n, table, reference_quirk, st);
         if (v == 2) return arb::build_impl<arb::Cfg4A>(grid, ncomp, n, table, reference_quirk, st);
         if (v == 3) return arb::build_impl<arb::Cfg4C>(grid, ncomp, n, table, reference_quirk, st);

@@ -17,7 +17,8 @@
 //     alpha_ref[l][k][j][i] = (M^(x)4 f)[l][k][j][i] + sum_c Hq[i][cx] Hq[j][cy] Hq[k][cz] Hq[l][ct] e[240 + c],
 // Hq = [[0,0],[1,0],[-2,-1],[1,1]] the slope columns of the Hermite inverse.  The 4-D kernel marches along t:
 // each new grid plane goes through the x, y and z passes once, the three previous planes' results wait in
-// a shared-memory ring, and the t pass emits one layer of cells per step.
+// a shared-memory ring, and the t pass emits one layer of cells per step.  The march is software-pipelined:
+// the x/y passes of plane s+1 share their two barrier intervals with the two halves of step s's emit phase.
 //
 // Everything here is __host__ __device__ and written as "for (e = tid; e < tasks; e += nthreads)" loops
 // over shared arrays, so tools/micro/sep_host_emul.cu can run the very same phases on the CPU and compare
@@ -41,6 +42,7 @@ struct SepParams {
     int ncomp;
     int quirk;            // 4-D: reproduce A.py:860
     int lt;               // 4-D: cell layers per CTA along t
+    int comp_fast;        // blockIdx.x = tile * ncomp + comp (the components of a tile are built side by side)
 };
 
 // one line: grid values at -1, 0, 1, 2 -> monomial coefficients a0..a3 (row e of M applied to f)
@@ -135,64 +137,64 @@ struct Sep4 {
     static constexpr int GY = 5, GZ = 5, NROW = 25, PLANE = NROW * GX;
     static constexpr int PLANE_PITCH = 304;                    // 128-byte multiple: TMA destination alignment
     static constexpr int NCELL = 8 * TY * TZ;                  // cells per layer
+    static constexpr int NTASK_E = NCELL * 16;
     static constexpr int X_ELEMS = NROW * XP, Y_ELEMS = GZ * TY * YROW;
-    static constexpr int WXP = 9, WX_ELEMS = NROW * WXP + 7;   // d/dx at the 9 corner points of each row (even size)
     static constexpr int W3 = 81;                              // dxdydz at the 9 x 3 x 3 corner points of a plane
+    static constexpr int W3_PITCH = 82;
     static constexpr int RING_SLOT = NCELL * 64;
-    // offsets into dynamic shared memory (doubles)
-    static constexpr int OFF_PLANE = 0, OFF_X = 2 * PLANE_PITCH, OFF_WX = OFF_X + X_ELEMS, OFF_Y = OFF_WX + WX_ELEMS,
-                         OFF_RING = OFF_Y + Y_ELEMS, OFF_W3 = OFF_RING + 3 * RING_SLOT, OFF_DELTA = OFF_W3 + 4 * W3,
-                         TOTAL = OFF_DELTA + NCELL * 16;
+    static constexpr int DELTA_ELEMS = NCELL * 16;
+    // offsets into dynamic shared memory (doubles); Y and delta are double-buffered (software pipeline)
+    static constexpr int OFF_PLANE = 0, OFF_X = 2 * PLANE_PITCH, OFF_Y = OFF_X + X_ELEMS, OFF_RING = OFF_Y + 2 * Y_ELEMS,
+                         OFF_W3 = OFF_RING + 3 * RING_SLOT, OFF_DELTA = OFF_W3 + 4 * W3_PITCH,
+                         TOTAL = OFF_DELTA + 2 * DELTA_ELEMS;
     static_assert(OFF_Y % 2 == 0 && OFF_RING % 2 == 0 && OFF_DELTA % 2 == 0, "16-byte alignment of vector reads");
     static constexpr size_t SMEM = (size_t)TOTAL * 8 + 128;
 
-    // phase A: x pass of the new plane; with the quirk also d/dx at the corner points (grid x = px + 1)
-    ARB_HD static void phase_a(const double* plane, double* X, double* wx, int quirk, int tid, int nthr) {
+    // phase A: x pass of a new plane; with the quirk also dxdydz (central differences, unit spacing) at the
+    // plane's 9 x 3 x 3 corner points (corner p <-> tile grid coordinate p + 1) -> this plane's w3 slot
+    ARB_HD static void phase_a(const double* plane, double* X, double* w3, int quirk, int tid, int nthr) {
         pass_x(plane, X, NROW, tid, nthr);
-        if (quirk)
-            for (int e = tid; e < NROW * 9; e += nthr) {
-                const int row = e / 9, px = e % 9;
-                wx[row * WXP + px] = 0.5 * (plane[row * GX + px + 2] - plane[row * GX + px]);
-            }
-    }
-    // phase B: y pass; with the quirk also dxdydz at the plane's corner points -> w3 slot of this plane
-    ARB_HD static void phase_b(const double* X, double* Y, const double* wx, double* w3, int quirk, int tid,
-                               int nthr) {
-        pass_y(X, Y, GZ, TY, tid, nthr);
         if (quirk)
             for (int e = tid; e < W3; e += nthr) {
                 const int px = e % 9, py = (e / 9) % 3, pz = e / 27;
-                const double* s = wx + (pz * GY + py) * WXP + px;    // row (z = pz, y = py)
-                const double lo = s[2 * WXP] - s[0];                        // d/dy at z = pz     (x2)
-                const double hi = s[(2 * GY + 2) * WXP] - s[2 * GY * WXP];  // d/dy at z = pz + 2 (x2)
-                w3[e] = 0.25 * (hi - lo);
+                const double* s = plane + (pz * GY + py) * GX + px;
+                const double lo = (s[2 * GX + 2] - s[2 * GX]) - (s[2] - s[0]);                  // z = pz     (x4)
+                const double* u = s + 2 * GY * GX;
+                const double hi = (u[2 * GX + 2] - u[2 * GX]) - (u[2] - u[0]);                  // z = pz + 2 (x4)
+                w3[e] = 0.125 * (hi - lo);
             }
     }
-    // phase D (quirk only, step s >= 3): e[240 + c] of every cell of the layer.  The layer's corners sit on the
-    // local planes s-2 (ct = 0) and s-1 (ct = 1); fxyzt there = 0.5 * (w3[plane + 1] - w3[plane - 1]).
+    // fxyzt at corner c of a cell of the layer completed by local plane s: the layer's corners sit on the local
+    // planes s-2 (ct = 0) and s-1 (ct = 1); fxyzt there = 0.5 * (w3[plane + 1] - w3[plane - 1]).
     ARB_HD static double fxyzt(const double* w3ring, int s, int c, int cellx, int celly, int cellz) {
         const int cx = c & 1, cy = (c >> 1) & 1, cz = (c >> 2) & 1, ct = c >> 3;
         const int pt = ((cellz + cz) * 3 + (celly + cy)) * 9 + cellx + cx;
         const int q = s - 2 + ct;                                       // local plane of the corner
-        return 0.5 * (w3ring[((q + 1) & 3) * W3 + pt] - w3ring[((q - 1) & 3) * W3 + pt]);
+        return 0.5 * (w3ring[((q + 1) & 3) * W3_PITCH + pt] - w3ring[((q - 1) & 3) * W3_PITCH + pt]);
     }
-    ARB_HD static void phase_d(const double* w3ring, double* delta, int s, int tid, int nthr) {
-        for (int e = tid; e < NCELL * 16; e += nthr) {
-            const int c = e & 15, cell = e >> 4;
-            const int cellx = cell & 7, celly = (cell >> 3) & 1, cellz = cell >> 4;
-            const double cur = fxyzt(w3ring, s, c, cellx, celly, cellz);
-            const double prev = (c > 0) ? fxyzt(w3ring, s, c - 1, cellx, celly, cellz) : 0.0;
-            delta[e] = prev - cur;
-        }
+    // phase B: y pass of plane s; with the quirk (and s >= 3) also e[240 + c] of every cell of the layer that
+    // plane s completes
+    ARB_HD static void phase_b(const double* X, double* Y, const double* w3ring, double* delta, int s, int quirk,
+                               int tid, int nthr) {
+        pass_y(X, Y, GZ, TY, tid, nthr);
+        if (quirk && s >= 3)
+            for (int e = tid; e < DELTA_ELEMS; e += nthr) {
+                const int c = e & 15, cell = e >> 4;
+                const int cellx = cell & 7, celly = (cell >> 3) & 1, cellz = cell >> 4;
+                const double cur = fxyzt(w3ring, s, c, cellx, celly, cellz);
+                const double prev = (c > 0) ? fxyzt(w3ring, s, c - 1, cellx, celly, cellz) : 0.0;
+                delta[e] = prev - cur;
+            }
     }
     // phase E: z pass of the new plane fused with the t pass of the layer it completes.
     // task = (cell, j*4 + i): the 4 fresh z-pass values (k = 0..3) replace the oldest ring plane in place after
     // the thread has read it, so the ring needs three slots and no barrier of its own.
+    // Tasks [e_begin, e_end) only: the kernel spreads a step's tasks over its two barrier intervals.
     ARB_HD static void phase_e(const double* Y, double* ring, const double* delta, const SepParams& p, int s, int x0,
-                               int y0, int z0, int64_t layer, int comp, int tid, int nthr) {
+                               int y0, int z0, int64_t layer, int comp, int e_begin, int e_end, int tid, int nthr) {
         const int slot_new = s % 3;                      // holds local plane s-3, receives plane s
         const int slot_1 = (s + 1) % 3, slot_2 = (s + 2) % 3;   // planes s-2, s-1
-        for (int e = tid; e < NCELL * 16; e += nthr) {
+        for (int e = e_begin + tid; e < e_end; e += nthr) {
             const int ji = e & 15, cell = e >> 4;
             const int cx = cell & 7, cy = (cell >> 3) & 1, cz = cell >> 4;
             const double* sy = Y + (cz * TY + cy) * YROW + cx * YCX + ji;

@@ -85,7 +85,9 @@ static double run3(const Grid& g) {
     return check(3, g, table, 0);
 }
 
-static double run4(const Grid& g, int quirk, int lt) {
+// order = +1: threads 0..T-1 within a barrier interval, -1: T-1..0 (an intra-interval dependency between
+// threads would make the two orders disagree)
+static double run4(const Grid& g, int quirk, int lt, int order = 1) {
     using S4 = sep::Sep4;
     sep::SepParams p{};
     int64_t ncell = 1;
@@ -96,6 +98,11 @@ static double run4(const Grid& g, int quirk, int lt) {
     p.table = table.data();
     const int64_t nchunk = (p.nc[3] + p.lt - 1) / p.lt;
     std::vector<double> sm(S4::TOTAL);
+    const int T = S4::THREADS;
+    auto each = [&](auto&& fn) {
+        if (order > 0) for (int t = 0; t < T; ++t) fn(t);
+        else for (int t = T - 1; t >= 0; --t) fn(t);
+    };
     for (int comp = 0; comp < g.ncomp; ++comp)
         for (int64_t chunk = 0; chunk < nchunk; ++chunk)
             for (int64_t tz = 0; tz < p.ntile[2]; ++tz)
@@ -107,23 +114,39 @@ static double run4(const Grid& g, int quirk, int lt) {
                         const int nlayer = (int)((p.nc[3] - t0 < p.lt) ? (p.nc[3] - t0) : p.lt);
                         const int nstep = nlayer + 3;
                         double* base = sm.data();
-                        for (int s = 0; s < nstep; ++s) {
-                            double* plane = base + S4::OFF_PLANE + (s & 1) * S4::PLANE_PITCH;
+                        double *X = base + S4::OFF_X, *Y = base + S4::OFF_Y, *ring = base + S4::OFF_RING,
+                               *w3ring = base + S4::OFF_W3, *delta = base + S4::OFF_DELTA;
+                        auto fetch = [&](int q) {                 // what the TMA unit delivers for plane q
+                            double* plane = base + S4::OFF_PLANE + (q & 1) * S4::PLANE_PITCH;
                             for (int z = 0; z < S4::GZ; ++z)
                                 for (int y = 0; y < S4::GY; ++y)
                                     for (int x = 0; x < sep::GX; ++x)
-                                        plane[(z * S4::GY + y) * sep::GX + x] = g.at(comp, x0 + x, y0 + y, z0 + z, t0 + s);
-                            for (int t = 0; t < S4::THREADS; ++t)
-                                S4::phase_a(plane, base + S4::OFF_X, base + S4::OFF_WX, quirk, t, S4::THREADS);
-                            for (int t = 0; t < S4::THREADS; ++t)
-                                S4::phase_b(base + S4::OFF_X, base + S4::OFF_Y, base + S4::OFF_WX,
-                                            base + S4::OFF_W3 + (s & 3) * S4::W3, quirk, t, S4::THREADS);
-                            if (quirk && s >= 3)
-                                for (int t = 0; t < S4::THREADS; ++t)
-                                    S4::phase_d(base + S4::OFF_W3, base + S4::OFF_DELTA, s, t, S4::THREADS);
-                            for (int t = 0; t < S4::THREADS; ++t)
-                                S4::phase_e(base + S4::OFF_Y, base + S4::OFF_RING, base + S4::OFF_DELTA, p, s, x0, y0, z0,
-                                            t0 + s - 3, comp, t, S4::THREADS);
+                                        plane[(z * S4::GY + y) * sep::GX + x] = g.at(comp, x0 + x, y0 + y, z0 + z, t0 + q);
+                        };
+                        // same schedule as build_sep4_kernel
+                        fetch(0); fetch(1);
+                        each([&](int t) { S4::phase_a(base + S4::OFF_PLANE, X, w3ring, quirk, t, T); });
+                        fetch(2);
+                        each([&](int t) { S4::phase_b(X, Y, w3ring, delta, 0, quirk, t, T); });
+                        for (int s = 0; s < nstep; ++s) {
+                            const int q = s + 1;
+                            const bool more = q < nstep;
+                            const double* Ys = Y + (s & 1) * S4::Y_ELEMS;
+                            const double* ds = delta + (s & 1) * S4::DELTA_ELEMS;
+                            each([&](int t) {
+                                if (more)
+                                    S4::phase_a(base + S4::OFF_PLANE + (q & 1) * S4::PLANE_PITCH, X,
+                                                w3ring + (q & 3) * S4::W3_PITCH, quirk, t, T);
+                                S4::phase_e(Ys, ring, ds, p, s, x0, y0, z0, t0 + s - 3, comp, 0, S4::NTASK_E / 2, t, T);
+                            });
+                            if (more && q + 2 < nstep) fetch(q + 2);
+                            each([&](int t) {
+                                if (more)
+                                    S4::phase_b(X, Y + (q & 1) * S4::Y_ELEMS, w3ring, delta + (q & 1) * S4::DELTA_ELEMS, q,
+                                                quirk, t, T);
+                                S4::phase_e(Ys, ring, ds, p, s, x0, y0, z0, t0 + s - 3, comp, S4::NTASK_E / 2, S4::NTASK_E,
+                                            t, T);
+                            });
                         }
                     }
     return check(4, g, table, quirk);
@@ -159,6 +182,7 @@ int main() {
         Grid g = make_grid(12, 6, 7, 9, 2, 4);
         report("4d 12x6x7x9 C=2 quirk lt=all", run4(g, 1, 1 << 20));
         report("4d 12x6x7x9 C=2 quirk lt=4", run4(g, 1, 4));
+        report("4d 12x6x7x9 C=2 quirk lt=4, threads in reverse order", run4(g, 1, 4, -1));
         report("4d 12x6x7x9 C=2 quirk lt=1", run4(g, 1, 1));
         report("4d 12x6x7x9 C=2 fixed lt=5", run4(g, 0, 5));
         Grid h = make_grid(4, 4, 4, 4, 1, 5);
