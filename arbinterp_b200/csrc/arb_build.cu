@@ -3,22 +3,28 @@
 // (A.py:570-621, 523-525 tricubic; A.py:1322-1381, 1260-1262 quadcubic), which does the same with
 // one Python-level dgemv of the fused matrix A = inv(B) D per cell and component.
 //
-// One CTA builds one tile of cells for one component:
-//   1. TMA (cp.async.bulk.tensor, SASS UTMALDG) stages the grid tile plus its 3-point halo into
-//      shared memory; out-of-range points are zero-filled by the TMA unit and only ever feed
-//      cells that are not stored.
-//   2. stencil stage: the 2^d derivative fields (f, fx, fy, ..., fxyz[t]; central differences in
-//      unit-cell coordinates, the rows of D, A.py:129-173 / 762-876) are evaluated at every
-//      cell-corner point of the tile and kept in shared memory.  A cell's b-vector is a gather
-//      of 2^d corners x 2^d types from these fields, so it is never materialised.
-//   3. solve stage: alpha = inv(B) b on the FP64 tensor cores (mma.sync m8n8k4 f64, SASS DMMA), either
-//      as ONE dense contraction alpha^T[cells x 4^d] = b^T * inv(B)^T (build_kernel; inv(B) is integer,
-//      |entries| <= 27 / 81, read as pre-swizzled fragments from an L1/L2-resident buffer) or, by default,
-//      as TWO small dense contractions that exploit inv(B) = G_hi (x) G_lo (build_kron_kernel, below).
-//      Accumulators stay in registers and go straight to the cell-major table with 16-byte stores.
+// Three formulations of the same solve live here (arb_set_build_variant picks one; all write the same
+// cell-major table and agree to round-off):
+//   * separable, FP64 pipe (default; build_sep3_kernel / build_sep4_kernel, phases in arb_build_sep.cuh):
+//     A factorises into 1-D line transforms, one pass per axis over a TMA-staged grid tile; ~200 FP64
+//     instructions per 3-D cell, so the kernel runs at the HBM write roofline.
+//   * dense, FP64 tensor pipe (build_kernel): one CTA builds one tile of cells for one component,
+//       1. TMA (cp.async.bulk.tensor, SASS UTMALDG) stages the grid tile plus its 3-point halo into
+//          shared memory; out-of-range points are zero-filled by the TMA unit and only ever feed
+//          cells that are not stored.
+//       2. stencil stage: the 2^d derivative fields (f, fx, fy, ..., fxyz[t]; central differences in
+//          unit-cell coordinates, the rows of D, A.py:129-173 / 762-876) are evaluated at every
+//          cell-corner point of the tile and kept in shared memory.  A cell's b-vector is a gather
+//          of 2^d corners x 2^d types from these fields, so it is never materialised.
+//       3. solve stage: alpha^T[cells x 4^d] = b^T * inv(B)^T on the FP64 tensor cores (mma.sync m8n8k4 f64,
+//          SASS DMMA); inv(B) is integer, |entries| <= 27 / 81, read as pre-swizzled fragments from an
+//          L1/L2-resident buffer.  Accumulators go straight to the table with 16-byte stores.
+//   * Kronecker-factored, FP64 tensor pipe (build_kron_kernel): same stencil stage, then TWO small DMMA
+//     contractions that exploit inv(B) = G_hi (x) G_lo.
 // The 4-D reference matrix carries the A.py:860 off-by-one (row 240 of D is zero and rows
-// 241..255 use the stencil centre of the previous corner); it is reproduced in the b-vector gather,
-// where the quadruple-mixed type reads corner c-1 (and 0 for c = 0).
+// 241..255 use the stencil centre of the previous corner); the DMMA kernels reproduce it in the b-vector
+// gather, where the quadruple-mixed type reads corner c-1 (and 0 for c = 0), the separable kernel adds the
+// equivalent rank-16 term in its t pass.
 #include <cstdlib>
 #include <vector>
 #include <mutex>
@@ -227,7 +233,7 @@ build_kernel(const __grid_constant__ CUtensorMap tmap, const BuildParams p) {
 }
 
 // ======================================================================================
-// Kronecker-factored solve (build variant 3)
+// Kronecker-factored solve (build variants 9 and 4)
 // ======================================================================================
 // inv(B) is a Kronecker product of the 1-D cubic Hermite inverse H (4x4, integer):
 //     alpha[kl][ji] = sum_{s_hi, s_lo} G_hi[kl][s_hi] * G_lo[ji][s_lo] * b[s_hi][s_lo]
@@ -444,7 +450,7 @@ build_kron_kernel(const __grid_constant__ CUtensorMap tmap, const BuildParams p)
 
 
 // ======================================================================================
-// Separable build on the FP64 pipe (build variants 5..7; phases in arb_build_sep.cuh)
+// Separable build on the FP64 pipe (build variants 0 and 5..8; phases in arb_build_sep.cuh)
 // ======================================================================================
 // 3-D: one CTA = one tile of 8 x TY x TZ cells of one component.  TMA stages the grid tile, then the x, y
 // and z passes of the 1-D line transform run back to back; the z pass writes the table.
@@ -795,29 +801,30 @@ int arb_build_coeffs(int d, const double* grid, int ncomp, const int64_t n[4], d
     if (ncomp < 1 || ncomp > 4) { arb::set_error("arb_build_coeffs: ncomp=%d not in 1..4", ncomp); return 1; }
     cudaStream_t st = (cudaStream_t)stream;
     const int v = arb::g_build_variant;
-    // variant 0 (default): Kronecker-factored solve (build_kron_kernel); 1-3: the dense 4^d x 4^d contraction
-    // with different tiles (1 = its best); 4: Kronecker with the smaller tile.  profiles/r01_build_configs.log
+    // 0 (default) and 5..8: separable FP64-pipe kernels (build_sep3_kernel / build_sep4_kernel) in different tile /
+    //    march / block-order configurations; 1..3: dense 4^d x 4^d DMMA contraction (1 = its best tile);
+    // 9, 4: Kronecker-factored DMMA solve (9 = its best tile).  profiles/r01_build_variants.log
     if (d == 3) {
-        if (v == 5) return arb::build_sep3_impl<4, 4, 128, 4>(grid, ncomp, n, table, 0, st);
-        if (v == 6) return arb::build_sep3_impl<4, 4, 128, 4>(grid, ncomp, n, table, 1, st);
-        if (v == 7) return arb::build_sep3_impl<4, 8, 256, 2>(grid, ncomp, n, table, 1, st);
-        if (v == 8) return arb::build_sep3_impl<2, 4, 128, 6>(grid, ncomp, n, table, 1, st);
         if (v == 1) return arb::build_impl<arb::Cfg3A>(grid, ncomp, n, table, reference_quirk, st);
         if (v == 2) return arb::build_impl<arb::Cfg3B>(grid, ncomp, n, table, reference_quirk, st);
         if (v == 3) return arb::build_impl<arb::Cfg3C>(grid, ncomp, n, table, reference_quirk, st);
         if (v == 4) return arb::build_impl<arb::Cfg3B, true>(grid, ncomp, n, table, reference_quirk, st);
-        return arb::build_impl<arb::Cfg3A, true>(grid, ncomp, n, table, reference_quirk, st);
+        if (v == 9) return arb::build_impl<arb::Cfg3A, true>(grid, ncomp, n, table, reference_quirk, st);
+        if (v == 5) return arb::build_sep3_impl<4, 4, 128, 4>(grid, ncomp, n, table, 0, st);
+        if (v == 6) return arb::build_sep3_impl<4, 4, 128, 4>(grid, ncomp, n, table, 1, st);
+        if (v == 7) return arb::build_sep3_impl<4, 8, 256, 2>(grid, ncomp, n, table, 1, st);
+        return arb::build_sep3_impl<2, 4, 128, 6>(grid, ncomp, n, table, 1, st);
     }
     if (d == 4) {
-        if (v == 5) return arb::build_sep4_impl(grid, ncomp, n, table, reference_quirk, 0, 0, st);
-        if (v == 6) return arb::build_sep4_impl(grid, ncomp, n, table, reference_quirk, 0, 1, st);
-        if (v == 7) return arb::build_sep4_impl(grid, ncomp, n, table, reference_quirk, 8, 1, st);
-        if (v == 8) return arb::build_sep4_impl(grid, ncomp, n, table, reference_quirk, 3, 1, st);
         if (v == 1) return arb::build_impl<arb::Cfg4B>(grid, ncomp, n, table, reference_quirk, st);
         if (v == 2) return arb::build_impl<arb::Cfg4A>(grid, ncomp, n, table, reference_quirk, st);
         if (v == 3) return arb::build_impl<arb::Cfg4C>(grid, ncomp, n, table, reference_quirk, st);
         if (v == 4) return arb::build_impl<arb::Cfg4B, true>(grid, ncomp, n, table, reference_quirk, st);
-        return arb::build_impl<arb::Cfg4A, true>(grid, ncomp, n, table, reference_quirk, st);
+        if (v == 9) return arb::build_impl<arb::Cfg4A, true>(grid, ncomp, n, table, reference_quirk, st);
+        if (v == 5) return arb::build_sep4_impl(grid, ncomp, n, table, reference_quirk, 0, 0, st);
+        if (v == 7) return arb::build_sep4_impl(grid, ncomp, n, table, reference_quirk, 8, 1, st);
+        if (v == 8) return arb::build_sep4_impl(grid, ncomp, n, table, reference_quirk, 3, 1, st);
+        return arb::build_sep4_impl(grid, ncomp, n, table, reference_quirk, 0, 1, st);
     }
     arb::set_error("arb_build_coeffs: d=%d not in {3,4}", d);
     return 1;

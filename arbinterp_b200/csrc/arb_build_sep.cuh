@@ -1,4 +1,4 @@
-// Separable coefficient build (build variants 5..8): the phases of build_sep3_kernel / build_sep4_kernel.
+// Separable coefficient build (the default; build variants 0 and 5..8): the phases of build_sep3_kernel / build_sep4_kernel.
 //
 // The Lekien-Marsden matrix of the reference, A = inv(B) D (A.py:175, 878), factorises: in 3-D
 // A == M (x) M (x) M exactly, M = 1/2 [[0,2,0,0],[-1,0,1,0],[2,-5,4,-1],[-1,3,-3,1]] being the 1-D map from

@@ -387,6 +387,31 @@ def run_b200(args):
     # sanity inside the bench: outputs are finite for in-volume queries
     assert bool(torch.isfinite(outs[1] if outs[1] is not None else outs[0]).all()), "non-finite outputs in bench"
 
+    # ---- the coefficient-build kernel on its own (rebuilds the table in place; HBM-write roofline)
+    build_info = None
+    if rank == 0 and world == 1:
+        import ctypes
+        lo, hi = obj._slab
+        sub = obj._planes[:, lo:hi + 3].contiguous()
+        npts = (ctypes.c_int64 * 4)(*([obj._geo.npts[a] for a in range(d - 1)] + [hi - lo + 3] + [1] * (4 - d)))
+        stream = torch.cuda.current_stream()
+        times = []
+        for _ in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            _lib.check(lib.arb_build_coeffs(d, sub.data_ptr(), sub.shape[0], ctypes.byref(npts), obj.table.data_ptr(), 1,
+                                            stream.cuda_stream), "build")
+            e1.record(stream)
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        del sub
+        ms = float(np.mean(times[1:]))
+        gb = obj.table.numel() * 8 / 1e9
+        build_info = {"kernel": "coefficient build (arb_build_coeffs, separable FP64-pipe kernel + NaN sentinel row)",
+                      "ms": ms, "table_gb": gb, "achieved_gbs": gb / ms * 1e3, "bound": "hbm (table write)",
+                      "frac_of_measured_hbm": gb / ms * 1e3 / measured_peak()[0],
+                      "cell_components_per_s": obj.nc * obj.table.shape[1] / ms * 1e3, "launches": 3}
+
     # ---- other modes (device-resident), optional
     others = {}
     if not args.no_other_modes and rank == 0 and world == 1:
@@ -409,6 +434,35 @@ def run_b200(args):
                          "queries_per_step": Q2, "table_gb": o2.table.numel() * 8 / 1e9}
             del o2, outs2
             torch.cuda.empty_cache()
+        # quadcubic (time-dependent field, 256x256 Lekien-Marsden matrix with the A.py:860 quirk), value + 4-gradient
+        from arbinterp_b200 import quadcubic
+        shape4 = (48, 48, 48, 32)
+        axes = [torch.linspace(-1.0, 1.0, m, dtype=torch.float64, device=device) for m in shape4[:3]]
+        axes.append(torch.linspace(0.0, 1.0, shape4[3], dtype=torch.float64, device=device))
+        T, Z, Y, X = torch.meshgrid(*reversed(axes), indexing="ij")
+        u = torch.sin(2 * np.pi * X) * torch.cos(np.pi * Y) * torch.exp(-Z) * torch.cos(2 * T) + X * X * Y + Z * (1 + T)
+        t1 = time.perf_counter()
+        o4 = quadcubic(torch.stack([t.reshape(-1) for t in (X, Y, Z, T, u)], dim=1), "quiet")
+        torch.cuda.synchronize()
+        t_ctor4 = time.perf_counter() - t1
+        del T, Z, Y, X, u
+        Q4 = Q // 4
+        g4 = torch.Generator(device=device)
+        g4.manual_seed(4321)
+        lo4 = torch.tensor(o4._geo.int_min, dtype=torch.float64, device=device)
+        hi4 = torch.tensor(o4._geo.int_max, dtype=torch.float64, device=device)
+        q4 = lo4 + torch.rand(Q4, 4, generator=g4, dtype=torch.float64, device=device) * (hi4 - lo4) * (1 - 1e-12)
+        outs4 = alloc_outputs(torch, "norm", 4, Q4, device)
+        el, per = time_device(torch, lib, o4, "norm", 4, q4, outs4, cells[:Q4], args.steps, args.warmup)
+        rate = Q4 * args.steps / el
+        others["quadcubic_norm"] = {"value": rate, "unit": "queries/s", "alg_bytes_per_query": ALG_BYTES[(4, "norm")],
+                                    "achieved_gbs": ALG_BYTES[(4, "norm")] * rate / 1e9,
+                                    "frac_of_measured_hbm": ALG_BYTES[(4, "norm")] * rate / 1e9 / measured_peak()[0],
+                                    "queries_per_step": Q4, "table_gb": o4.table.numel() * 8 / 1e9,
+                                    "workload": "quadcubic scalar field %dx%dx%dx%d (config 4 stand-in), uniform random "
+                                                "(x,y,z,t) queries" % shape4, "constructor_s": t_ctor4}
+        del o4, outs4, q4
+        torch.cuda.empty_cache()
         _, rows = analytic_field_rows(torch, n, device)
         obj = tricubic(rows, "quiet", mode=args.mode)
         del rows
@@ -498,6 +552,8 @@ def run_b200(args):
         "gpu_launches": args.steps * world,
         "clocks": clocks,
     }
+    if build_info:
+        line["build"] = build_info
     if others:
         line["other_modes"] = others
     print(json.dumps(line))

@@ -63,9 +63,10 @@ const char* arb_last_error(void);
 int arb_get_matrix(int d, int which, int reference_quirk, double* out_host);
 
 /* Coefficient build = allCoeffs() (A.py:523-525, 1260-1262) for every cell of `grid`:
- * finite-difference b-vector (A.py:129-173) in shared memory over a TMA-staged grid tile,
- * then the Lekien-Marsden solve alpha = inv(B) b (A.py:175, 577-579) as an FP64 tensor-core
- * contraction.  Writes (prod(n-3) + 1) * C * 4^d doubles to `table` (device), including the
+ * finite-difference b-vector (A.py:129-173) in shared memory over a TMA-staged grid tile and
+ * the Lekien-Marsden solve alpha = inv(B) b (A.py:175, 577-579), by default fused into separable
+ * 1-D line transforms on the FP64 pipe (HBM-write bound); the dense and Kronecker-factored FP64
+ * tensor-core (DMMA) contractions are build variants 1-3 and 9, 4.  Writes (prod(n-3) + 1) * C * 4^d doubles to `table` (device), including the
  * NaN sentinel row.  For slab sharding pass the sub-grid of planes [lo-1, hi+2] of the
  * slowest axis: the build is local to the planes it is given.
  *   n[a] = grid points per axis (x first).  grid/table: device pointers. */
@@ -135,7 +136,8 @@ int arb_permute_rows(double* dst, const double* src, const int64_t* order, int64
 /* Tuning knob for experiments/benchmarks: selects the query-kernel variant
  * (0 = default).  Returns the previous value. */
 int arb_set_query_variant(int variant);
-/* Same for the tile configuration of the build kernel (0 = default). */
+/* Same for the build kernel: 0 = default (separable FP64-pipe kernel), 5-8 its other tile / march
+ * configurations, 1-3 dense DMMA contraction, 9 and 4 Kronecker-factored DMMA solve. */
 int arb_set_build_variant(int variant);
 
 #ifdef __cplusplus

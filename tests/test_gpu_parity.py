@@ -104,7 +104,7 @@ def test_golden_coefficient_table(name, d, modes):
         assert np.array_equal(np.isnan(got[:, -1]), np.isnan(ref[:, -1]))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
 @pytest.mark.parametrize("name,d,modes", CASES)
 def test_build_tile_configurations(name, d, modes, variant, cuda_lib):
     """Every tile configuration of the build kernel produces the reference's coefficient table."""

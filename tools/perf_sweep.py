@@ -86,7 +86,7 @@ def main():
     ap.add_argument("--grid3", type=int, default=256)
     ap.add_argument("--grid4", default="48,48,48,32")
     ap.add_argument("--queries", type=int, default=1 << 25)
-    ap.add_argument("--build-variants", default="0,1,4")
+    ap.add_argument("--build-variants", default="0,9,1")
     ap.add_argument("--table-free", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
