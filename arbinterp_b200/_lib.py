@@ -33,7 +33,12 @@ class ArbGeom(ctypes.Structure):
         ("int_min", ctypes.c_double * 4),
         ("int_max", ctypes.c_double * 4),
         ("h", ctypes.c_double * 4),
+        ("flags", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
     ]
+
+
+GEOM_FIXED_D4 = 1
 
 
 class ArbError(RuntimeError):

@@ -23,6 +23,7 @@
 //   2  DIRECT: one query per thread reading its block straight from global memory
 //             (32 uncoalesced LDG.128 per component); kept as the naive baseline.
 #include "arb_device.cuh"
+#include "arb_gridfree.cuh"
 
 namespace arb {
 
@@ -365,17 +366,7 @@ struct GridQueryParams {
     QueryParams q;
 };
 
-__device__ __forceinline__ void catmull_rom(double t, double (&w)[4], double (&dw)[4]) {
-    const double t2 = t * t, t3 = t2 * t;
-    w[0] = fma(-0.5, t3, fma(1.0, t2, -0.5 * t));
-    w[1] = fma(1.5, t3, fma(-2.5, t2, 1.0));
-    w[2] = fma(-1.5, t3, fma(2.0, t2, 0.5 * t));
-    w[3] = fma(0.5, t3, -0.5 * t2);
-    dw[0] = fma(-1.5, t2, fma(2.0, t, -0.5));
-    dw[1] = fma(4.5, t2, -5.0 * t);
-    dw[2] = fma(-4.5, t2, fma(4.0, t, 0.5));
-    dw[3] = fma(1.5, t2, -t);
-}
+using gridfree::catmull_rom;
 
 template <int MODE, int THREADS>
 __global__ void __launch_bounds__(THREADS) query_grid_kernel(const __grid_constant__ CUtensorMap tmap, const QueryParams p) {
@@ -478,6 +469,119 @@ __global__ void __launch_bounds__(THREADS) query_grid_kernel(const __grid_consta
                 p.out_grad[n * 3 + 0] = L.ok ? __ddiv_rn(gx, p.h[0]) : nan;
                 p.out_grad[n * 3 + 1] = L.ok ? __ddiv_rn(gy, p.h[1]) : nan;
                 p.out_grad[n * 3 + 2] = L.ok ? __ddiv_rn(gz, p.h[2]) : nan;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// 4-D table-free query (quadcubic(..., table=False)).  Four adjacent lanes own the four grid planes
+// l = 0..3 of (query, component): each fetches its plane's 6x4x4 box through a 5-D tensor map, contracts it
+// with the Catmull-Rom weights in (u, v, w) and scales by the t weight of its plane; with the reference quirk
+// (A.py:860) the lanes also accumulate the plane's signed parity sums, exchange them over two shuffles to form
+// fxyzt at the cell's 16 corners, and lanes 0/1 add the rank-16 term of their ct (arb_gridfree.cuh).  The four
+// partial results are summed over two more shuffle steps.
+template <int MODE, int THREADS, bool QUIRK>
+__global__ void __launch_bounds__(THREADS) query_grid4_kernel(const __grid_constant__ CUtensorMap tmap, const QueryParams p) {
+    constexpr int D = 4;
+    constexpr int C = MODE == 0 ? 3 : (MODE == 1 ? 1 : 4);
+    constexpr uint32_t BYTES = 6 * 4 * 4 * 8;     // 768
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bars[THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int qi = lane >> 2, l = lane & 3;
+    uint64_t* bar = &bars[wid];
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    const int64_t warp_global = ((int64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * THREADS) >> 5;
+    const int64_t nbatch = (p.N + 7) / 8;
+    const int64_t nitem = nbatch * C;
+    const int rj = lane & 3, rk = (lane >> 2) & 1;     // row rotation of this lane
+    const unsigned char* slot = smem + (size_t)threadIdx.x * BYTES;
+    uint32_t phase = 0;
+    for (int64_t item = warp_global; item < nitem; item += nwarps) {
+        const int64_t batch = item / C;
+        const int comp = (int)(item - batch * C);
+        const int64_t n = batch * 8 + qi;
+        Located<D> L;
+        L.ok = false; L.masked = false; L.cell_global = 0; L.cell_local = 0;
+        L.idx[0] = L.idx[1] = L.idx[2] = L.idx[3] = 0;
+        L.frac[0] = L.frac[1] = L.frac[2] = L.frac[3] = 0.0;
+        if (n < p.N) L = locate<D>(p, n);
+        const unsigned fmask = __ballot_sync(0xffffffffu, L.ok);
+        if (lane == 0) mbar_expect_tx(bar, (uint32_t)__popc(fmask) * BYTES);
+        __syncwarp();
+        const int off = L.idx[0] & 1;
+        if (L.ok) tma_load_5d(const_cast<unsigned char*>(slot), &tmap, bar, L.idx[0] - off, L.idx[1], L.idx[2], L.idx[3] + l, comp);
+        if (comp == 0 && l == 0 && n < p.N) {
+            if (p.out_cell) p.out_cell[n] = L.cell_global;
+            if (L.masked) mask_row_in_place(p, n);
+        }
+        // weights while the box is in flight
+        double wx[4], dwx[4], wy[4], dwy[4], wz[4], dwz[4], wt[4], dwt[4];
+        catmull_rom(L.frac[0], wx, dwx);
+        catmull_rom(L.frac[1], wy, dwy);
+        catmull_rom(L.frac[2], wz, dwz);
+        catmull_rom(L.frac[3], wt, dwt);
+        const double wt_l = gridfree::sel4(wt, l), dwt_l = gridfree::sel4(dwt, l);
+        const bool grad_comp = (MODE == 1) || (MODE == 2 && comp == 3);     // warp-uniform
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        gridfree::PlanePartial pp;
+        pp.val = pp.gx = pp.gy = pp.gz = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pp.S[i] = 0.0;
+        if (L.ok) {
+            if (grad_comp) gridfree::plane_partial<true, QUIRK>(slot, off, rj, rk, wx, dwx, wy, dwy, wz, dwz, pp);
+            else gridfree::plane_partial<false, QUIRK>(slot, off, rj, rk, wx, dwx, wy, dwy, wz, dwz, pp);
+        }
+        double m[5] = {pp.val * wt_l, pp.gx * wt_l, pp.gy * wt_l, pp.gz * wt_l, pp.val * dwt_l};
+        if (QUIRK) {
+            // fxyzt at the 8 corners of ct = l & 1: planes ct + 2 and ct are held by lanes l | 2 and l & 1
+            double g[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const double other = __shfl_xor_sync(0xffffffffu, pp.S[i], 2);
+                g[i] = 0.0625 * ((l >= 2) ? (pp.S[i] - other) : (other - pp.S[i]));
+            }
+            const double g7_other = __shfl_xor_sync(0xffffffffu, g[7], 1);
+            const int ct = l & 1;
+            double hx[2], dhx[2], hy[2], dhy[2], hz[2], dhz[2], ht[2], dht[2], c[4];
+            gridfree::hermite_slope(L.frac[0], hx, dhx);
+            gridfree::hermite_slope(L.frac[1], hy, dhy);
+            gridfree::hermite_slope(L.frac[2], hz, dhz);
+            gridfree::hermite_slope(L.frac[3], ht, dht);
+            if (grad_comp) gridfree::corner_term<true>(g, ct ? g7_other : 0.0, hx, dhx, hy, dhy, hz, dhz, c);
+            else gridfree::corner_term<false>(g, ct ? g7_other : 0.0, hx, dhx, hy, dhy, hz, dhz, c);
+            if (l < 2) {          // lanes 2, 3 hold copies of the same corners
+                const double h = ct ? ht[1] : ht[0], dh = ct ? dht[1] : dht[0];
+                m[0] = fma(h, c[0], m[0]);
+                m[1] = fma(h, c[1], m[1]);
+                m[2] = fma(h, c[2], m[2]);
+                m[3] = fma(h, c[3], m[3]);
+                m[4] = fma(dh, c[0], m[4]);
+            }
+        }
+        const int nred = grad_comp ? 5 : 1;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            if (i < nred) {
+                m[i] += __shfl_xor_sync(0xffffffffu, m[i], 1);
+                m[i] += __shfl_xor_sync(0xffffffffu, m[i], 2);
+            }
+        }
+        if (n < p.N && l == 0) {
+            const double nan = qnan();
+            if (!grad_comp) {
+                p.out_comps[n * 3 + comp] = L.ok ? m[0] : nan;
+            } else {
+                p.out_norm[n] = L.ok ? m[0] : nan;
+#pragma unroll
+                for (int a = 0; a < D; ++a) p.out_grad[n * D + a] = L.ok ? __ddiv_rn(m[1 + a], p.h[a]) : nan;
             }
         }
         __syncwarp();
@@ -647,6 +751,19 @@ static int launch_grid(const CUtensorMap& tm, const QueryParams& p, cudaStream_t
     return check_cuda(cudaGetLastError(), "query_grid_kernel launch");
 }
 
+template <int MODE, bool QUIRK>
+static int launch_grid4(const CUtensorMap& tm, const QueryParams& p, cudaStream_t st) {
+    constexpr int C = MODE == 0 ? 3 : (MODE == 1 ? 1 : 4);
+    constexpr int THREADS = 128;
+    const size_t smem = (size_t)THREADS * 768;
+    auto k = query_grid4_kernel<MODE, THREADS, QUIRK>;
+    static LaunchCache cache = {};
+    const int64_t items = ((p.N + 7) / 8) * C;
+    const int grid = persistent_grid(k, THREADS, smem, (items + THREADS / 32 - 1) / (THREADS / 32), cache);
+    k<<<grid, THREADS, smem, st>>>(tm, p);
+    return check_cuda(cudaGetLastError(), "query_grid4_kernel launch");
+}
+
 int query_grid_device(const arb_geom* g, const double* grid, int64_t pitch_x, int mode, double* q, int64_t N,
                       int64_t ldq, double* out_comps, double* out_norm, double* out_grad, int64_t* out_cell,
                       int64_t* masked_rows, unsigned long long* masked_count, cudaStream_t st) {
@@ -654,12 +771,13 @@ int query_grid_device(const arb_geom* g, const double* grid, int64_t pitch_x, in
     const int rc = fill_params("arb_query_grid", g, true, grid, mode, q, N, ldq, out_comps, out_norm, out_grad,
                                out_cell, masked_rows, masked_count, p);
     if (rc) return rc < 0 ? 0 : rc;
-    if (g->d != 3) { set_error("arb_query_grid: only the tricubic (d=3) path has a table-free form"); return 1; }
-    if (g->slab_lo != 0 || g->slab_hi != g->ncell[2]) { set_error("arb_query_grid: slabs are not supported"); return 1; }
-    const int64_t nx = g->ncell[0] + 3, ny = g->ncell[1] + 3, nz = g->ncell[2] + 3;
-    if (pitch_x < nx || (pitch_x & 1) || (reinterpret_cast<uintptr_t>(grid) & 15)) {
+    const int d = g->d;
+    if (g->slab_lo != 0 || g->slab_hi != g->ncell[d - 1]) { set_error("arb_query_grid: slabs are not supported"); return 1; }
+    int64_t npt[4] = {1, 1, 1, 1};
+    for (int a = 0; a < d; ++a) npt[a] = g->ncell[a] + 3;
+    if (pitch_x < npt[0] || (pitch_x & 1) || (reinterpret_cast<uintptr_t>(grid) & 15)) {
         set_error("arb_query_grid: row pitch must be even and >= nx, grid 16-byte aligned (pitch=%lld nx=%lld)",
-                  (long long)pitch_x, (long long)nx);
+                  (long long)pitch_x, (long long)npt[0]);
         return 1;
     }
     static EncodeTiledFn encode = nullptr;
@@ -673,17 +791,31 @@ int query_grid_device(const arb_geom* g, const double* grid, int64_t pitch_x, in
         }
         encode = reinterpret_cast<EncodeTiledFn>(ptr);
     }
+    // grid [C][nt][nz][ny][pitch_x]: rank d + 1, box = 6 x 4 x 4 points of one plane of one component
     CUtensorMap tm;
-    cuuint64_t gdim[4] = {(cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)nz, (cuuint64_t)g->ncomp};
-    cuuint64_t gstr[3] = {(cuuint64_t)pitch_x * 8, (cuuint64_t)pitch_x * ny * 8, (cuuint64_t)pitch_x * ny * nz * 8};
-    cuuint32_t box[4] = {6, 4, 4, 1}, estr[4] = {1, 1, 1, 1};
-    const CUresult cr = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double*>(grid), gdim, gstr, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t box[5] = {6, 4, 4, 1, 1}, estr[5] = {1, 1, 1, 1, 1};
+    gdim[0] = (cuuint64_t)npt[0];
+    uint64_t stride = (uint64_t)pitch_x * 8;
+    for (int a = 1; a < d; ++a) { gdim[a] = (cuuint64_t)npt[a]; gstr[a - 1] = stride; stride *= (uint64_t)npt[a]; }
+    gdim[d] = (cuuint64_t)g->ncomp; gstr[d - 1] = stride;
+    const CUresult cr = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, d + 1, const_cast<double*>(grid), gdim, gstr, box,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { set_error("arb_query_grid: cuTensorMapEncodeTiled failed with CUresult %d", (int)cr); return 2; }
-    if (mode == ARB_MODE_VECTOR) return launch_grid<0>(tm, p, st);
-    if (mode == ARB_MODE_NORM) return launch_grid<1>(tm, p, st);
-    return launch_grid<2>(tm, p, st);
+    if (d == 3) {
+        if (mode == ARB_MODE_VECTOR) return launch_grid<0>(tm, p, st);
+        if (mode == ARB_MODE_NORM) return launch_grid<1>(tm, p, st);
+        return launch_grid<2>(tm, p, st);
+    }
+    if (g->flags & ARB_GEOM_FIXED_D4) {       // corrected 4-D matrix: plain M^(x)4
+        if (mode == ARB_MODE_VECTOR) return launch_grid4<0, false>(tm, p, st);
+        if (mode == ARB_MODE_NORM) return launch_grid4<1, false>(tm, p, st);
+        return launch_grid4<2, false>(tm, p, st);
+    }
+    if (mode == ARB_MODE_VECTOR) return launch_grid4<0, true>(tm, p, st);
+    if (mode == ARB_MODE_NORM) return launch_grid4<1, true>(tm, p, st);
+    return launch_grid4<2, true>(tm, p, st);
 }
 
 }  // namespace arb

@@ -15,8 +15,9 @@ Differences a user can observe, all documented in DESIGN.md:
     (the reference wraps into a neighbouring cell or raises, SURVEY 7.2);
   * ``quiet=True`` is accepted as a keyword as well as the positional string ``'quiet'``;
   * torch CUDA tensors are accepted as queries and then returned as CUDA tensors;
-  * ``tricubic(..., table=False)`` keeps no coefficient table at all and evaluates every query from
-    its 4x4x4 grid neighbourhood (for fields that change often; CHANGELOG.md:9 of the reference);
+  * ``tricubic(..., table=False)`` / ``quadcubic(..., table=False)`` keep no coefficient table at all and
+    evaluate every query from its 4^d grid neighbourhood (for fields that change often; CHANGELOG.md:9 of the
+    reference); the 4-D form adds the rank-16 term that reproduces A.py:860 unless ``fixed_d4=True``;
   * ``save(path)`` / ``load(path)`` persist the coefficient table.
 """
 from __future__ import annotations
@@ -118,9 +119,8 @@ class _CubicInterpolator:
         self._slab = (lo, hi)
         self._table_free = kwargs.get("table", True) is False
         if self._table_free:
-            if d != 3 or (lo, hi) != (0, nslow):
-                raise ValueError("table=False is available for unsharded tricubic interpolators only "
-                                 "(the 4-D reference matrix is not a Kronecker product, A.py:860)")
+            if (lo, hi) != (0, nslow):
+                raise ValueError("table=False is available for unsharded interpolators only")
             self._table = None
             nx = geo.npts[0]
             self._pitch = nx + (nx & 1)                           # TMA needs 16-byte row strides
@@ -166,6 +166,7 @@ class _CubicInterpolator:
             g.int_max[a] = geo.int_max[a] if a < d else 0.0
             g.h[a] = geo.h[a] if a < d else 1.0
         g.slab_lo, g.slab_hi = self._slab
+        g.flags = 0 if self._reference_quirk else _lib.GEOM_FIXED_D4
         self._cgeom = g
 
     # ------------------------------------------------------------------ persistence (CHANGELOG.md:9 "save these coefficients to a file")

@@ -50,7 +50,13 @@ typedef struct arb_geom {
     double  int_min[4];   /* xIntMin.. : second grid coordinate per axis (A.py:551-553)          */
     double  int_max[4];   /* xIntMax.. : second-to-last grid coordinate  (A.py:554-556)          */
     double  h[4];         /* hx.. = |axis[0]-axis[1]| (A.py:547-549)                             */
+    int32_t flags;        /* ARB_GEOM_* bits; 0 = reference behaviour                            */
+    int32_t reserved;
 } arb_geom;
+
+/* Table-free quadcubic queries evaluate with the corrected 4-D matrix (no A.py:860 off-by-one) when this
+ * bit is set; coefficient tables carry the choice made at build time (arb_build_coeffs' reference_quirk). */
+#define ARB_GEOM_FIXED_D4 1
 
 const char* arb_version(void);
 const char* arb_last_error(void);
@@ -104,11 +110,12 @@ int arb_query_host(const arb_geom* g, const double* table, int mode, double* q_h
                    double* out_comps_host, double* out_norm_host, double* out_grad_host,
                    int64_t* out_cell_host, int64_t chunk_rows);
 
-/* Table-free tricubic query (d = 3 only): evaluates straight from the 4x4x4 grid neighbourhood
- * -- no coefficient table, no build, 64x less memory; about half the throughput of arb_query.
- * It is the reference's lazy path taken to its limit (A.py:376-377 computes a cell's coefficients
- * on first touch; here nothing is ever stored) and relies on A = M(x)M(x)M being exact in 3-D.
- *   grid    : device [C][nz][ny][pitch_x] float64, nx = ncell[0]+3 etc.; pitch_x even, >= nx.
+/* Table-free query: evaluates straight from the 4^d grid neighbourhood -- no coefficient table, no
+ * build, 4^d x less memory; about half the throughput of arb_query.  It is the reference's lazy path
+ * taken to its limit (A.py:376-377 computes a cell's coefficients on first touch; here nothing is ever
+ * stored) and relies on A = M(x)M(x)M being exact in 3-D; in 4-D the reference matrix is M^(x)4 plus a
+ * rank-16 term (A.py:860), which the kernel adds from the cell's 16 corner values of fxyzt.
+ *   grid    : device [C][nt][nz][ny][pitch_x] float64, nx = ncell[0]+3 etc.; pitch_x even, >= nx.
  * Other arguments as arb_query / arb_query_host. */
 int arb_query_grid(const arb_geom* g, const double* grid, int64_t pitch_x, int mode, double* q, int64_t N,
                    int64_t ldq, double* out_comps, double* out_norm, double* out_grad, int64_t* out_cell,

@@ -399,18 +399,18 @@ def test_save_and_load_coefficients(name, d, mode, tmp_path):
         _cls(7 - d).load(str(path))
 
 
-@pytest.mark.parametrize("name,modes", [("tri_12x10x9", ["vector", "norm", "both"]), ("tri_scalar_9x8x11", ["scalar"])])
-def test_table_free_path_golden(name, modes):
-    """tricubic(table=False): no coefficient table, every query evaluated from its 4x4x4 neighbourhood
-    (odd nx = 9 exercises the padded TMA pitch).  Same parity bar as the table path."""
-    from arbinterp_b200 import tricubic
+@pytest.mark.parametrize("name,d,modes", CASES)
+def test_table_free_path_golden(name, d, modes):
+    """tricubic / quadcubic(table=False): no coefficient table, every query evaluated from its 4^d grid
+    neighbourhood (odd nx = 9 exercises the padded TMA pitch; the 4-D cases exercise the rank-16 term that
+    reproduces A.py:860).  Same parity bar as the table path."""
     g = load_golden(name)
     for mode in modes:
         kw = {} if mode == "scalar" else {"mode": mode}
-        obj = tricubic(g["field"].copy(), "quiet", table=False, **kw)
+        obj = _cls(d)(g["field"].copy(), "quiet", table=False, **kw)
         q = g[mode + "_q_in"].copy()
         res = obj.Query(q)
-        _check_outputs(res, _golden_ref(g, mode), mode, g["field"], 3, g["h"], f"{name}/{mode}/table-free")
+        _check_outputs(res, _golden_ref(g, mode), mode, g["field"], d, g["h"], f"{name}/{mode}/table-free")
         assert np.array_equal(q, g[mode + "_q_after"], equal_nan=True)
         assert np.array_equal(obj.queryInds, g[mode + "_inds"])
         with pytest.raises(AttributeError):
@@ -418,8 +418,7 @@ def test_table_free_path_golden(name, modes):
         if mode in ("vector", "scalar"):
             assert np.array_equal(obj.inputfield, g["sorted_field"])      # padded pitch is not visible
     with pytest.raises(ValueError):
-        from arbinterp_b200 import quadcubic
-        quadcubic(load_golden("quad_8x7x7x6")["field"], "quiet", table=False)
+        _cls(d)(g["field"].copy(), "quiet", table=False, slab=(0, 1))
 
 
 @pytest.mark.parametrize("mode", ["vector", "norm", "both"])
@@ -442,6 +441,45 @@ def test_table_free_matches_table_path(mode):
     dev = dev if isinstance(dev, tuple) else (dev,)
     for x, y in zip(rb, dev):
         assert np.array_equal(x, y.cpu().numpy(), equal_nan=True)
+
+
+def _analytic_field4(nx, ny, nz, nt, rng=None):
+    x = np.linspace(-1.0, 1.0, nx); y = np.linspace(-0.7, 0.9, ny); z = np.linspace(0.0, 1.5, nz)
+    t = np.linspace(0.0, 2.0, nt)
+    T, Z, Y, X = [a.ravel() for a in np.meshgrid(t, z, y, x, indexing="ij")]
+    cols = [X, Y, Z, T, np.sin(2 * np.pi * X) * np.cos(np.pi * Y) * np.exp(-Z) * np.cos(T), X * X * Y + Z * (1 + T) + X * Y * Z * T,
+            np.cos(X + Y + Z + T)]
+    f = np.stack(cols, axis=1)
+    return f if rng is None else f[rng.permutation(len(f))]
+
+
+@pytest.mark.parametrize("fixed", [False, True])
+@pytest.mark.parametrize("mode", ["vector", "norm", "both"])
+def test_table_free_quadcubic_matches_table_path(mode, fixed):
+    """4-D table-free kernel against the table path on the same field (xyzt monomial present, so the A.py:860
+    term is visible: the quirk and fixed_d4 results differ by ~1e-6 and each must match its own table)."""
+    from arbinterp_b200 import quadcubic
+    rng = np.random.default_rng(78)
+    field = _analytic_field4(13, 11, 10, 9, rng=rng)
+    a = quadcubic(field.copy(), "quiet", mode=mode, fixed_d4=fixed)
+    b = quadcubic(field.copy(), "quiet", mode=mode, fixed_d4=fixed, table=False)
+    q = _uniform_queries(a, 4, 100_003, rng, extra=2)
+    q[::97, 3] = 1e3
+    qa, qb = q.copy(), q.copy()
+    ra, rb = a.Query(qa), b.Query(qb)
+    hs = [a.hx, a.hy, a.hz, a.ht]
+    ra = ra if isinstance(ra, tuple) else (ra,)
+    rb = rb if isinstance(rb, tuple) else (rb,)
+    _check_outputs(rb, ra, mode, field, 4, hs, f"4-D table-free vs table {mode} fixed={fixed}")
+    assert np.array_equal(qa, qb, equal_nan=True) and np.array_equal(a.queryInds, b.queryInds)
+    dev = b.Query(torch.from_numpy(q.copy()).cuda())
+    dev = dev if isinstance(dev, tuple) else (dev,)
+    for x, y in zip(rb, dev):
+        assert np.array_equal(x, y.cpu().numpy(), equal_nan=True)
+    if mode == "norm":
+        other = quadcubic(field.copy(), "quiet", mode=mode, fixed_d4=not fixed, table=False).Query(q.copy())
+        ok = ~np.isnan(rb[0][:, 0])
+        assert np.abs(other[0][ok] - rb[0][ok]).max() > 1e-9, "quirk and corrected matrices must differ on this field"
 
 
 def _verlet_reference(query_grad, pos, vel, dt, nsteps, kappa, g):

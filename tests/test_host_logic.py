@@ -134,6 +134,25 @@ def test_separable_build_phases_on_host(tmp_path):
     assert len(errs) >= 10 and max(errs) <= 1e-12
 
 
+def test_table_free_quadcubic_math_on_host(tmp_path):
+    """The __host__ __device__ pieces of the 4-D table-free kernel (plane contraction with rotated row order,
+    parity sums, rank-16 corner term), combined as the kernel's four lanes combine them, equal the monomial
+    evaluation of A f with and without the A.py:860 quirk."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "gridfree4_host_emul")
+    subprocess.run([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", exe,
+                    os.path.join(ROOT, "tests", "host_emul", "gridfree4_host_emul.cu"),
+                    os.path.join(ROOT, "arbinterp_b200", "csrc", "arb_core.cu")], check=True, timeout=600)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    errs = [float(x) for x in re.findall(r"max scaled error ([0-9.eE+-]+)", out.stdout)]
+    assert out.returncode == 0, out.stdout
+    assert len(errs) >= 4 and max(errs) <= 1e-12
+
+
 def test_argument_validation_without_gpu():
     lib = _lib.load()
     g = _lib.ArbGeom()

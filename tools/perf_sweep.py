@@ -126,15 +126,15 @@ def main():
                           f"({ALG_BYTES[(d, mode)] * rate / 1e9 / 6458.4:.3f} of measured copy peak)", flush=True)
                 except Exception as e:  # noqa: BLE001
                     print(f"[query] d={d} mode={mode} variant={v}: FAILED {e}", flush=True)
-            if d == 3 and args.table_free:
+            if args.table_free:
                 del obj
                 torch.cuda.empty_cache()
                 rows = field_rows(shape, dev)
-                tf = tricubic(rows, "quiet", mode=mode, table=False)
+                tf = (tricubic if d == 3 else quadcubic)(rows, "quiet", mode=mode, table=False)
                 del rows
                 comps = torch.empty(q.shape[0], 3, dtype=torch.float64, device=dev) if mode in ("vector", "both") else None
                 norm = torch.empty(q.shape[0], 1, dtype=torch.float64, device=dev) if mode in ("norm", "both") else None
-                grad = torch.empty(q.shape[0], 3, dtype=torch.float64, device=dev) if mode in ("norm", "both") else None
+                grad = torch.empty(q.shape[0], d, dtype=torch.float64, device=dev) if mode in ("norm", "both") else None
                 cells = torch.empty(q.shape[0], dtype=torch.int64, device=dev)
                 ptr = lambda t: None if t is None else t.data_ptr()
                 st = torch.cuda.current_stream()
@@ -149,7 +149,7 @@ def main():
                     launch()
                 e1.record(st); torch.cuda.synchronize()
                 rate = q.shape[0] * 5 / (e0.elapsed_time(e1) / 1e3)
-                print(f"[query] d=3 mode={mode} TABLE-FREE grid={shape}: {rate:.4e} q/s (grid {tf._planes.numel() * 8 / 1e6:.0f} MB)", flush=True)
+                print(f"[query] d={d} mode={mode} TABLE-FREE grid={shape}: {rate:.4e} q/s (grid {tf._planes.numel() * 8 / 1e6:.0f} MB)", flush=True)
                 del tf
                 obj = None
             del obj, q

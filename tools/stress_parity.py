@@ -25,7 +25,7 @@ for case in range(a.cases):
     vals = [np.sin(arg + phase[0])] if scalar else [np.sin(arg + phase[0]), np.cos(1.7 * arg + phase[1]) + 0.1 * arg, np.sin(0.6 * arg + phase[2]) * arg]
     field = np.stack(coords + vals, axis=1)[rng.permutation(len(coords[0]))]
     mode = "scalar" if scalar else str(rng.choice(["vector", "norm", "both"]))
-    table_free = d == 3 and bool(rng.integers(0, 3) == 0)
+    table_free = bool(rng.integers(0, 3) == 0)
     bv = int(rng.integers(0, 10)); qv = int(rng.choice([0, 1, 2, 10, 11, 20, 21, 22, 23, 30]))
     kw = {} if scalar else {"mode": mode}
     if table_free:
