@@ -22,6 +22,10 @@ for mode in ("vector", "norm", "both"):
             lib.arb_set_query_variant(v)
             o.Query(q.copy())
         lib.arb_set_query_variant(0)
+    for bv in (5, 7, 8, 9):                       # every formulation of the build (default 0 is used below)
+        lib.arb_set_build_variant(bv)
+        tricubic(f3, "quiet", mode=mode); quadcubic(f4, "quiet", mode=mode)
+    lib.arb_set_build_variant(0)
     o4 = quadcubic(f4, "quiet", mode=mode)
     q4 = np.stack([rng.uniform(o4.xIntMin, o4.xIntMax, 300), rng.uniform(o4.yIntMin, o4.yIntMax, 300),
                    rng.uniform(o4.zIntMin, o4.zIntMax, 300), rng.uniform(o4.tIntMin, o4.tIntMax * 1.1, 300)], 1)
@@ -29,4 +33,6 @@ for mode in ("vector", "norm", "both"):
         lib.arb_set_query_variant(v)
         o4.Query(q4.copy())
     lib.arb_set_query_variant(0)
+    for fixed in (False, True):
+        quadcubic(f4, "quiet", mode=mode, table=False, fixed_d4=fixed).Query(q4.copy())
 print("sanitize target done")
