@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import warnings
 from dataclasses import dataclass, field as dc_field
-from typing import List
+from typing import List, Optional
 
 import torch
 
@@ -29,6 +29,7 @@ class Geometry:
     int_min: List[float]       # xIntMin.. = 2nd grid coordinate (A.py:551-553)
     int_max: List[float]       # xIntMax.. = 2nd-to-last grid coordinate (A.py:554-556)
     axes: List[torch.Tensor] = dc_field(default_factory=list, repr=False)
+    row_index: Optional[torch.Tensor] = dc_field(default=None, repr=False)   # grid index of every input row
 
     @property
     def nc(self) -> int:       # A.py:568, 1320
@@ -116,7 +117,8 @@ def ingest_field(field, d: int, device=None, spacing_rtol: float = 1e-6):
         h.append(float(step))
         lo.append(float(ax[1]))
         hi.append(float(ax[-2]))
-    geo = Geometry(d=d, npts=npts, ncell=[n - 3 for n in npts], h=h, int_min=lo, int_max=hi, axes=axes)
+    geo = Geometry(d=d, npts=npts, ncell=[n - 3 for n in npts], h=h, int_min=lo, int_max=hi, axes=axes,
+                   row_index=lin.to(torch.int32) if total < 2 ** 31 else lin)   # kept for update_values(order='rows')
     return planes, geo
 
 

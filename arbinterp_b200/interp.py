@@ -98,16 +98,7 @@ class _CubicInterpolator:
         self._mode = mode
         self._mode_code = {"vector": _lib.MODE_VECTOR, "norm": _lib.MODE_NORM, "both": _lib.MODE_BOTH}[mode]
 
-        # value planes the table is built from, in table component order
-        if scalar:
-            comp = planes[0:1]
-        elif mode == "vector":
-            comp = planes[0:3]
-        elif mode == "norm":
-            comp = norm_plane(planes[0:3]).unsqueeze(0)
-        else:
-            comp = torch.cat([planes[0:3], norm_plane(planes[0:3]).unsqueeze(0)], dim=0)
-        self._planes = comp.contiguous()
+        self._planes = self._component_planes(planes)
         del planes
 
         self._set_geometry_attributes()
@@ -133,6 +124,61 @@ class _CubicInterpolator:
         self.queryInd = None
 
         self._bind_mode()
+
+    def _component_planes(self, planes):
+        """Value planes the table is built from, in table component order (A.py:32, 58, 74 and the 4-D twins)."""
+        if self._scalar_input:
+            comp = planes[0:1]
+        elif self._mode == "vector":
+            comp = planes[0:3]
+        elif self._mode == "norm":
+            comp = norm_plane(planes[0:3]).unsqueeze(0)
+        else:
+            comp = torch.cat([planes[0:3], norm_plane(planes[0:3]).unsqueeze(0)], dim=0)
+        return comp.contiguous()
+
+    def update_values(self, values, order="rows"):
+        """Replace the field values on the same grid and rebuild in place -- no re-ingest, no reallocation.
+
+        The reference has no such call: a changed field means a new object and, with it, a new lazy coefficient
+        fill ("not a good idea ... where you are frequently updating the field", CHANGELOG.md:9).  Here the
+        rebuild of a 256^3 table is one 1.2 ms kernel, so time-varying fields can keep their table.
+        ``values``: (N, 1) / (N,) for scalar input or (N, 3) for vector input, array-like or tensor (CUDA tensors
+        are not copied through the host).  ``order='rows'``: in the row order of the ``field`` array the object was
+        constructed from; ``order='grid'``: in sorted grid order (x fastest -- the row order of ``inputfield``).
+        Results afterwards are bit-identical to a freshly constructed interpolator of the updated field."""
+        if self._planes is None:
+            raise ValueError("update_values() needs the field planes; an interpolator restored with load() has none")
+        geo, d = self._geo, self._d
+        ncol = 1 if self._scalar_input else 3
+        v = torch.as_tensor(values)
+        if v.dim() == 1:
+            v = v.unsqueeze(1)
+        total = 1
+        for n in geo.npts:
+            total *= n
+        if v.dim() != 2 or tuple(v.shape) != (total, ncol):
+            raise ValueError(f"values must have shape ({total}, {ncol}), got {tuple(v.shape)}")
+        v = v.to(device=self._device, dtype=torch.float64)
+        if order == "rows":
+            if geo.row_index is None:
+                raise ValueError("order='rows' needs the row map of the constructor's field; this interpolator was "
+                                 "built from pre-ingested planes -- pass order='grid'")
+            planes = torch.empty((ncol, total), dtype=torch.float64, device=self._device)
+            planes[:, geo.row_index.to(self._device).long()] = v.T
+        elif order == "grid":
+            planes = v.T.contiguous()
+        else:
+            raise ValueError("order must be 'rows' or 'grid'")
+        self._planes = self._component_planes(planes.reshape([ncol] + list(geo.npts[::-1])))
+        del planes
+        if self._table is None:
+            if self._pitch != geo.npts[0]:
+                self._planes = torch.nn.functional.pad(self._planes, (0, 1)).contiguous()
+        else:
+            self._build_table()
+        self._last_cells = None
+        self.queryInd = None
 
     def _bind_mode(self):
         # bind the mode-specific entry points like the reference does (A.py:27-30, 38-41, ...)
@@ -252,7 +298,8 @@ class _CubicInterpolator:
             layer *= geo.ncell[a]
         ncell_local = layer * (hi - lo)
         sub = self._planes[:, lo:hi + 3].contiguous()          # cell layer k needs grid planes k..k+3
-        self._table = torch.empty((ncell_local + 1, ncomp, nm), dtype=torch.float64, device=self._device)
+        if getattr(self, "_table", None) is None or tuple(self._table.shape) != (ncell_local + 1, ncomp, nm):
+            self._table = torch.empty((ncell_local + 1, ncomp, nm), dtype=torch.float64, device=self._device)
         n = (ctypes.c_int64 * 4)(*([geo.npts[a] for a in range(d - 1)] + [hi - lo + 3] + [1] * (4 - d)))
         with torch.cuda.device(self._device):
             stream = torch.cuda.current_stream(self._device).cuda_stream

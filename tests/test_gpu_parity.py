@@ -724,3 +724,52 @@ def test_randomised_parity_stress():
                          capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "0 failures" in out.stdout
+
+
+def test_plain_c_client_of_the_c_abi(tmp_path):
+    """tests/c_abi/c_smoke.c: build + device query + host-buffer query from plain C, checked against an
+    analytic quadratic field, the NaN / cell-index conventions and the error path."""
+    import subprocess
+    from test_host_logic import _compile_c_client
+    exe = _compile_c_client(str(tmp_path / "c_smoke"))
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "c_smoke ok" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("d", [3, 4])
+@pytest.mark.parametrize("table", [True, False])
+def test_update_values_equals_fresh_construction(d, table):
+    """update_values(): new field values on the same grid, rebuilt in place (no re-ingest, no reallocation);
+    afterwards every answer is bit-identical to a freshly constructed interpolator of the updated field."""
+    rng = np.random.default_rng(5 + d)
+    field = _analytic_field3(13, 12, 11, rng=rng) if d == 3 else _analytic_field4(9, 8, 7, 6, rng=rng)
+    cls = _cls(d)
+    for mode in ("vector", "both"):
+        obj = cls(field.copy(), "quiet", mode=mode, table=table)
+        ptr = obj.table.data_ptr() if table else None
+        new = field.copy()
+        new[:, d:] = np.cos(3.0 * field[:, d:]) + field[:, [0]] * field[:, [1]]
+        obj.update_values(new[:, d:])                                # order='rows': the constructor's row order
+        fresh = cls(new.copy(), "quiet", mode=mode, table=table)
+        q = _uniform_queries(fresh, d, 20_000, rng)
+        a, b = obj.Query(q.copy()), fresh.Query(q.copy())
+        for x, y in zip(a if isinstance(a, tuple) else (a,), b if isinstance(b, tuple) else (b,)):
+            assert np.array_equal(x, y, equal_nan=True)
+        if table:
+            assert obj.table.data_ptr() == ptr and torch.equal(obj.table[:-1], fresh.table[:-1])
+        # order='grid': values in sorted grid order (the rows of inputfield)
+        if mode == "vector":
+            grid_vals = fresh.inputfield[:, d:]
+            obj.update_values(np.zeros_like(grid_vals), order="grid")
+            obj.update_values(grid_vals, order="grid")
+            c = obj.Query(q.copy())
+            assert np.array_equal(c, b, equal_nan=True)
+        with pytest.raises(ValueError):
+            obj.update_values(new[:-1, d:])
+    scal = np.concatenate([field[:, :d], np.linalg.norm(field[:, d:], axis=1)[:, None]], axis=1)
+    obj = cls(scal.copy(), "quiet", table=table)
+    obj.update_values(2.0 * scal[:, d])                              # 1-D values for scalar input
+    fresh = cls(np.concatenate([scal[:, :d], 2.0 * scal[:, [d]]], axis=1), "quiet", table=table)
+    q = _uniform_queries(fresh, d, 5_000, rng)
+    for x, y in zip(obj.Query(q.copy()), fresh.Query(q.copy())):
+        assert np.array_equal(x, y, equal_nan=True)

@@ -153,6 +153,35 @@ def test_table_free_quadcubic_math_on_host(tmp_path):
     assert len(errs) >= 4 and max(errs) <= 1e-12
 
 
+def _compile_c_client(out):
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    cuda = "/usr/local/cuda"
+    if not gcc or not os.path.exists(os.path.join(cuda, "include", "cuda_runtime_api.h")):
+        pytest.skip("gcc or the CUDA runtime headers are not available")
+    libdir = os.path.join(ROOT, "arbinterp_b200")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), "-I",
+                    os.path.join(cuda, "include"), "-o", out, os.path.join(ROOT, "tests", "c_abi", "c_smoke.c"),
+                    "-L", libdir, "-larbinterp_b200", "-L", os.path.join(cuda, "lib64"), "-lcudart", "-lm",
+                    "-Wl,-rpath," + libdir, "-Wl,-rpath," + os.path.join(cuda, "lib64")], check=True, timeout=300)
+    return out
+
+
+def test_header_is_plain_c_and_c_client_links(tmp_path):
+    """The drop-in boundary is a C ABI: the header compiles as strict C99 and a plain-C client
+    (tests/c_abi/c_smoke.c) builds and links against the shared library (it runs in the GPU suite)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("gcc not available")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c",
+                    os.path.join(ROOT, "include", "arbinterp_b200.h")], check=True, timeout=120)
+    _lib.load()                                   # makes sure the library is built
+    _compile_c_client(str(tmp_path / "c_smoke"))
+
+
 def test_argument_validation_without_gpu():
     lib = _lib.load()
     g = _lib.ArbGeom()
