@@ -491,6 +491,7 @@ build_sep3_kernel(const __grid_constant__ CUtensorMap tmap, const sep::SepParams
 // along x, y, z once, and the fused z/t phase emits the layer the plane completes.  Software pipeline: iteration
 // s runs {x pass of plane s+1, first half of emit(s)} | barrier | {y pass of plane s+1, second half of emit(s)} |
 // barrier, so the latency-bound passes always share an interval with table stores (Y and delta are double-buffered).
+template <bool QUIRK>
 __global__ void __launch_bounds__(sep::Sep4::THREADS, 2)
 build_sep4_kernel(const __grid_constant__ CUtensorMap tmap, const sep::SepParams p) {
     using S4 = sep::Sep4;
@@ -501,7 +502,7 @@ build_sep4_kernel(const __grid_constant__ CUtensorMap tmap, const sep::SepParams
     double* Y = base + S4::OFF_Y;
     double* ring = base + S4::OFF_RING;
     double* w3ring = base + S4::OFF_W3;
-    double* delta = base + S4::OFF_DELTA;
+    double* gbuf = base + S4::OFF_G;
     __shared__ uint64_t bar[2];
 
     int64_t tl = blockIdx.x;
@@ -526,31 +527,35 @@ build_sep4_kernel(const __grid_constant__ CUtensorMap tmap, const sep::SepParams
         fetch(0);
         fetch(1);
     }
+    // the thread's two emit tasks (the same in every step: their ring elements are private to the thread)
+    const S4::ETask task0 = S4::make_task(tid, p, x0, y0, z0, t0, comp);
+    const S4::ETask task1 = S4::make_task(tid + S4::NTASK_E / 2, p, x0, y0, z0, t0, comp);
+    const int64_t layer_stride = p.nc[0] * p.nc[1] * p.nc[2] * p.ncomp * 256;
     __syncthreads();
     // prologue: plane 0 through the x and y passes
     mbar_wait(&bar[0], 0);
-    S4::phase_a(plane, X, w3ring, p.quirk, tid, S4::THREADS);
+    S4::phase_a<QUIRK>(plane, X, w3ring, tid, S4::THREADS);
     __syncthreads();
     if (tid == 0) { fence_proxy_async(); fetch(2); }              // nstep >= 4 always
-    S4::phase_b(X, Y, w3ring, delta, 0, p.quirk, tid, S4::THREADS);
+    S4::phase_b<QUIRK>(X, Y, w3ring, gbuf, 0, tid, S4::THREADS);
     __syncthreads();
+#pragma unroll 1
     for (int s = 0; s < nstep; ++s) {
         const int q = s + 1;                                       // plane whose x/y passes ride along
         const bool more = q < nstep;
         const double* Ys = Y + (s & 1) * S4::Y_ELEMS;
-        const double* ds = delta + (s & 1) * S4::DELTA_ELEMS;
+        const double* gs = gbuf + (s & 1) * S4::G_ELEMS;
         if (more) {
             mbar_wait(&bar[q & 1], (q >> 1) & 1);
-            S4::phase_a(plane + (q & 1) * S4::PLANE_PITCH, X, w3ring + (q & 3) * S4::W3_PITCH, p.quirk, tid, S4::THREADS);
+            S4::phase_a<QUIRK>(plane + (q & 1) * S4::PLANE_PITCH, X, w3ring + (q & 3) * S4::W3_PITCH, tid, S4::THREADS);
         }
-        S4::phase_e(Ys, ring, ds, p, s, x0, y0, z0, t0 + s - 3, comp, 0, S4::NTASK_E / 2, tid, S4::THREADS);
+        S4::emit_task<QUIRK>(task0, Ys, ring, gs, p.table, layer_stride, s);
         __syncthreads();
         if (more) {
             if (tid == 0 && q + 2 < nstep) { fence_proxy_async(); fetch(q + 2); }
-            S4::phase_b(X, Y + (q & 1) * S4::Y_ELEMS, w3ring, delta + (q & 1) * S4::DELTA_ELEMS, q, p.quirk, tid,
-                        S4::THREADS);
+            S4::phase_b<QUIRK>(X, Y + (q & 1) * S4::Y_ELEMS, w3ring, gbuf + (q & 1) * S4::G_ELEMS, q, tid, S4::THREADS);
         }
-        S4::phase_e(Ys, ring, ds, p, s, x0, y0, z0, t0 + s - 3, comp, S4::NTASK_E / 2, S4::NTASK_E, tid, S4::THREADS);
+        S4::emit_task<QUIRK>(task1, Ys, ring, gs, p.table, layer_stride, s);
         __syncthreads();
     }
 }
@@ -782,11 +787,12 @@ static int build_sep4_impl(const double* grid, int ncomp, const int64_t* n, doub
     GridMap gm;
     const cuuint32_t box[4] = {sep::GX, S4::GY, S4::GZ, 1};
     { const int rc = make_grid_map(4, grid, ncomp, n, box, st, &gm); if (rc) return rc; }
-    ARB_CUDA(cudaFuncSetAttribute(build_sep4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S4::SMEM));
+    auto k = quirk ? build_sep4_kernel<true> : build_sep4_kernel<false>;
+    ARB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S4::SMEM));
     p.comp_fast = comp_fast && ntiles * ncomp <= 0x7fffffffLL;
     const dim3 blocks = p.comp_fast ? dim3((unsigned)(ntiles * ncomp), 1, (unsigned)nchunk)
                                     : dim3((unsigned)ntiles, (unsigned)ncomp, (unsigned)nchunk);
-    build_sep4_kernel<<<blocks, S4::THREADS, S4::SMEM, st>>>(gm.tmap, p);
+    k<<<blocks, S4::THREADS, S4::SMEM, st>>>(gm.tmap, p);
     ARB_CUDA(cudaGetLastError());
     return finish_build(4, ncomp, ncell, table, &gm, st);
 }

@@ -31,6 +31,11 @@
 #else
 #define ARB_HD inline
 #endif
+#if defined(__CUDA_ARCH__)
+#define ARB_SEP_UNROLL _Pragma("unroll")
+#else
+#define ARB_SEP_UNROLL
+#endif
 
 namespace arb {
 namespace sep {
@@ -137,24 +142,23 @@ struct Sep4 {
     static constexpr int GY = 5, GZ = 5, NROW = 25, PLANE = NROW * GX;
     static constexpr int PLANE_PITCH = 304;                    // 128-byte multiple: TMA destination alignment
     static constexpr int NCELL = 8 * TY * TZ;                  // cells per layer
-    static constexpr int NTASK_E = NCELL * 16;
+    static constexpr int NTASK_E = NCELL * 16;                 // emit tasks per layer: (cell, j*4 + i)
     static constexpr int X_ELEMS = NROW * XP, Y_ELEMS = GZ * TY * YROW;
-    static constexpr int W3 = 81;                              // dxdydz at the 9 x 3 x 3 corner points of a plane
+    static constexpr int W3 = 81;                              // corner points of a plane: 9 x 3 x 3
     static constexpr int W3_PITCH = 82;
     static constexpr int RING_SLOT = NCELL * 64;
-    static constexpr int DELTA_ELEMS = NCELL * 16;
-    // offsets into dynamic shared memory (doubles); Y and delta are double-buffered (software pipeline)
+    static constexpr int G_ELEMS = 2 * W3_PITCH;               // fxyzt at the corner points of a layer: [ct][point]
+    // offsets into dynamic shared memory (doubles); Y and the corner values are double-buffered (software pipeline)
     static constexpr int OFF_PLANE = 0, OFF_X = 2 * PLANE_PITCH, OFF_Y = OFF_X + X_ELEMS, OFF_RING = OFF_Y + 2 * Y_ELEMS,
-                         OFF_W3 = OFF_RING + 3 * RING_SLOT, OFF_DELTA = OFF_W3 + 4 * W3_PITCH,
-                         TOTAL = OFF_DELTA + 2 * DELTA_ELEMS;
-    static_assert(OFF_Y % 2 == 0 && OFF_RING % 2 == 0 && OFF_DELTA % 2 == 0, "16-byte alignment of vector reads");
+                         OFF_W3 = OFF_RING + 3 * RING_SLOT, OFF_G = OFF_W3 + 4 * W3_PITCH, TOTAL = OFF_G + 2 * G_ELEMS;
     static constexpr size_t SMEM = (size_t)TOTAL * 8 + 128;
 
     // phase A: x pass of a new plane; with the quirk also dxdydz (central differences, unit spacing) at the
     // plane's 9 x 3 x 3 corner points (corner p <-> tile grid coordinate p + 1) -> this plane's w3 slot
-    ARB_HD static void phase_a(const double* plane, double* X, double* w3, int quirk, int tid, int nthr) {
+    template <bool QUIRK>
+    ARB_HD static void phase_a(const double* plane, double* X, double* w3, int tid, int nthr) {
         pass_x(plane, X, NROW, tid, nthr);
-        if (quirk)
+        if (QUIRK)
             for (int e = tid; e < W3; e += nthr) {
                 const int px = e % 9, py = (e / 9) % 3, pz = e / 27;
                 const double* s = plane + (pz * GY + py) * GX + px;
@@ -164,91 +168,90 @@ struct Sep4 {
                 w3[e] = 0.125 * (hi - lo);
             }
     }
-    // fxyzt at corner c of a cell of the layer completed by local plane s: the layer's corners sit on the local
-    // planes s-2 (ct = 0) and s-1 (ct = 1); fxyzt there = 0.5 * (w3[plane + 1] - w3[plane - 1]).
-    ARB_HD static double fxyzt(const double* w3ring, int s, int c, int cellx, int celly, int cellz) {
-        const int cx = c & 1, cy = (c >> 1) & 1, cz = (c >> 2) & 1, ct = c >> 3;
-        const int pt = ((cellz + cz) * 3 + (celly + cy)) * 9 + cellx + cx;
-        const int q = s - 2 + ct;                                       // local plane of the corner
-        return 0.5 * (w3ring[((q + 1) & 3) * W3_PITCH + pt] - w3ring[((q - 1) & 3) * W3_PITCH + pt]);
-    }
-    // phase B: y pass of plane s; with the quirk (and s >= 3) also e[240 + c] of every cell of the layer that
-    // plane s completes
-    ARB_HD static void phase_b(const double* X, double* Y, const double* w3ring, double* delta, int s, int quirk,
-                               int tid, int nthr) {
+    // phase B: y pass of local plane s; with the quirk (and s >= 3) also fxyzt at the corner points of the layer
+    // that plane s completes: its corners sit on the local planes s-2 (ct = 0) and s-1 (ct = 1), and
+    // fxyzt(plane q) = 0.5 * (w3[q + 1] - w3[q - 1]).
+    template <bool QUIRK>
+    ARB_HD static void phase_b(const double* X, double* Y, const double* w3ring, double* g, int s, int tid, int nthr) {
         pass_y(X, Y, GZ, TY, tid, nthr);
-        if (quirk && s >= 3)
-            for (int e = tid; e < DELTA_ELEMS; e += nthr) {
-                const int c = e & 15, cell = e >> 4;
-                const int cellx = cell & 7, celly = (cell >> 3) & 1, cellz = cell >> 4;
-                const double cur = fxyzt(w3ring, s, c, cellx, celly, cellz);
-                const double prev = (c > 0) ? fxyzt(w3ring, s, c - 1, cellx, celly, cellz) : 0.0;
-                delta[e] = prev - cur;
+        if (QUIRK && s >= 3)
+            for (int e = tid; e < 2 * W3; e += nthr) {
+                const int ct = e >= W3, pt = e - ct * W3;
+                const int q = s - 2 + ct;
+                g[ct * W3_PITCH + pt] = 0.5 * (w3ring[((q + 1) & 3) * W3_PITCH + pt] - w3ring[((q - 1) & 3) * W3_PITCH + pt]);
             }
     }
-    // phase E: z pass of the new plane fused with the t pass of the layer it completes.
-    // task = (cell, j*4 + i): the 4 fresh z-pass values (k = 0..3) replace the oldest ring plane in place after
-    // the thread has read it, so the ring needs three slots and no barrier of its own.
-    // Tasks [e_begin, e_end) only: the kernel spreads a step's tasks over its two barrier intervals.
-    ARB_HD static void phase_e(const double* Y, double* ring, const double* delta, const SepParams& p, int s, int x0,
-                               int y0, int z0, int64_t layer, int comp, int e_begin, int e_end, int tid, int nthr) {
-        const int slot_new = s % 3;                      // holds local plane s-3, receives plane s
-        const int slot_1 = (s + 1) % 3, slot_2 = (s + 2) % 3;   // planes s-2, s-1
-        for (int e = e_begin + tid; e < e_end; e += nthr) {
-            const int ji = e & 15, cell = e >> 4;
-            const int cx = cell & 7, cy = (cell >> 3) & 1, cz = cell >> 4;
-            const double* sy = Y + (cz * TY + cy) * YROW + cx * YCX + ji;
-            double fresh[4];
-            cr_line(sy[0], sy[TY * YROW], sy[2 * TY * YROW], sy[3 * TY * YROW], fresh[0], fresh[1], fresh[2], fresh[3]);
-            double* r0 = ring + slot_new * RING_SLOT + cell * 64 + ji;
-            if (s >= 3) {
-                const int64_t gx = x0 + cx, gy = y0 + cy, gz = z0 + cz;
-                const bool ok = gx < p.nc[0] && gy < p.nc[1] && gz < p.nc[2];
-                if (ok) {
-                    const double* r1 = ring + slot_1 * RING_SLOT + cell * 64 + ji;
-                    const double* r2 = ring + slot_2 * RING_SLOT + cell * 64 + ji;
-                    const int64_t gcell = gx + p.nc[0] * (gy + p.nc[1] * (gz + p.nc[2] * layer));
-                    double* d = p.table + (gcell * p.ncomp + comp) * 256 + ji;
-                    double G0[4] = {0, 0, 0, 0}, G1[4] = {0, 0, 0, 0};
-                    if (p.quirk) {
-                        // F[ct][cz] = sum_{cy,cx} Hq[j][cy] Hq[i][cx] e[ct][cz][cy][cx]
-                        const int i = ji & 3, j = ji >> 2;
-                        const double hi0 = (i == 1 || i == 3) ? 1.0 : (i == 2 ? -2.0 : 0.0);
-                        const double hi1 = (i == 3) ? 1.0 : (i == 2 ? -1.0 : 0.0);
-                        const double hj0 = (j == 1 || j == 3) ? 1.0 : (j == 2 ? -2.0 : 0.0);
-                        const double hj1 = (j == 3) ? 1.0 : (j == 2 ? -1.0 : 0.0);
-                        const double p00 = hj0 * hi0, p01 = hj0 * hi1, p10 = hj1 * hi0, p11 = hj1 * hi1;
-                        const Pair* dl = reinterpret_cast<const Pair*>(delta + cell * 16);   // 16-byte broadcast reads
-                        double F[4];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-                        for (int m = 0; m < 4; ++m) {
-                            const Pair lo = dl[2 * m], hi = dl[2 * m + 1];
-                            F[m] = (p00 * lo.x + p01 * lo.y) + (p10 * hi.x + p11 * hi.y);
-                        }
-                        // G[ct][k] = Hq[k][0] F[ct][0] + Hq[k][1] F[ct][1]
-                        G0[1] = F[0]; G0[2] = -2.0 * F[0] - F[1]; G0[3] = F[0] + F[1];
-                        G1[1] = F[2]; G1[2] = -2.0 * F[2] - F[3]; G1[3] = F[2] + F[3];
-                    }
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-                    for (int k = 0; k < 4; ++k) {
-                        double a0, a1, a2, a3;
-                        cr_line(r0[k * 16], r1[k * 16], r2[k * 16], fresh[k], a0, a1, a2, a3);
-                        if (p.quirk) {   // + Hq[l][0] G[0][k] + Hq[l][1] G[1][k]
-                            a1 += G0[k];
-                            a2 += -2.0 * G0[k] - G1[k];
-                            a3 += G0[k] + G1[k];
-                        }
-                        emit(d + k * 16, a0); emit(d + 64 + k * 16, a1); emit(d + 128 + k * 16, a2);
-                        emit(d + 192 + k * 16, a3);
-                    }
+
+    // Step-invariant part of one emit task (cell, j*4 + i); a thread owns the same tasks in every step.
+    struct ETask {
+        int y_off, ring_off, g_off;   // into a Y buffer, a ring slot, a corner-value plane
+        int64_t out_off;              // table offset (doubles) of the task's first output in layer 0 of the march; -1: not stored
+        double p00, p01, p10, p11;    // Hq[j][cy] Hq[i][cx]
+    };
+    ARB_HD static ETask make_task(int e, const SepParams& p, int x0, int y0, int z0, int64_t t0, int comp) {
+        ETask t;
+        const int ji = e & 15, cell = e >> 4;
+        const int cx = cell & 7, cy = (cell >> 3) & 1, cz = cell >> 4;
+        t.y_off = (cz * TY + cy) * YROW + cx * YCX + ji;
+        t.ring_off = cell * 64 + ji;
+        t.g_off = (cz * 3 + cy) * 9 + cx;
+        const int64_t gx = x0 + cx, gy = y0 + cy, gz = z0 + cz;
+        const bool ok = gx < p.nc[0] && gy < p.nc[1] && gz < p.nc[2];
+        t.out_off = ok ? ((gx + p.nc[0] * (gy + p.nc[1] * (gz + p.nc[2] * t0))) * p.ncomp + comp) * 256 + ji : -1;
+        const int i = ji & 3, j = ji >> 2;
+        const double hi0 = (i == 1 || i == 3) ? 1.0 : (i == 2 ? -2.0 : 0.0);
+        const double hi1 = (i == 3) ? 1.0 : (i == 2 ? -1.0 : 0.0);
+        const double hj0 = (j == 1 || j == 3) ? 1.0 : (j == 2 ? -2.0 : 0.0);
+        const double hj1 = (j == 3) ? 1.0 : (j == 2 ? -1.0 : 0.0);
+        t.p00 = hj0 * hi0; t.p01 = hj0 * hi1; t.p10 = hj1 * hi0; t.p11 = hj1 * hi1;
+        return t;
+    }
+    // phase E, one task: z pass of the new plane fused with the t pass of the layer it completes.  The 4 fresh
+    // z-pass values (k = 0..3) replace the oldest ring plane in place after the thread has read it, so the ring
+    // needs three slots and no barrier of its own.  layer_stride = doubles between consecutive t layers of the table.
+    template <bool QUIRK>
+    ARB_HD static void emit_task(const ETask& t, const double* Y, double* ring, const double* g, double* table,
+                                 int64_t layer_stride, int s) {
+        const double* sy = Y + t.y_off;
+        double fresh[4];
+        cr_line(sy[0], sy[TY * YROW], sy[2 * TY * YROW], sy[3 * TY * YROW], fresh[0], fresh[1], fresh[2], fresh[3]);
+        const int slot_new = s % 3;                                   // holds local plane s-3, receives plane s
+        double* r0 = ring + slot_new * RING_SLOT + t.ring_off;
+        if (s >= 3 && t.out_off >= 0) {
+            const double* r1 = ring + ((s + 1) % 3) * RING_SLOT + t.ring_off;       // plane s-2
+            const double* r2 = ring + ((s + 2) % 3) * RING_SLOT + t.ring_off;       // plane s-1
+            double* d = table + t.out_off + (int64_t)(s - 3) * layer_stride;
+            double G0[4] = {0.0, 0.0, 0.0, 0.0}, G1[4] = {0.0, 0.0, 0.0, 0.0};
+            if (QUIRK) {
+                // e[c] = fxyzt(corner c-1) - fxyzt(corner c);  F[ct][cz] = sum_{cy,cx} Hq[j][cy] Hq[i][cx] e[ct][cz][cy][cx]
+                const double* gc = g + t.g_off;
+                double F[4];
+                double prev = 0.0;
+                ARB_SEP_UNROLL
+                for (int m = 0; m < 4; ++m) {                                    // m = 2 ct + cz
+                    const double* gm = gc + (m >> 1) * W3_PITCH + (m & 1) * 27;
+                    const double g0 = gm[0], g1 = gm[1], g2 = gm[9], g3 = gm[10];
+                    F[m] = (t.p00 * (prev - g0) + t.p01 * (g0 - g1)) + (t.p10 * (g1 - g2) + t.p11 * (g2 - g3));
+                    prev = g3;
                 }
+                // G[ct][k] = Hq[k][0] F[ct][0] + Hq[k][1] F[ct][1]
+                G0[1] = F[0]; G0[2] = -2.0 * F[0] - F[1]; G0[3] = F[0] + F[1];
+                G1[1] = F[2]; G1[2] = -2.0 * F[2] - F[3]; G1[3] = F[2] + F[3];
             }
-            r0[0] = fresh[0]; r0[16] = fresh[1]; r0[32] = fresh[2]; r0[48] = fresh[3];
+            ARB_SEP_UNROLL
+            for (int k = 0; k < 4; ++k) {
+                double a0, a1, a2, a3;
+                cr_line(r0[k * 16], r1[k * 16], r2[k * 16], fresh[k], a0, a1, a2, a3);
+                if (QUIRK) {   // + Hq[l][0] G[0][k] + Hq[l][1] G[1][k]
+                    a1 += G0[k];
+                    a2 += -2.0 * G0[k] - G1[k];
+                    a3 += G0[k] + G1[k];
+                }
+                emit(d + k * 16, a0); emit(d + 64 + k * 16, a1); emit(d + 128 + k * 16, a2);
+                emit(d + 192 + k * 16, a3);
+            }
         }
+        r0[0] = fresh[0]; r0[16] = fresh[1]; r0[32] = fresh[2]; r0[48] = fresh[3];
     }
 };
 

@@ -87,7 +87,9 @@ static double run3(const Grid& g) {
 
 // order = +1: threads 0..T-1 within a barrier interval, -1: T-1..0 (an intra-interval dependency between
 // threads would make the two orders disagree)
-static double run4(const Grid& g, int quirk, int lt, int order = 1) {
+template <bool QUIRK>
+static double run4(const Grid& g, int lt, int order = 1) {
+    const int quirk = QUIRK ? 1 : 0;
     using S4 = sep::Sep4;
     sep::SepParams p{};
     int64_t ncell = 1;
@@ -115,7 +117,7 @@ static double run4(const Grid& g, int quirk, int lt, int order = 1) {
                         const int nstep = nlayer + 3;
                         double* base = sm.data();
                         double *X = base + S4::OFF_X, *Y = base + S4::OFF_Y, *ring = base + S4::OFF_RING,
-                               *w3ring = base + S4::OFF_W3, *delta = base + S4::OFF_DELTA;
+                               *w3ring = base + S4::OFF_W3, *gbuf = base + S4::OFF_G;
                         auto fetch = [&](int q) {                 // what the TMA unit delivers for plane q
                             double* plane = base + S4::OFF_PLANE + (q & 1) * S4::PLANE_PITCH;
                             for (int z = 0; z < S4::GZ; ++z)
@@ -123,29 +125,29 @@ static double run4(const Grid& g, int quirk, int lt, int order = 1) {
                                     for (int x = 0; x < sep::GX; ++x)
                                         plane[(z * S4::GY + y) * sep::GX + x] = g.at(comp, x0 + x, y0 + y, z0 + z, t0 + q);
                         };
+                        const int64_t layer_stride = p.nc[0] * p.nc[1] * p.nc[2] * p.ncomp * 256;
+                        auto task = [&](int e) { return S4::make_task(e, p, x0, y0, z0, t0, comp); };
                         // same schedule as build_sep4_kernel
                         fetch(0); fetch(1);
-                        each([&](int t) { S4::phase_a(base + S4::OFF_PLANE, X, w3ring, quirk, t, T); });
+                        each([&](int t) { S4::phase_a<QUIRK>(base + S4::OFF_PLANE, X, w3ring, t, T); });
                         fetch(2);
-                        each([&](int t) { S4::phase_b(X, Y, w3ring, delta, 0, quirk, t, T); });
+                        each([&](int t) { S4::phase_b<QUIRK>(X, Y, w3ring, gbuf, 0, t, T); });
                         for (int s = 0; s < nstep; ++s) {
                             const int q = s + 1;
                             const bool more = q < nstep;
                             const double* Ys = Y + (s & 1) * S4::Y_ELEMS;
-                            const double* ds = delta + (s & 1) * S4::DELTA_ELEMS;
+                            const double* gs = gbuf + (s & 1) * S4::G_ELEMS;
                             each([&](int t) {
                                 if (more)
-                                    S4::phase_a(base + S4::OFF_PLANE + (q & 1) * S4::PLANE_PITCH, X,
-                                                w3ring + (q & 3) * S4::W3_PITCH, quirk, t, T);
-                                S4::phase_e(Ys, ring, ds, p, s, x0, y0, z0, t0 + s - 3, comp, 0, S4::NTASK_E / 2, t, T);
+                                    S4::phase_a<QUIRK>(base + S4::OFF_PLANE + (q & 1) * S4::PLANE_PITCH, X,
+                                                       w3ring + (q & 3) * S4::W3_PITCH, t, T);
+                                S4::emit_task<QUIRK>(task(t), Ys, ring, gs, p.table, layer_stride, s);
                             });
                             if (more && q + 2 < nstep) fetch(q + 2);
                             each([&](int t) {
                                 if (more)
-                                    S4::phase_b(X, Y + (q & 1) * S4::Y_ELEMS, w3ring, delta + (q & 1) * S4::DELTA_ELEMS, q,
-                                                quirk, t, T);
-                                S4::phase_e(Ys, ring, ds, p, s, x0, y0, z0, t0 + s - 3, comp, S4::NTASK_E / 2, S4::NTASK_E,
-                                            t, T);
+                                    S4::phase_b<QUIRK>(X, Y + (q & 1) * S4::Y_ELEMS, w3ring, gbuf + (q & 1) * S4::G_ELEMS, q, t, T);
+                                S4::emit_task<QUIRK>(task(t + S4::NTASK_E / 2), Ys, ring, gs, p.table, layer_stride, s);
                             });
                         }
                     }
@@ -180,15 +182,15 @@ int main() {
     }
     {
         Grid g = make_grid(12, 6, 7, 9, 2, 4);
-        report("4d 12x6x7x9 C=2 quirk lt=all", run4(g, 1, 1 << 20));
-        report("4d 12x6x7x9 C=2 quirk lt=4", run4(g, 1, 4));
-        report("4d 12x6x7x9 C=2 quirk lt=4, threads in reverse order", run4(g, 1, 4, -1));
-        report("4d 12x6x7x9 C=2 quirk lt=1", run4(g, 1, 1));
-        report("4d 12x6x7x9 C=2 fixed lt=5", run4(g, 0, 5));
+        report("4d 12x6x7x9 C=2 quirk lt=all", run4<true>(g, 1 << 20));
+        report("4d 12x6x7x9 C=2 quirk lt=4", run4<true>(g, 4));
+        report("4d 12x6x7x9 C=2 quirk lt=4, threads in reverse order", run4<true>(g, 4, -1));
+        report("4d 12x6x7x9 C=2 quirk lt=1", run4<true>(g, 1));
+        report("4d 12x6x7x9 C=2 fixed lt=5", run4<false>(g, 5));
         Grid h = make_grid(4, 4, 4, 4, 1, 5);
-        report("4d 4x4x4x4 C=1 (one cell) quirk", run4(h, 1, 3));
+        report("4d 4x4x4x4 C=1 (one cell) quirk", run4<true>(h, 3));
         Grid k = make_grid(7, 9, 5, 6, 1, 6);
-        report("4d 7x9x5x6 C=1 quirk lt=2", run4(k, 1, 2));
+        report("4d 7x9x5x6 C=1 quirk lt=2", run4<true>(k, 2));
     }
     return bad;
 }
