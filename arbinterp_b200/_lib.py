@@ -18,7 +18,7 @@ EXPORTED_SYMBOLS = (
     "arb_version", "arb_last_error", "arb_get_matrix",
     "arb_build_coeffs", "arb_build_coeffs_3d", "arb_build_coeffs_4d",
     "arb_query", "arb_query_host", "arb_query_grid", "arb_query_grid_host",
-    "arb_push", "arb_permute_rows", "arb_set_query_variant", "arb_set_build_variant",
+    "arb_push", "arb_push_steps", "arb_permute_rows", "arb_set_query_variant", "arb_set_build_variant",
 )
 
 
@@ -83,6 +83,9 @@ def load():
     lib.arb_push.restype = i32
     lib.arb_push.argtypes = [ctypes.POINTER(ArbGeom), vp, i32, vp, vp, i64, ctypes.c_double, i64, ctypes.c_double,
                              ctypes.POINTER(ctypes.c_double * 3), vp, vp]
+    lib.arb_push_steps.restype = i32
+    lib.arb_push_steps.argtypes = [ctypes.POINTER(ArbGeom), vp, i32, vp, vp, vp, i64, ctypes.c_double, i64,
+                                   ctypes.c_double, ctypes.POINTER(ctypes.c_double * 3), vp, vp]
     lib.arb_permute_rows.restype = i32
     lib.arb_permute_rows.argtypes = [vp, vp, vp, i64, i32, i32, vp]
     lib.arb_set_query_variant.restype = i32

@@ -11,6 +11,12 @@
 // particle stays in its cell no memory traffic is issued at all, so small time steps run at FP64
 // issue rate instead of HBM rate.  Particles that leave the interpolation volume are marked lost:
 // position and velocity become NaN (the Query convention for out-of-volume points).
+//
+// Slab-sharded tables (arb_push_steps): every particle carries the index of the next step whose force has to
+// be evaluated.  A particle that is inside the volume but outside this table's slab is parked -- position,
+// velocity (with the half kick still pending) and step index are written back unchanged -- so that the rank
+// owning the neighbouring slab resumes it with exactly the arithmetic of an unsharded run
+// (sharding.SlabShardedInterp.push moves the rows).
 #include "arb_device.cuh"
 
 namespace arb {
@@ -22,6 +28,7 @@ struct PushParams {
     double dt, kappa, g[3];
     int64_t nsteps;
     unsigned long long* lost;
+    int64_t* step_io;       // optional [N]: in = first step to evaluate (0 = fresh), out = step reached (nsteps + 1 = done)
     int ncomp;              // table components per cell; the norm block is the last one
 };
 
@@ -61,17 +68,25 @@ __global__ void __launch_bounds__(THREADS) push_kernel(const PushParams P) {
 #pragma unroll
             for (int a = 0; a < 3; ++a) v[a] = P.vel[n * 3 + a];
         }
-        bool alive = active;
+        // `step` = index of the next force evaluation of this particle; lanes of a warp may be at different steps
+        // (resumed particles), so the loop runs until no lane has work left.
+        int64_t step = (active && P.step_io) ? P.step_io[n] : 0;
+        bool alive = active && step >= 0 && step <= P.nsteps;
         int64_t cur_blk = -1;
-        for (int64_t step = 0; step <= P.nsteps; ++step) {
+        while (__any_sync(0xffffffffu, alive)) {
             Located<D> L;
-            L.ok = false;
+            L.ok = false; L.cell_global = p.total_cells; L.cell_local = 0;
             if (alive) L = locate_coords<D>(p, x);
-            if (alive && !L.ok) {               // left the volume (or NaN): lost from here on
+            if (alive && !L.ok) {
                 alive = false;
+                if (P.step_io && L.cell_global != p.total_cells) {
+                    // inside the volume, outside this slab: parked as is, the owner of that slab resumes at `step`
+                } else {                        // left the volume (or NaN): lost from here on
 #pragma unroll
-                for (int a = 0; a < 3; ++a) x[a] = v[a] = qnan();
-                if (P.lost && sl == 0) atomicAdd(P.lost, 1ULL);
+                    for (int a = 0; a < 3; ++a) x[a] = v[a] = qnan();
+                    step = P.nsteps + 1;
+                    if (P.lost && sl == 0) atomicAdd(P.lost, 1ULL);
+                }
             }
             const int64_t blk = (L.cell_local * P.ncomp + (P.ncomp - 1)) * SL + sl;
             const bool fetch = alive && (blk != cur_blk);
@@ -97,22 +112,26 @@ __global__ void __launch_bounds__(THREADS) push_kernel(const PushParams P) {
                     g[c] += __shfl_xor_sync(0xffffffffu, g[c], 2);
                 }
             }
-            double a[3] = {0, 0, 0};
             if (alive) {
+                double a[3];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) a[c] = fma(P.kappa, __ddiv_rn(g[1 + c], p.h[c]), P.g[c]);
-            }
-            if (step > 0) {                      // second half kick of the previous step
+                if (step > 0) {                  // second half kick of the previous step
 #pragma unroll
-                for (int c = 0; c < 3; ++c) v[c] = fma(hdt, a[c], v[c]);
-            }
-            if (step == P.nsteps) break;
+                    for (int c = 0; c < 3; ++c) v[c] = fma(hdt, a[c], v[c]);
+                }
+                if (step == P.nsteps) {
+                    alive = false;
+                } else {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {        // first half kick + drift
-                v[c] = fma(hdt, a[c], v[c]);
-                x[c] = fma(P.dt, v[c], x[c]);
+                    for (int c = 0; c < 3; ++c) {    // first half kick + drift
+                        v[c] = fma(hdt, a[c], v[c]);
+                        x[c] = fma(P.dt, v[c], x[c]);
+                    }
+                    if (D == 4) x[3] += P.dt;
+                }
+                ++step;
             }
-            if (D == 4) x[3] += P.dt;
             __syncwarp();
         }
         if (active && sl == 0) {
@@ -120,6 +139,7 @@ __global__ void __launch_bounds__(THREADS) push_kernel(const PushParams P) {
             for (int a = 0; a < D; ++a) P.pos[n * D + a] = x[a];
 #pragma unroll
             for (int a = 0; a < 3; ++a) P.vel[n * 3 + a] = v[a];
+            if (P.step_io) P.step_io[n] = step;
         }
         __syncwarp();
     }
@@ -144,9 +164,9 @@ static int launch_push(const PushParams& P, int64_t N, cudaStream_t st) {
 
 }  // namespace arb
 
-extern "C" int arb_push(const arb_geom* g, const double* table, int mode, double* pos, double* vel, int64_t N,
-                        double dt, int64_t nsteps, double kappa, const double* gravity,
-                        unsigned long long* lost_count, void* stream) {
+extern "C" int arb_push_steps(const arb_geom* g, const double* table, int mode, double* pos, double* vel,
+                              int64_t* step_io, int64_t N, double dt, int64_t nsteps, double kappa,
+                              const double* gravity, unsigned long long* lost_count, void* stream) {
     using namespace arb;
     if (mode != ARB_MODE_NORM && mode != ARB_MODE_BOTH) {
         set_error("arb_push: needs a table with a norm component (mode norm or both), got mode %d", mode);
@@ -159,9 +179,16 @@ extern "C" int arb_push(const arb_geom* g, const double* table, int mode, double
                                nullptr, nullptr, P.q, false);
     if (rc) return rc < 0 ? 0 : rc;
     P.pos = pos; P.vel = vel; P.dt = dt; P.kappa = kappa; P.nsteps = nsteps; P.lost = lost_count; P.ncomp = g->ncomp;
+    P.step_io = step_io;
     for (int a = 0; a < 3; ++a) P.g[a] = gravity ? gravity[a] : 0.0;
     if (g->d == 3) return launch_push<3>(P, N, (cudaStream_t)stream);
     return launch_push<4>(P, N, (cudaStream_t)stream);
+}
+
+extern "C" int arb_push(const arb_geom* g, const double* table, int mode, double* pos, double* vel, int64_t N,
+                        double dt, int64_t nsteps, double kappa, const double* gravity,
+                        unsigned long long* lost_count, void* stream) {
+    return arb_push_steps(g, table, mode, pos, vel, nullptr, N, dt, nsteps, kappa, gravity, lost_count, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------

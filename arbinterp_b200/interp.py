@@ -540,28 +540,42 @@ class _CubicInterpolator:
         (for a magnetic trap: value = |B|, kappa = -mu/m).  ``pos``: (N,d), ``vel``: (N,3) float64 torch CUDA
         tensors, updated in place (numpy arrays are copied to the GPU and back); for a quadcubic
         (time-dependent) field the 4th column of ``pos`` is each particle's own time and advances by ``dt``
-        per step.  Particles that leave the interpolation volume get NaN position and velocity.
-        Returns the number of particles lost."""
-        if self._mode == "vector" or self._table is None or self._slab != (0, self._geo.ncell[self._d - 1]):
-            raise ValueError("push() needs an unsharded coefficient table in 'norm', 'both' or scalar mode")
+        per step.  Particles that leave the interpolation volume get NaN position and velocity (in 4-D the time
+        column keeps the time at which they left).  Returns the number of particles lost."""
+        if self._slab != (0, self._geo.ncell[self._d - 1]):
+            raise ValueError("this interpolator holds one slab of a sharded table: use SlabShardedInterp.push(), which "
+                             "moves particles between the slab owners")
         host = not isinstance(pos, torch.Tensor)
         p = torch.as_tensor(pos, dtype=torch.float64).to(self._device).contiguous() if host else pos
         v = torch.as_tensor(vel, dtype=torch.float64).to(self._device).contiguous() if host else vel
+        nlost = self._push_local(p, v, None, dt, nsteps, kappa, gravity)
+        if host:
+            np.copyto(pos, p.cpu().numpy())
+            np.copyto(vel, v.cpu().numpy())
+        return nlost
+
+    def _push_local(self, p, v, steps, dt, nsteps, kappa, gravity=None):
+        """One launch of the push kernel on this table.  ``steps``: optional int64 CUDA tensor (N,) with every
+        particle's next step index (arb_push_steps; a particle inside the volume but outside this table's slab
+        is parked unchanged); None = plain arb_push.  Returns the number of particles lost in this launch."""
+        if self._mode == "vector" or self._table is None:
+            raise ValueError("push() needs a coefficient table in 'norm', 'both' or scalar mode")
         for t, w in ((p, self._d), (v, 3)):
             if t.dtype != torch.float64 or not t.is_contiguous() or t.dim() != 2 or t.shape[1] != w or t.device != self._device:
                 raise ValueError(f"pos must be (N,{self._d}) and vel (N,3): contiguous float64 on the interpolator's device")
         if p.shape[0] != v.shape[0]:
             raise ValueError("pos and vel must have the same number of rows")
+        if steps is not None and (steps.dtype != torch.int64 or not steps.is_contiguous() or steps.shape != (p.shape[0],)
+                                  or steps.device != self._device):
+            raise ValueError("steps must be a contiguous int64 (N,) tensor on the interpolator's device")
         lost = torch.zeros(1, dtype=torch.int64, device=self._device)
         grav = (ctypes.c_double * 3)(*([0.0, 0.0, 0.0] if gravity is None else [float(x) for x in gravity]))
         with torch.cuda.device(self._device):
             stream = torch.cuda.current_stream(self._device).cuda_stream
-            _lib.check(self._lib.arb_push(ctypes.byref(self._cgeom), self._table.data_ptr(), self._mode_code,
-                                          p.data_ptr(), v.data_ptr(), p.shape[0], float(dt), int(nsteps), float(kappa),
-                                          ctypes.byref(grav), lost.data_ptr(), stream), "arb_push")
-        if host:
-            np.copyto(pos, p.cpu().numpy())
-            np.copyto(vel, v.cpu().numpy())
+            _lib.check(self._lib.arb_push_steps(ctypes.byref(self._cgeom), self._table.data_ptr(), self._mode_code,
+                                                p.data_ptr(), v.data_ptr(), None if steps is None else steps.data_ptr(),
+                                                p.shape[0], float(dt), int(nsteps), float(kappa), ctypes.byref(grav),
+                                                lost.data_ptr(), stream), "arb_push")
         return int(lost.item())
 
     # ------------------------------------------------------------------ single-point queries

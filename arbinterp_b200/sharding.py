@@ -54,13 +54,10 @@ def owner_ranks(coord_slow: torch.Tensor, int_min: float, int_max: float, h: flo
     return torch.where(valid, owner, torch.zeros_like(owner))
 
 
-def exchange_and_query(q: torch.Tensor, owner: torch.Tensor, evaluate: Callable[[torch.Tensor], torch.Tensor],
-                       out_cols: int, group=None) -> torch.Tensor:
-    """Route rows of ``q`` to their owners, evaluate there, route the results back.
-
-    ``evaluate(rows) -> (len(rows), out_cols)`` runs on the receiving rank (the local slab's query
-    kernel).  Returns ``(len(q), out_cols)`` in the caller's row order.  Two all-to-alls, none of
-    them inside the query kernel."""
+def route_rows(rows: torch.Tensor, owner: torch.Tensor, group=None):
+    """Send every row of ``rows`` to rank ``owner[row]`` (one all-to-all of the counts, one of the rows).
+    Returns ``(received, order, send_split, recv_split)``: ``order`` sorts the caller's rows by owner (what was
+    sent is ``rows[order]``), the splits are what :func:`return_rows` needs to send answers back."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
     # owners are tiny integers: a 16-bit stable radix sort is two passes instead of eight, the per-owner
@@ -74,15 +71,82 @@ def exchange_and_query(q: torch.Tensor, owner: torch.Tensor, evaluate: Callable[
     send_split = send_counts.tolist()
     recv_split = recv_counts.tolist()
     from ._lib import permute_rows
-    sendbuf = permute_rows(q, order)
-    recvbuf = q.new_empty((sum(recv_split), q.shape[1]))
+    sendbuf = permute_rows(rows, order)
+    recvbuf = rows.new_empty((sum(recv_split), rows.shape[1]))
     dist.all_to_all_single(recvbuf, sendbuf, recv_split, send_split, group=group)
+    return recvbuf, order, send_split, recv_split
+
+
+def return_rows(res: torch.Tensor, order: torch.Tensor, send_split, recv_split, group=None) -> torch.Tensor:
+    """Inverse of :func:`route_rows` for per-row results: ``res`` (one row per received row) travels back and is
+    put into the caller's original row order."""
+    import torch.distributed as dist
+    from ._lib import permute_rows
+    back = res.new_empty((sum(send_split), res.shape[1]))
+    dist.all_to_all_single(back, res.contiguous(), send_split, recv_split, group=group)
+    return permute_rows(back, order, scatter=True)
+
+
+def exchange_and_query(q: torch.Tensor, owner: torch.Tensor, evaluate: Callable[[torch.Tensor], torch.Tensor],
+                       out_cols: int, group=None) -> torch.Tensor:
+    """Route rows of ``q`` to their owners, evaluate there, route the results back.
+
+    ``evaluate(rows) -> (len(rows), out_cols)`` runs on the receiving rank (the local slab's query
+    kernel).  Returns ``(len(q), out_cols)`` in the caller's row order.  Two all-to-alls, none of
+    them inside the query kernel."""
+    recvbuf, order, send_split, recv_split = route_rows(q, owner, group)
     res = evaluate(recvbuf)
     if res.shape != (recvbuf.shape[0], out_cols):
         raise ValueError(f"evaluate returned {tuple(res.shape)}, expected {(recvbuf.shape[0], out_cols)}")
-    back = res.new_empty((sendbuf.shape[0], out_cols))
-    dist.all_to_all_single(back, res.contiguous(), send_split, recv_split, group=group)
-    return permute_rows(back, order, scatter=True)
+    return return_rows(res, order, send_split, recv_split, group)
+
+
+def push_sharded(pos: torch.Tensor, vel: torch.Tensor, nsteps: int, owner_of: Callable[[torch.Tensor], torch.Tensor],
+                 advance: Callable[[torch.Tensor, torch.Tensor, torch.Tensor], None], group=None) -> int:
+    """Particle push over a slab-sharded table: particles migrate between the slab owners.
+
+    ``pos`` (N, d), ``vel`` (N, 3): this rank's particles, updated in place.  ``owner_of(pos) -> rank`` names the rank
+    whose slab holds a position; ``advance(pos, vel, step)`` runs the local push kernel in its resumable form
+    (arb_push_steps): it advances every row until it is finished (``step > nsteps``; lost particles are NaN and
+    finished) or leaves the local slab (parked unchanged, ``step`` = the next force evaluation).  Rounds of
+    {route parked rows to their owner, advance} repeat until no rank has a parked row; every round moves each
+    parked particle by at least one step, so the loop ends.  Finished rows go home in one last exchange.
+    All exchanges are all-to-alls of (d + 6)-double rows; none is inside the kernel.  Returns the number of this
+    rank's particles that were lost."""
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    n, d = pos.shape
+    dev = pos.device
+    # row = [pos | vel | next step | home rank | home index]; the three integers are exact in float64
+    rows = torch.empty((n, d + 6), dtype=torch.float64, device=dev)
+    rows[:, :d] = pos
+    rows[:, d:d + 3] = vel
+    rows[:, d + 3] = 0.0
+    rows[:, d + 4] = float(rank)
+    rows[:, d + 5] = torch.arange(n, dtype=torch.float64, device=dev)
+    finished = []
+    while True:
+        recv, _, _, _ = route_rows(rows, owner_of(rows[:, :d]), group)
+        p, v = recv[:, :d].contiguous(), recv[:, d:d + 3].contiguous()
+        step = recv[:, d + 3].to(torch.int64).contiguous()
+        if recv.shape[0]:
+            advance(p, v, step)
+        recv[:, :d], recv[:, d:d + 3], recv[:, d + 3] = p, v, step.to(torch.float64)
+        done = step > nsteps
+        finished.append(recv[done])
+        rows = recv[~done].contiguous()
+        left = torch.tensor([rows.shape[0]], dtype=torch.int64, device=dev)
+        dist.all_reduce(left, group=group)
+        if int(left.item()) == 0:
+            break
+    fin = torch.cat(finished, dim=0)
+    home, _, _, _ = route_rows(fin, fin[:, d + 4].to(torch.int64), group)
+    if home.shape[0] != n:
+        raise RuntimeError(f"push_sharded: {home.shape[0]} particles came home, {n} left")
+    idx = home[:, d + 5].to(torch.int64)
+    pos[idx] = home[:, :d]
+    vel[idx] = home[:, d:d + 3]
+    return int(torch.isnan(home[:, 0]).sum().item())
 
 
 def broadcast_field(field, src: int = 0, device=None, group=None) -> torch.Tensor:
@@ -171,3 +235,20 @@ class SlabShardedInterp:
             outs.append(flat[:, col:col + w])
             col += w
         return outs[0] if len(outs) == 1 else tuple(outs)
+
+    def push(self, pos: torch.Tensor, vel: torch.Tensor, dt, nsteps, kappa, gravity=None) -> int:
+        """Fused query + push (``tricubic.push`` / ``quadcubic.push``) over the sharded table: this rank's particles
+        (``pos`` (N, d), ``vel`` (N, 3), CUDA tensors, updated in place) are advanced by ``nsteps`` velocity-Verlet steps;
+        a particle that crosses into another rank's slab is parked by the kernel and resumed there with the
+        arithmetic of an unsharded run, so the result is bit-identical to ``push`` on an unsharded table.
+        Particles whose position is outside the volume (or NaN) at the start are sent to rank 0, which marks them
+        lost.  Returns the number of this rank's particles lost."""
+        d = self.d
+
+        def owner_of(p):
+            return owner_ranks(p[:, d - 1], *self._slow, self.slabs)
+
+        def advance(p, v, step):
+            self.local._push_local(p, v, step, dt, nsteps, kappa, gravity)
+
+        return push_sharded(pos, vel, int(nsteps), owner_of, advance, self.group)

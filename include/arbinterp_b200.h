@@ -133,6 +133,14 @@ int arb_query_grid_host(const arb_geom* g, const double* grid, int64_t pitch_x, 
  *   gravity  : host pointer to 3 doubles or NULL. */
 int arb_push(const arb_geom* g, const double* table, int mode, double* pos, double* vel, int64_t N, double dt,
              int64_t nsteps, double kappa, const double* gravity, unsigned long long* lost_count, void* stream);
+/* Resumable form for slab-sharded tables (g->slab_lo/hi): step_io (device [N] int64, may be NULL = arb_push) holds
+ * for every particle the index of the next step whose force has to be evaluated -- 0 for a fresh particle, a value
+ * > nsteps for one that is finished.  A particle that is inside the volume but outside the table's slab is parked:
+ * pos, vel and step_io are left as they are, so the rank owning that slab resumes it with the arithmetic of an
+ * unsharded run.  On return step_io[n] = nsteps + 1 for finished or lost particles. */
+int arb_push_steps(const arb_geom* g, const double* table, int mode, double* pos, double* vel, int64_t* step_io,
+                   int64_t N, double dt, int64_t nsteps, double kappa, const double* gravity,
+                   unsigned long long* lost_count, void* stream);
 
 /* Row permutation used by the slab-sharded routing path (no counterpart in the single-process reference):
  * gather  (scatter == 0): dst[i][:] = src[order[i]][:];  scatter (scatter != 0): dst[order[i]][:] = src[i][:].

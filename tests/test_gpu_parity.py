@@ -773,3 +773,43 @@ def test_update_values_equals_fresh_construction(d, table):
     q = _uniform_queries(fresh, d, 5_000, rng)
     for x, y in zip(obj.Query(q.copy()), fresh.Query(q.copy())):
         assert np.array_equal(x, y, equal_nan=True)
+
+
+@pytest.mark.parametrize("d", [3, 4])
+def test_resumable_push_across_slabs_equals_unsharded(d):
+    """arb_push_steps on one GPU: two slab tables of the same field take turns; a particle that leaves a slab is
+    parked unchanged and resumed by the other table.  The end state is bit-identical to one fused push on the
+    unsharded table (what SlabShardedInterp.push does across ranks)."""
+    from test_multi_gpu import _push_field
+    rng = np.random.default_rng(31)
+    if d == 4:
+        field = _push_field()
+    else:
+        field = _analytic_field3(14, 13, 17, scalar=True)
+    cls = _cls(d)
+    whole = cls(field.copy(), "quiet")
+    nslow = whole._geo.ncell[d - 1]
+    cut = nslow // 2
+    parts = [cls(field.copy(), "quiet", slab=(0, cut)), cls(field.copy(), "quiet", slab=(cut, nslow))]
+    n, dt, nsteps, kappa = 5000, 0.02, 60, -0.5
+    pos = _uniform_queries(whole, d, n, rng)
+    vel = rng.normal(0, 0.4, (n, 3))
+    grav = (0.0, 0.0, 0.3)
+    pr, vr = torch.from_numpy(pos.copy()).cuda(), torch.from_numpy(vel.copy()).cuda()
+    lost_ref = whole.push(pr, vr, dt, nsteps, kappa, gravity=grav)
+    p, v = torch.from_numpy(pos.copy()).cuda(), torch.from_numpy(vel.copy()).cuda()
+    step = torch.zeros(n, dtype=torch.int64, device="cuda")
+    lost, rounds, migrated = 0, 0, 0
+    while bool((step <= nsteps).any()):
+        for part in parts:
+            before = step.clone()
+            lost += part._push_local(p, v, step, dt, nsteps, kappa, grav)
+            migrated += int(((step > before) & (step <= nsteps)).sum())     # advanced, then parked at the boundary
+        rounds += 1
+        assert rounds <= nsteps + 2
+    assert migrated > 0, "no particle crossed the slab boundary"
+    assert torch.equal(torch.nan_to_num(p, nan=-7.0), torch.nan_to_num(pr, nan=-7.0))
+    assert torch.equal(torch.nan_to_num(v, nan=-7.0), torch.nan_to_num(vr, nan=-7.0))
+    assert lost == lost_ref and 0 < lost < n
+    with pytest.raises(ValueError):
+        parts[0].push(p, v, dt, 1, kappa)               # a slab object points to the sharded entry point

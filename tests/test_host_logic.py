@@ -14,7 +14,7 @@ from conftest import ROOT, load_golden
 
 from arbinterp_b200 import _lib
 from arbinterp_b200.ingest import FieldError, ingest_field, norm_plane, sorted_field
-from arbinterp_b200.sharding import exchange_and_query, owner_ranks, plan_slabs, slab_planes
+from arbinterp_b200.sharding import exchange_and_query, owner_ranks, plan_slabs, push_sharded, slab_planes
 
 
 # ----------------------------------------------------------------------------------------- ingest
@@ -321,3 +321,83 @@ def test_query_routing_world2_gloo(tmp_path):
         got = np.load(tmp_path / f"out{rank}.npy")
         assert np.array_equal(got, ref[rank::world], equal_nan=True)
         assert np.load(tmp_path / f"ok{rank}.npy").all()
+
+
+# ---- sharded push: particle migration between slab owners (CPU stand-in for the resumable kernel)
+_PUSH = dict(t_min=0.0, t_max=6.0, h=1.0, n_layers=6, x_lim=5.0, dt=0.37, nsteps=11)
+
+
+def _fake_advance(p, v, step, lo, hi):
+    """What arb_push_steps does, with a force that depends on the t layer (so a step evaluated by the wrong rank or
+    twice would show): drift in x and t, parked on leaving layers [lo, hi), lost on leaving the volume."""
+    c = _PUSH
+    for n in range(p.shape[0]):
+        while step[n] <= c["nsteps"]:
+            x, t = float(p[n, 0]), float(p[n, 1])
+            if not (c["t_min"] <= t <= c["t_max"]) or abs(x) > c["x_lim"] or np.isnan(x):
+                p[n, 0] = float("nan"); v[n, :] = float("nan"); step[n] = c["nsteps"] + 1
+                break
+            layer = int(np.floor((t - c["t_min"]) / c["h"]))
+            if layer >= c["n_layers"]:
+                p[n, 0] = float("nan"); v[n, :] = float("nan"); step[n] = c["nsteps"] + 1   # upper edge: NaN (DESIGN)
+                break
+            if not (lo <= layer < hi):
+                break                                                  # parked unchanged
+            a = 0.1 * (layer + 1)
+            if step[n] > 0:
+                v[n, 0] += 0.5 * c["dt"] * a
+            if step[n] < c["nsteps"]:
+                v[n, 0] += 0.5 * c["dt"] * a
+                p[n, 0] += c["dt"] * v[n, 0]
+                p[n, 1] += c["dt"]
+            step[n] += 1
+
+
+def _push_worker(rank, world, port, pos_all, vel_all, out_dir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    c = _PUSH
+    slabs = plan_slabs(c["n_layers"], world)
+    lo, hi = slabs[rank]
+    pos = torch.from_numpy(pos_all[rank::world].copy())
+    vel = torch.from_numpy(vel_all[rank::world].copy())
+    rounds = []
+
+    def advance(p, v, step):
+        rounds.append(int(p.shape[0]))
+        _fake_advance(p, v, step, lo, hi)
+
+    lost = push_sharded(pos, vel, c["nsteps"], lambda p: owner_ranks(p[:, 1], c["t_min"], c["t_max"], c["h"], slabs), advance)
+    np.savez(os.path.join(out_dir, f"push{rank}.npz"), pos=pos.numpy(), vel=vel.numpy(), lost=lost, rounds=len(rounds))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_push_migration_gloo(tmp_path, world):
+    """push_sharded over gloo: particles drift through the t slabs of several ranks (and some out of the volume);
+    positions, velocities and loss counts equal a single-process run of the same stepping rule, rows come home in
+    their original order, and the run needs more than one round (so particles really migrated)."""
+    import torch.multiprocessing as mp
+    rng = np.random.default_rng(3)
+    n = 301
+    pos = np.stack([rng.uniform(-4.5, 4.5, n), rng.uniform(0.0, 5.9, n)], axis=1)
+    pos[5, 1] = 7.5                                  # starts outside the volume
+    pos[6, 0] = np.nan
+    vel = np.stack([rng.normal(0, 0.8, n), np.zeros(n), np.zeros(n)], axis=1)
+    mp.spawn(_push_worker, args=(world, _free_port(), pos, vel, str(tmp_path)), nprocs=world, join=True)
+    p_ref, v_ref = torch.from_numpy(pos.copy()), torch.from_numpy(vel.copy())
+    step = torch.zeros(n, dtype=torch.int64)
+    _fake_advance(p_ref, v_ref, step, 0, _PUSH["n_layers"])
+    assert bool((step == _PUSH["nsteps"] + 1).all())
+    total_lost, rounds = 0, []
+    for rank in range(world):
+        z = np.load(tmp_path / f"push{rank}.npz")
+        assert np.array_equal(z["pos"], p_ref.numpy()[rank::world], equal_nan=True)
+        assert np.array_equal(z["vel"], v_ref.numpy()[rank::world], equal_nan=True)
+        assert int(z["lost"]) == int(np.isnan(p_ref.numpy()[rank::world, 0]).sum())
+        rounds.append(int(z["rounds"]))
+        total_lost += int(z["lost"])
+    assert 0 < total_lost < n and max(rounds) > 1
