@@ -490,7 +490,7 @@ build_sep3_kernel(const __grid_constant__ CUtensorMap tmap, const sep::SepParams
 // Grid planes arrive through a two-deep TMA pipeline (one mbarrier per buffer); every plane is transformed
 // along x, y, z once, and the fused z/t phase emits the layer the plane completes.  Software pipeline: iteration
 // s runs {x pass of plane s+1, first half of emit(s)} | barrier | {y pass of plane s+1, second half of emit(s)} |
-// barrier, so the latency-bound passes always share an interval with table stores (Y and delta are double-buffered).
+// barrier, so the latency-bound passes always share an interval with table stores (Y and the corner values are double-buffered).
 template <bool QUIRK>
 __global__ void __launch_bounds__(sep::Sep4::THREADS, 2)
 build_sep4_kernel(const __grid_constant__ CUtensorMap tmap, const sep::SepParams p) {

@@ -20,8 +20,8 @@
 // a shared-memory ring, and the t pass emits one layer of cells per step.  The march is software-pipelined:
 // the x/y passes of plane s+1 share their two barrier intervals with the two halves of step s's emit phase.
 //
-// Everything here is __host__ __device__ and written as "for (e = tid; e < tasks; e += nthreads)" loops
-// over shared arrays, so tools/micro/sep_host_emul.cu can run the very same phases on the CPU and compare
+// Everything here is __host__ __device__ and written as per-thread task loops ("for (e = tid; e < tasks; e += nthreads)")
+// over shared arrays, so tests/host_emul/sep_host_emul.cu can run the very same phases on the CPU and compare
 // them with A f (tests/test_host_logic.py::test_separable_build_phases_on_host).
 #pragma once
 #include <stdint.h>
