@@ -207,10 +207,23 @@ int retire(Slot& s, const Call& c) {
 // Small batches (the reference's single-point and short line queries, A.py:213-342): latency matters,
 // not overlap.  One pinned + one device scratch block laid out [q | count | comps | norm | grad | cell |
 // rows]: one H2D (q and the zeroed counter), the kernel, one D2H (counter and all outputs), one sync.
+// Tiny batches (<= ARB_ZEROCOPY_ROWS rows, default 256) skip both copies: the pinned block is mapped into the
+// device's address space, so the kernel reads the rows and writes the results straight over PCIe -- one launch and
+// one stream synchronise per call.  The NaN-masked rows come back with the scratch copy of q itself.
 // ---------------------------------------------------------------------------------------------------
 namespace arb {
 namespace {
 constexpr int64_t SMALL_ROWS = 8192;
+
+int64_t zero_copy_rows() {
+    static int64_t v = -1;
+    if (v < 0) {
+        const char* e = getenv("ARB_ZEROCOPY_ROWS");
+        v = e ? atoll(e) : 256;
+        if (v < 0) v = 0;
+    }
+    return v;
+}
 
 struct SmallCtx {
     cudaStream_t stream = nullptr;
@@ -241,9 +254,32 @@ int query_host_small(const arb_geom* g, const double* table, int64_t grid_pitch,
         c.cap = want;
     }
     memcpy(c.h + o_q, q_host, sizeof(double) * N * ldq);
+    const bool cell_dev = is_device(cell);
+    if (N <= zero_copy_rows()) {
+        // zero-copy: every pointer the kernel sees is the mapped pinned block (the cell indices too, unless the
+        // caller keeps them on the device)
+        int64_t* z_cell = cell ? (cell_dev ? cell : reinterpret_cast<int64_t*>(c.h + o_cell)) : nullptr;
+        double* zq = reinterpret_cast<double*>(c.h + o_q);
+        int zrc;
+        if (grid_pitch > 0)
+            zrc = query_grid_device(g, table, grid_pitch, mode, zq, N, ldq, reinterpret_cast<double*>(c.h + o_comps),
+                                    reinterpret_cast<double*>(c.h + o_norm), reinterpret_cast<double*>(c.h + o_grad),
+                                    z_cell, nullptr, nullptr, c.stream);
+        else
+            zrc = query_device(g, table, mode, zq, N, ldq, reinterpret_cast<double*>(c.h + o_comps),
+                               reinterpret_cast<double*>(c.h + o_norm), reinterpret_cast<double*>(c.h + o_grad), z_cell,
+                               nullptr, nullptr, c.stream, current_query_variant());
+        if (zrc) return zrc;
+        ARB_CUDA(cudaStreamSynchronize(c.stream));
+        if (comps) memcpy(comps, c.h + o_comps, sizeof(double) * N * 3);
+        if (norm) memcpy(norm, c.h + o_norm, sizeof(double) * N);
+        if (grad) memcpy(grad, c.h + o_grad, sizeof(double) * N * d);
+        if (cell && !cell_dev) memcpy(cell, c.h + o_cell, 8 * N);
+        memcpy(q_host, c.h + o_q, sizeof(double) * N * ldq);      // rows the kernel NaN-masked in place (A.py:350-355)
+        return 0;
+    }
     *reinterpret_cast<unsigned long long*>(c.h + o_count) = 0ULL;
     ARB_CUDA(cudaMemcpyAsync(c.d, c.h, o_count + 8, cudaMemcpyHostToDevice, c.stream));
-    const bool cell_dev = is_device(cell);
     int64_t* d_cell = cell ? (cell_dev ? cell : reinterpret_cast<int64_t*>(c.d + o_cell)) : nullptr;
     double* dq = reinterpret_cast<double*>(c.d + o_q);
     int rc;

@@ -813,3 +813,27 @@ def test_resumable_push_across_slabs_equals_unsharded(d):
     assert lost == lost_ref and 0 < lost < n
     with pytest.raises(ValueError):
         parts[0].push(p, v, dt, 1, kappa)               # a slab object points to the sharded entry point
+
+
+@pytest.mark.parametrize("d", [3, 4])
+def test_zero_copy_tiny_batches_equal_copy_path(d):
+    """Batches of <= 256 rows take the zero-copy path (kernel reads/writes the mapped pinned block); the same rows
+    inside a larger batch take the copy path.  Outputs, in-place NaN rows and cell indices must be identical."""
+    rng = np.random.default_rng(41)
+    field = _analytic_field3(13, 12, 11, rng=rng) if d == 3 else _analytic_field4(9, 8, 7, 6, rng=rng)
+    obj = _cls(d)(field.copy(), "quiet", mode="both")
+    q = _uniform_queries(obj, d, 700, rng, extra=2)
+    q[3, 0] = 1e9; q[17, d - 1] = -1e9; q[30, 1] = np.nan
+    big_q = q.copy()
+    big = obj.Query(big_q)
+    big_inds = obj.queryInds.copy()
+    for n in (1, 2, 31, 200, 256):
+        small_q = q[:n].copy()
+        if n == 1:
+            res = obj.rQuery(small_q)
+        else:
+            res = obj.Query(small_q)
+        for a, b in zip(res, big):
+            assert np.array_equal(a, b[:n], equal_nan=True)
+        assert np.array_equal(small_q, big_q[:n], equal_nan=True)
+        assert np.array_equal(obj.queryInds, big_inds[:n])
