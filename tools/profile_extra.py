@@ -22,3 +22,14 @@ vel = vel / vel.norm(dim=1, keepdim=True) * 0.3 * h
 obj.push(pos, vel, 1.0, 16, 1e-6)
 torch.cuda.synchronize()
 print("profile_extra done")
+# 4-D table-free kernel (quadcubic(table=False)) on the 48^3 x 32 bench grid
+from arbinterp_b200 import quadcubic
+del obj
+torch.cuda.empty_cache()
+rows4 = field_rows((48, 48, 48, 32), dev)
+tf4 = quadcubic(rows4[:, :5].contiguous(), "quiet", table=False)
+lo4 = torch.tensor(tf4._geo.int_min, dtype=torch.float64, device=dev); hi4 = torch.tensor(tf4._geo.int_max, dtype=torch.float64, device=dev)
+q4 = lo4 + torch.rand(n, 4, generator=g, dtype=torch.float64, device=dev) * (hi4 - lo4) * (1 - 1e-12)
+tf4.Query(q4); tf4.Query(q4)
+torch.cuda.synchronize()
+print("profile_extra 4-D table-free done")
