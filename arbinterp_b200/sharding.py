@@ -191,7 +191,10 @@ def broadcast_ingested(field, d: int, src: int = 0, device=None, group=None):
     for n in npts:
         per_axis.append(axes[off:off + n].clone())
         off += n
-    return IngestedField(planes=planes, geo=geometry_from_axes(per_axis))
+    out = IngestedField(planes=planes, geo=geometry_from_axes(per_axis))
+    if rank == src:
+        out.geo.row_index = geo.row_index          # row -> grid point map of the raw rows (update_values(order='rows'))
+    return out
 
 
 class SlabShardedInterp:
@@ -212,6 +215,8 @@ class SlabShardedInterp:
         if hi == lo:
             raise ValueError(f"rank {self.rank} has an empty slab: {n_slow} layers over {self.world} ranks")
         self.local = cls(full, *args, slab=(lo, hi), **kwargs)
+        self._src = src
+        self._ncol = int(full.planes.shape[0])      # 1 (scalar input) or 3 (vector input)
         del full
         self.d = d
         g = self.local._geo
@@ -252,3 +257,32 @@ class SlabShardedInterp:
             self.local._push_local(p, v, step, dt, nsteps, kappa, gravity)
 
         return push_sharded(pos, vel, int(nsteps), owner_of, advance, self.group)
+
+
+    def update_values(self, values=None, order: str = "rows") -> None:
+        """New field values on the same grid (``tricubic.update_values``) for the sharded table: the source rank
+        passes ``values`` ((N, 1|3), in the row order of the field it constructed from, or ``order='grid'``), every
+        other rank passes None; the dense planes are broadcast once and every rank rebuilds its slab in place."""
+        import torch.distributed as dist
+        loc = self.local
+        geo = loc._geo
+        total = 1
+        for n in geo.npts:
+            total *= n
+        dev = loc._device
+        planes = torch.empty((self._ncol, total), dtype=torch.float64, device=dev)
+        if self.rank == self._src:
+            v = torch.as_tensor(values)
+            if v.dim() == 1:
+                v = v.unsqueeze(1)
+            if tuple(v.shape) != (total, self._ncol):
+                raise ValueError(f"values must have shape ({total}, {self._ncol}), got {tuple(v.shape)}")
+            v = v.to(device=dev, dtype=torch.float64)
+            if order == "rows":
+                planes[:, geo.row_index.to(dev).long()] = v.T
+            elif order == "grid":
+                planes.copy_(v.T)
+            else:
+                raise ValueError("order must be 'rows' or 'grid'")
+        dist.broadcast(planes, src=self._src, group=self.group)
+        loc.update_values(planes.T, order="grid")

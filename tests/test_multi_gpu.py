@@ -38,6 +38,13 @@ def _worker(rank, world, port, field, q_all, out_dir):
     out = sharded.Query(mine)
     np.save(os.path.join(out_dir, f"slab{rank}.npy"), torch.cat(out, dim=1).cpu().numpy())
     np.save(os.path.join(out_dir, f"table_rows{rank}.npy"), np.array([sharded.local.table.shape[0], whole.table.shape[0]]))
+    # (c) new field values on the same grid: rank 0 supplies them, every rank rebuilds its slab in place
+    new_vals = np.cos(2.0 * field[:, 4:]) + field[:, [0]]
+    sharded.update_values(new_vals if rank == 0 else None)
+    fresh = quadcubic(np.concatenate([field[:, :4], new_vals], axis=1), "quiet", mode="both")
+    out2 = sharded.Query(mine)
+    ref2 = np.hstack(fresh.Query(q_all.copy()))[rank::world]
+    np.save(os.path.join(out_dir, f"upd{rank}.npy"), np.array([np.array_equal(torch.cat(out2, dim=1).cpu().numpy(), ref2, equal_nan=True)]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -56,6 +63,7 @@ def test_replicated_and_slab_sharded_world2(tmp_path):
         assert np.array_equal(got, w0[rank::world], equal_nan=True)
         local_rows, whole_rows = np.load(tmp_path / f"table_rows{rank}.npy")
         assert local_rows < whole_rows                      # each rank really holds only its slab
+        assert bool(np.load(tmp_path / f"upd{rank}.npy")[0]), "update_values on the sharded table"
 
 
 def _push_field():
