@@ -368,7 +368,7 @@ struct GridQueryParams {
 
 using gridfree::catmull_rom;
 
-template <int MODE, int THREADS>
+template <int MODE, int THREADS, bool DEDUP>
 __global__ void __launch_bounds__(THREADS) query_grid_kernel(const __grid_constant__ CUtensorMap tmap, const QueryParams p) {
     constexpr int D = 3;
     constexpr int C = MODE == 0 ? 3 : (MODE == 1 ? 1 : 4);
@@ -397,11 +397,21 @@ __global__ void __launch_bounds__(THREADS) query_grid_kernel(const __grid_consta
         L.ok = false; L.masked = false; L.cell_global = 0; L.cell_local = 0;
         L.idx[0] = L.idx[1] = L.idx[2] = 0;
         if (n < p.N) L = locate<D>(p, n);
-        const unsigned fmask = __ballot_sync(0xffffffffu, L.ok);
+        // DEDUP: lanes whose queries fall into the same cell share one box (the elected lane fetches it, the
+        // others read its slot with their own row rotation -- still distinct banks or a broadcast)
+        bool fetch = L.ok;
+        const unsigned char* rd = slot;
+        if (DEDUP) {
+            const unsigned peers = __match_any_sync(0xffffffffu, L.ok ? L.cell_global : (int64_t)(-1 - lane));
+            const int src_lane = __ffs(peers) - 1;
+            fetch = L.ok && (src_lane == lane);
+            rd = smem + (size_t)(threadIdx.x - lane + src_lane) * BYTES;
+        }
+        const unsigned fmask = __ballot_sync(0xffffffffu, fetch);
         if (lane == 0) mbar_expect_tx(bar, (uint32_t)__popc(fmask) * BYTES);
         __syncwarp();
         const int off = L.idx[0] & 1;
-        if (L.ok) tma_load_4d(slot, &tmap, bar, L.idx[0] - off, L.idx[1], L.idx[2], comp);
+        if (fetch) tma_load_4d(slot, &tmap, bar, L.idx[0] - off, L.idx[1], L.idx[2], comp);
         if (comp == 0 && n < p.N) {
             if (p.out_cell) p.out_cell[n] = L.cell_global;
             if (L.masked) mask_row_in_place(p, n);
@@ -438,7 +448,7 @@ __global__ void __launch_bounds__(THREADS) query_grid_kernel(const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int row = 4 * ((k + rk) & 3) + ((j + rj) & 3);
-                    const double2* r = reinterpret_cast<const double2*>(slot + row * 48);
+                    const double2* r = reinterpret_cast<const double2*>(rd + row * 48);
                     const double2 a = r[0], b = r[1], c = r[2];
                     double pp = a.x * wx6[0];
                     pp = fma(a.y, wx6[1], pp); pp = fma(b.x, wx6[2], pp); pp = fma(b.y, wx6[3], pp);
@@ -481,7 +491,7 @@ __global__ void __launch_bounds__(THREADS) query_grid_kernel(const __grid_consta
 // (A.py:860) the lanes also accumulate the plane's signed parity sums, exchange them over two shuffles to form
 // fxyzt at the cell's 16 corners, and lanes 0/1 add the rank-16 term of their ct (arb_gridfree.cuh).  The four
 // partial results are summed over two more shuffle steps.
-template <int MODE, int THREADS, bool QUIRK>
+template <int MODE, int THREADS, bool QUIRK, bool DEDUP>
 __global__ void __launch_bounds__(THREADS) query_grid4_kernel(const __grid_constant__ CUtensorMap tmap, const QueryParams p) {
     constexpr int D = 4;
     constexpr int C = MODE == 0 ? 3 : (MODE == 1 ? 1 : 4);
@@ -512,11 +522,19 @@ __global__ void __launch_bounds__(THREADS) query_grid4_kernel(const __grid_const
         L.idx[0] = L.idx[1] = L.idx[2] = L.idx[3] = 0;
         L.frac[0] = L.frac[1] = L.frac[2] = L.frac[3] = 0.0;
         if (n < p.N) L = locate<D>(p, n);
-        const unsigned fmask = __ballot_sync(0xffffffffu, L.ok);
+        bool fetch = L.ok;                                   // DEDUP: one box per distinct (cell, plane) in the warp
+        const unsigned char* rd = slot;
+        if (DEDUP) {
+            const unsigned peers = __match_any_sync(0xffffffffu, L.ok ? L.cell_global * 4 + l : (int64_t)(-1 - lane));
+            const int src_lane = __ffs(peers) - 1;
+            fetch = L.ok && (src_lane == lane);
+            rd = smem + (size_t)(threadIdx.x - lane + src_lane) * BYTES;
+        }
+        const unsigned fmask = __ballot_sync(0xffffffffu, fetch);
         if (lane == 0) mbar_expect_tx(bar, (uint32_t)__popc(fmask) * BYTES);
         __syncwarp();
         const int off = L.idx[0] & 1;
-        if (L.ok) tma_load_5d(const_cast<unsigned char*>(slot), &tmap, bar, L.idx[0] - off, L.idx[1], L.idx[2], L.idx[3] + l, comp);
+        if (fetch) tma_load_5d(const_cast<unsigned char*>(slot), &tmap, bar, L.idx[0] - off, L.idx[1], L.idx[2], L.idx[3] + l, comp);
         if (comp == 0 && l == 0 && n < p.N) {
             if (p.out_cell) p.out_cell[n] = L.cell_global;
             if (L.masked) mask_row_in_place(p, n);
@@ -536,8 +554,8 @@ __global__ void __launch_bounds__(THREADS) query_grid4_kernel(const __grid_const
 #pragma unroll
         for (int i = 0; i < 8; ++i) pp.S[i] = 0.0;
         if (L.ok) {
-            if (grad_comp) gridfree::plane_partial<true, QUIRK>(slot, off, rj, rk, wx, dwx, wy, dwy, wz, dwz, pp);
-            else gridfree::plane_partial<false, QUIRK>(slot, off, rj, rk, wx, dwx, wy, dwy, wz, dwz, pp);
+            if (grad_comp) gridfree::plane_partial<true, QUIRK>(rd, off, rj, rk, wx, dwx, wy, dwy, wz, dwz, pp);
+            else gridfree::plane_partial<false, QUIRK>(rd, off, rj, rk, wx, dwx, wy, dwy, wz, dwz, pp);
         }
         double m[5] = {pp.val * wt_l, pp.gx * wt_l, pp.gy * wt_l, pp.gz * wt_l, pp.val * dwt_l};
         if (QUIRK) {
@@ -738,12 +756,12 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-template <int MODE>
+template <int MODE, bool DEDUP = true>
 static int launch_grid(const CUtensorMap& tm, const QueryParams& p, cudaStream_t st) {
     constexpr int C = MODE == 0 ? 3 : (MODE == 1 ? 1 : 4);
     constexpr int THREADS = 128;
     const size_t smem = (size_t)THREADS * 768;
-    auto k = query_grid_kernel<MODE, THREADS>;
+    auto k = query_grid_kernel<MODE, THREADS, DEDUP>;
     static LaunchCache cache = {};
     const int64_t items = ((p.N + 31) / 32) * C;
     const int grid = persistent_grid(k, THREADS, smem, (items + THREADS / 32 - 1) / (THREADS / 32), cache);
@@ -751,12 +769,12 @@ static int launch_grid(const CUtensorMap& tm, const QueryParams& p, cudaStream_t
     return check_cuda(cudaGetLastError(), "query_grid_kernel launch");
 }
 
-template <int MODE, bool QUIRK>
+template <int MODE, bool QUIRK, bool DEDUP = true>
 static int launch_grid4(const CUtensorMap& tm, const QueryParams& p, cudaStream_t st) {
     constexpr int C = MODE == 0 ? 3 : (MODE == 1 ? 1 : 4);
     constexpr int THREADS = 128;
     const size_t smem = (size_t)THREADS * 768;
-    auto k = query_grid4_kernel<MODE, THREADS, QUIRK>;
+    auto k = query_grid4_kernel<MODE, THREADS, QUIRK, DEDUP>;
     static LaunchCache cache = {};
     const int64_t items = ((p.N + 7) / 8) * C;
     const int grid = persistent_grid(k, THREADS, smem, (items + THREADS / 32 - 1) / (THREADS / 32), cache);
@@ -803,10 +821,21 @@ int query_grid_device(const arb_geom* g, const double* grid, int64_t pitch_x, in
                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { set_error("arb_query_grid: cuTensorMapEncodeTiled failed with CUresult %d", (int)cr); return 2; }
+    const bool dedup = g_query_variant != 20;      // variant 20: no warp de-duplication (here as in the table kernel)
     if (d == 3) {
+        if (!dedup) {
+            if (mode == ARB_MODE_VECTOR) return launch_grid<0, false>(tm, p, st);
+            if (mode == ARB_MODE_NORM) return launch_grid<1, false>(tm, p, st);
+            return launch_grid<2, false>(tm, p, st);
+        }
         if (mode == ARB_MODE_VECTOR) return launch_grid<0>(tm, p, st);
         if (mode == ARB_MODE_NORM) return launch_grid<1>(tm, p, st);
         return launch_grid<2>(tm, p, st);
+    }
+    if (!dedup && !(g->flags & ARB_GEOM_FIXED_D4)) {
+        if (mode == ARB_MODE_VECTOR) return launch_grid4<0, true, false>(tm, p, st);
+        if (mode == ARB_MODE_NORM) return launch_grid4<1, true, false>(tm, p, st);
+        return launch_grid4<2, true, false>(tm, p, st);
     }
     if (g->flags & ARB_GEOM_FIXED_D4) {       // corrected 4-D matrix: plain M^(x)4
         if (mode == ARB_MODE_VECTOR) return launch_grid4<0, false>(tm, p, st);
