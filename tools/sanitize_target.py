@@ -35,4 +35,23 @@ for mode in ("vector", "norm", "both"):
     lib.arb_set_query_variant(0)
     for fixed in (False, True):
         quadcubic(f4, "quiet", mode=mode, table=False, fixed_d4=fixed).Query(q4.copy())
+# zero-copy path (<= 256 rows), single point, resumable push on slab tables, update_values
+import torch
+o = tricubic(f3, "quiet", mode="both")
+o.Query(q[:40].copy()); o.Query(q[0].copy())
+o4 = quadcubic(f4, "quiet", mode="both")
+o4.Query(q4[:8].copy())
+o4.update_values(f4[:, 4:] * 1.5)
+for cls, f, d in ((tricubic, f3, 3), (quadcubic, f4, 4)):
+    whole = cls(f[:, :d + 1].copy(), "quiet")
+    ns = whole._geo.ncell[d - 1]
+    parts = [cls(f[:, :d + 1].copy(), "quiet", slab=(0, ns // 2)), cls(f[:, :d + 1].copy(), "quiet", slab=(ns // 2, ns))]
+    lo = np.array(whole._geo.int_min); hi = np.array(whole._geo.int_max)
+    p = torch.from_numpy(lo + rng.uniform(0.1, 0.9, (500, d)) * (hi - lo)).cuda()
+    v = torch.from_numpy(rng.normal(0, 0.3, (500, 3))).cuda()
+    step = torch.zeros(500, dtype=torch.int64, device="cuda")
+    for _ in range(6):
+        for part in parts:
+            part._push_local(p, v, step, 0.02, 12, -0.5, (0.0, 0.0, 0.2))
+    whole.push(p.clone(), v.clone(), 0.02, 5, -0.5)
 print("sanitize target done")
