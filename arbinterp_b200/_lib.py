@@ -116,6 +116,10 @@ def permute_rows(src, order, scatter: bool = False):
     """Row gather ``src[order]`` / scatter ``out[order] = src`` of a contiguous float64 (N, w) CUDA tensor with the
     library's kernel (torch's row gather is ~30x slower for 24-64 byte rows); CPU tensors use torch."""
     import torch
+    if src.dim() != 2 or src.dtype != torch.float64:
+        raise TypeError(f"permute_rows moves float64 (N, w) rows, got {src.dtype} with shape {tuple(src.shape)}")
+    if order.dtype != torch.int64 or order.shape != (src.shape[0],):
+        raise TypeError("permute_rows needs an int64 order with one entry per row")
     if not src.is_cuda:
         if scatter:
             out = torch.empty_like(src)

@@ -619,6 +619,17 @@ static int g_build_variant = 0;
 struct GridMap {
     CUtensorMap tmap;
     double* padded = nullptr;
+    cudaStream_t stream = nullptr;
+    GridMap() = default;
+    GridMap(const GridMap&) = delete;
+    GridMap& operator=(const GridMap&) = delete;
+    // stream-ordered release on every exit path (error returns included): the free is queued behind the
+    // kernels that read the copy
+    void release() {
+        if (padded) cudaFreeAsync(padded, stream);
+        padded = nullptr;
+    }
+    ~GridMap() { release(); }
 };
 
 static int make_grid_map(int D, const double* grid, int ncomp, const int64_t* n, const cuuint32_t* box_dims,
@@ -629,6 +640,7 @@ static int make_grid_map(int D, const double* grid, int ncomp, const int64_t* n,
     int64_t pitch = n[0];
     int64_t rows = ncomp;
     for (int a = 1; a < D; ++a) rows *= n[a];
+    out->stream = st;
     if (n[0] & 1) {
         pitch = n[0] + 1;
         ARB_CUDA(cudaMallocAsync(&out->padded, sizeof(double) * pitch * rows, st));
@@ -637,8 +649,7 @@ static int make_grid_map(int D, const double* grid, int ncomp, const int64_t* n,
         src = out->padded;
     }
     if ((reinterpret_cast<uintptr_t>(src) & 15) != 0) {
-        if (out->padded) cudaFreeAsync(out->padded, st);
-        out->padded = nullptr;
+        out->release();
         set_error("arb_build_coeffs: grid pointer must be 16-byte aligned");
         return 1;
     }
@@ -656,8 +667,7 @@ static int make_grid_map(int D, const double* grid, int ncomp, const int64_t* n,
                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) {
-        if (out->padded) cudaFreeAsync(out->padded, st);
-        out->padded = nullptr;
+        out->release();
         set_error("arb_build_coeffs: cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
         return 2;
     }
@@ -675,8 +685,7 @@ static int finish_build(int D, int ncomp, int64_t ncell, double* table, GridMap*
     const int64_t tail = (int64_t)ncomp * (1 << (2 * D));
     fill_nan_kernel<<<(unsigned)((tail + 255) / 256), 256, 0, st>>>(table + ncell * tail, tail);
     ARB_CUDA(cudaGetLastError());
-    if (gm->padded) ARB_CUDA(cudaFreeAsync(gm->padded, st));
-    gm->padded = nullptr;
+    gm->release();
     return 0;
 }
 

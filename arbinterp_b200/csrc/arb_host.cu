@@ -8,6 +8,7 @@
 #include <thread>
 #include <vector>
 #include <unistd.h>
+#include <sched.h>
 #include "arb_common.cuh"
 
 namespace arb {
@@ -31,6 +32,7 @@ class CopyPool {
     void copy(void* dst, const void* src, size_t bytes) {
         if (bytes < (4u << 20)) { memcpy(dst, src, bytes); return; }
         ensure_started();
+        if (workers_.empty()) { memcpy(dst, src, bytes); return; }
         const int parts = (int)workers_.size() + 1;
         const size_t step = ((bytes / parts) + 4095) & ~(size_t)4095;
         {
@@ -51,13 +53,24 @@ class CopyPool {
   private:
     struct Task { char* dst; const char* src; size_t n; };
     void ensure_started() {
-        if (pid_ == getpid() && !workers_.empty()) return;
+        if (pid_ == getpid() && started_) return;
         if (pid_ != getpid()) {                    // forked child: the parent's threads do not exist here
             workers_.clear(); tasks_.clear(); pending_ = 0;   // (already detached)
         }
         pid_ = getpid();
-        unsigned hw = std::thread::hardware_concurrency();
-        const int n = hw >= 16 ? 5 : (hw >= 8 ? 3 : 1);
+        started_ = true;
+        // one memcpy thread moves 10-25 GB/s; a Gen5 x16 link needs ~55 GB/s each way, so the pool grows with the
+        // cores this process may run on (sched_getaffinity: a rank bound to its GPU's cores gets its share, not
+        // the whole box) up to 11 helpers; ARB_COPY_THREADS overrides
+        int allowed = 0;
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof(set), &set) == 0) allowed = CPU_COUNT(&set);
+        if (allowed <= 0) allowed = (int)std::thread::hardware_concurrency();
+        int n = allowed - 2;
+        if (n > 11) n = 11;
+        if (n < 1) n = 1;
+        if (const char* e = getenv("ARB_COPY_THREADS")) { const int v = atoi(e); if (v >= 1 && v <= 64) n = v - 1; }
+        if (n < 1) { workers_.clear(); return; }
         for (int i = 0; i < n; ++i) {
             workers_.emplace_back([this] {
                 for (;;) {
@@ -83,6 +96,7 @@ class CopyPool {
     std::vector<Task> tasks_;
     std::vector<std::thread> workers_;
     int pending_ = 0;
+    bool started_ = false;
     pid_t pid_ = 0;
 };
 // Never destroyed: the workers block on the condition variable for the life of the process, and
@@ -129,6 +143,7 @@ int ensure_capacity(HostCtx& c, int64_t rows, int64_t ldq) {
     if (rows <= c.cap_rows && ldq <= c.cap_ldq) return 0;
     if (rows < c.cap_rows) rows = c.cap_rows;
     if (ldq < c.cap_ldq) ldq = c.cap_ldq;
+    c.cap_rows = 0; c.cap_ldq = 0;            // a failed (re)allocation must not leave a stale capacity behind
     for (int i = 0; i < NSLOT; ++i) {
         Slot& s = c.slot[i];
         if (!s.stream) {

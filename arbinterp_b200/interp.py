@@ -18,7 +18,10 @@ Differences a user can observe, all documented in DESIGN.md:
   * ``tricubic(..., table=False)`` / ``quadcubic(..., table=False)`` keep no coefficient table at all and
     evaluate every query from its 4^d grid neighbourhood (for fields that change often; CHANGELOG.md:9 of the
     reference); the 4-D form adds the rank-16 term that reproduces A.py:860 unless ``fixed_d4=True``;
-  * ``save(path)`` / ``load(path)`` persist the coefficient table.
+  * ``save(path)`` / ``load(path)`` persist the coefficient table;
+  * ``tricubic(field, devices=[0, 1, ...])`` keeps one replica of the table per listed GPU in this process and
+    fans numpy range queries out over them (sharding.ReplicatedInterp / SlabShardedInterp are the
+    one-process-per-GPU forms).
 """
 from __future__ import annotations
 
@@ -62,7 +65,16 @@ class _CubicInterpolator:
         shape = (0, pre.ncols) if pre is not None else getattr(field, "shape", None)
         if shape is None or len(shape) != 2 or shape[1] not in (d + 1, d + 3) or (pre is not None and pre.geo.d != d):
             sys.exit(f"--- Input not shaped as expected - should be N x {d + 1} or N x {d + 3} ---")  # A.py:104, 723
-        self._device = _cuda_device(kwargs.get("device"))
+        devices = kwargs.get("devices")                          # single-process multi-GPU: one replica per device
+        if devices is not None:
+            devices = [_cuda_device(x) for x in devices]
+            if not devices or len(set(devices)) != len(devices):
+                raise ValueError("devices must be a non-empty list of distinct CUDA devices")
+            if kwargs.get("device") is not None and _cuda_device(kwargs["device"]) != devices[0]:
+                raise ValueError("device= and devices[0] disagree")
+            if kwargs.get("slab") is not None:
+                raise ValueError("devices=[...] replicates the table; slab-sharded tables use sharding.SlabShardedInterp")
+        self._device = devices[0] if devices else _cuda_device(kwargs.get("device"))
         self._lib = _lib.load()
         slab = kwargs.get("slab")                                # (lo, hi) cell layers of the slowest axis
         self._reference_quirk = not bool(kwargs.get("fixed_d4", False))
@@ -99,7 +111,9 @@ class _CubicInterpolator:
         self._mode_code = {"vector": _lib.MODE_VECTOR, "norm": _lib.MODE_NORM, "both": _lib.MODE_BOTH}[mode]
 
         self._planes = self._component_planes(planes)
-        del planes
+        # the reference keeps the sorted field in every mode (A.py:14, 530-532); in 'norm' mode the table is built
+        # from |B| only, so the three raw planes are kept beside it (not for one slab of a sharded table)
+        self._raw = planes[0:3] if (mode == "norm" and not scalar and slab is None) else None
 
         self._set_geometry_attributes()
 
@@ -118,10 +132,19 @@ class _CubicInterpolator:
             if self._pitch != nx:
                 self._planes = torch.nn.functional.pad(self._planes, (0, 1)).contiguous()
             self._make_cgeom()
+            # the planes were written by torch ops on the current stream; numpy queries run on the library's own
+            # non-blocking streams, which do not order against it -- finish the writes here (as _build_table does)
+            torch.cuda.current_stream(self._device).synchronize()
         else:
             self._build_table()
         self._last_cells = None
         self.queryInd = None
+        self._replicas = [self]
+        if devices and len(devices) > 1:
+            sub = {k: v for k, v in kwargs.items() if k not in ("devices", "device", "quiet")}
+            for dev in devices[1:]:
+                self._replicas.append(type(self)(IngestedField(planes=planes.to(dev), geo=geo), "quiet", device=dev, **sub))
+        del planes
 
         self._bind_mode()
 
@@ -170,11 +193,17 @@ class _CubicInterpolator:
             planes = v.T.contiguous()
         else:
             raise ValueError("order must be 'rows' or 'grid'")
-        self._planes = self._component_planes(planes.reshape([ncol] + list(geo.npts[::-1])))
-        del planes
+        dense = planes.reshape([ncol] + list(geo.npts[::-1]))
+        self._planes = self._component_planes(dense)
+        if getattr(self, "_raw", None) is not None:
+            self._raw = dense[0:3]
+        for rep in getattr(self, "_replicas", [self])[1:]:
+            rep.update_values(planes.T.to(rep._device), order="grid")
+        del planes, dense
         if self._table is None:
             if self._pitch != geo.npts[0]:
                 self._planes = torch.nn.functional.pad(self._planes, (0, 1)).contiguous()
+            torch.cuda.current_stream(self._device).synchronize()   # see __init__: lib streams do not order against torch's
         else:
             self._build_table()
         self._last_cells = None
@@ -251,6 +280,8 @@ class _CubicInterpolator:
             if f.read(8) != cls._MAGIC:
                 raise ValueError(f"{path}: not an arbinterp_b200 coefficient file")
             hlen = int(np.frombuffer(f.read(8), dtype=np.uint64)[0])
+            if hlen > (1 << 20):
+                raise ValueError(f"{path}: implausible header length {hlen}")
             header = json.loads(f.read(hlen).decode("utf-8"))
             if header["d"] != cls._d:
                 raise ValueError(f"{path} holds a {header['d']}-D table, {cls.__name__} is {cls._d}-D")
@@ -268,10 +299,27 @@ class _CubicInterpolator:
             unhex = lambda xs: [float.fromhex(v) for v in xs]
             self._geo = Geometry(d=cls._d, npts=npts, ncell=[n - 3 for n in npts], h=unhex(header["h"]),
                                  int_min=unhex(header["int_min"]), int_max=unhex(header["int_max"]))
-            self._slab = tuple(header["slab"])
+            self._slab = tuple(int(v) for v in header["slab"])
             self._planes = None
+            self._raw = None
+            self._replicas = [self]
             self._table_free = False
-            shape = tuple(header["table_shape"])
+            shape = tuple(int(v) for v in header["table_shape"])
+            # the header is untrusted input: the table shape must be the one this geometry, slab and mode imply,
+            # and the file must actually hold that many bytes, before anything is allocated
+            d = cls._d
+            lo, hi = self._slab if len(self._slab) == 2 else (-1, -1)
+            if len(npts) != d or min(npts) < 4 or not (0 <= lo < hi <= npts[d - 1] - 3):
+                raise ValueError(f"{path}: inconsistent geometry in header (npts {npts}, slab {self._slab})")
+            layer = 1
+            for a in range(d - 1):
+                layer *= npts[a] - 3
+            want = (layer * (hi - lo) + 1, {"vector": 3, "norm": 1, "both": 4}[self._mode], 4 ** d)
+            if shape != want:
+                raise ValueError(f"{path}: table shape {shape} does not match geometry/mode (expected {want})")
+            left = os.fstat(f.fileno()).st_size - f.tell()
+            if left < 8 * want[0] * want[1] * want[2]:
+                raise ValueError(f"{path}: truncated table")
             self._table = torch.empty(shape, dtype=torch.float64, device=self._device)
             flat = self._table.reshape(-1)
             step = max(1, chunk_bytes // 8)
@@ -325,13 +373,19 @@ class _CubicInterpolator:
 
     @property
     def inputfield(self):
+        """The sorted field (A.py:530-532 / 1266-1269): rows x fastest, columns as in the constructor's array."""
         planes = self._planes
         if planes is None:
             raise AttributeError("inputfield is unavailable after load(): a coefficient file does not store the field")
-        if self._mode in ("norm", "both") and not self._scalar_input:
-            raise AttributeError("inputfield is not kept in 'norm'/'both' mode; only the interpolated planes are")
-        if getattr(self, "_table_free", False):
-            planes = planes[..., :self._geo.npts[0]]              # drop the TMA pitch padding
+        if self._scalar_input:
+            planes = planes[0:1]
+        elif self._mode == "norm":
+            planes = getattr(self, "_raw", None)
+            if planes is None:
+                raise AttributeError("inputfield is not kept for one slab of a sharded 'norm' table")
+        else:
+            planes = planes[0:3]                                  # 'vector' / 'both': Bx, By, Bz (+ |B| behind them)
+        planes = planes[..., :self._geo.npts[0]]                  # drop the table-free TMA pitch padding, if any
         return sorted_field(planes, self._geo).cpu().numpy()
 
     @property
@@ -388,6 +442,8 @@ class _CubicInterpolator:
         c = self._last_cells
         if c is None:
             raise AttributeError("queryInds is set by the first range query")
+        if isinstance(c, list):                                  # one share per device replica, in row order
+            return np.concatenate([t.cpu().numpy() for t in c])
         return c.cpu().numpy() if isinstance(c, torch.Tensor) else c
 
     def allCoeffs(self):
@@ -442,8 +498,46 @@ class _CubicInterpolator:
         self._last_cells = cells
         return comps, norm, grad
 
+    def _host_outputs(self, n):
+        """Host result arrays of a numpy range query, as CPU torch tensors.  Page-locked ones let the D2H copies land
+        directly; beyond a few GB pinning itself becomes the cost (and can fail), so very large results are ordinary
+        arrays staged through the library's pinned ring."""
+        d, mode = self._d, self._mode
+        if n * 8 * (3 + 1 + d) <= self._PIN_LIMIT_BYTES:
+            return self._outputs(n, pinned=True)
+        comps = torch.from_numpy(np.empty((n, 3))) if mode in ("vector", "both") else None
+        norm = torch.from_numpy(np.empty((n, 1))) if mode in ("norm", "both") else None
+        grad = torch.from_numpy(np.empty((n, d))) if mode in ("norm", "both") else None
+        return comps, norm, grad
+
+    def _host_rows(self, work, lo, hi, comps, norm, grad):
+        """Rows [lo, hi) of the host batch ``work`` through this object's device: pipelined H2D / kernel / D2H inside
+        the library (arb_query_host).  Returns the device tensor of cell indices (read back lazily)."""
+        n = hi - lo
+        dev = self._device
+        row = lambda t: None if t is None else t[lo:hi].data_ptr()
+        with torch.cuda.device(dev):
+            # the library works on its own non-blocking streams: anything torch still has queued for the blocks
+            # involved (a freed block re-used for `cells`, planes being rewritten) must be finished first
+            torch.cuda.current_stream(dev).synchronize()
+            cells = torch.empty(n, dtype=torch.int64, device=dev)        # stays in HBM; read back lazily
+            chunk = int(os.environ.get("ARB_HOST_CHUNK_ROWS", "0"))
+            qptr = work.ctypes.data + lo * work.strides[0]
+            if self._table is None:
+                _lib.check(self._lib.arb_query_grid_host(ctypes.byref(self._cgeom), self._planes.data_ptr(), self._pitch,
+                                                         self._mode_code, qptr, n, work.shape[1],
+                                                         row(comps), row(norm), row(grad),
+                                                         cells.data_ptr(), chunk), "arb_query_grid_host")
+            else:
+                _lib.check(self._lib.arb_query_host(ctypes.byref(self._cgeom), self._table.data_ptr(), self._mode_code,
+                                                    qptr, n, work.shape[1], row(comps), row(norm), row(grad),
+                                                    cells.data_ptr(), chunk), "arb_query_host")
+        return cells
+
     def _range_host(self, query: np.ndarray):
-        """numpy queries: pipelined H2D / kernel / D2H inside the library (arb_query_host)."""
+        """numpy queries (the reference's call, A.py:177-211).  One device: arb_query_host.  ``devices=[...]``: the
+        batch is cut into one contiguous share per replica and the shares run concurrently, one host thread per
+        device (the library call releases the GIL); results land in one set of output arrays."""
         d = self._d
         if query.ndim != 2 or query.shape[1] < d:
             raise IndexError(f"query must be (N, >={d})")
@@ -452,35 +546,32 @@ class _CubicInterpolator:
         n = work.shape[0]
         if n <= self._SMALL_ROWS:
             return self._range_host_small(query, work, direct)
-        # page-locked outputs let the D2H copies land directly; beyond a few GB pinning itself becomes the cost
-        # (and can fail), so very large results are ordinary arrays staged through the library's pinned ring
-        pinned = n * 8 * (3 + 1 + d) <= self._PIN_LIMIT_BYTES
-        if pinned:
-            comps, norm, grad = self._outputs(n, pinned=True)
+        comps, norm, grad = self._host_outputs(n)
+        reps = getattr(self, "_replicas", None) or [self]
+        nrep = min(len(reps), max(1, n // self._MULTI_MIN_ROWS))
+        if nrep == 1:
+            cells = self._host_rows(work, 0, n, comps, norm, grad)
         else:
-            mode = self._mode
-            comps = torch.from_numpy(np.empty((n, 3))) if mode in ("vector", "both") else None
-            norm = torch.from_numpy(np.empty((n, 1))) if mode in ("norm", "both") else None
-            grad = torch.from_numpy(np.empty((n, d))) if mode in ("norm", "both") else None
-        cells = torch.empty(n, dtype=torch.int64, device=self._device)   # stays in HBM; read back lazily
-        with torch.cuda.device(self._device):
-            chunk = int(os.environ.get("ARB_HOST_CHUNK_ROWS", "0"))
-            if self._table is None:
-                _lib.check(self._lib.arb_query_grid_host(ctypes.byref(self._cgeom), self._planes.data_ptr(), self._pitch,
-                                                         self._mode_code, work.ctypes.data, n, work.shape[1],
-                                                         self._ptr(comps), self._ptr(norm), self._ptr(grad),
-                                                         cells.data_ptr(), chunk), "arb_query_grid_host")
-            else:
-                _lib.check(self._lib.arb_query_host(ctypes.byref(self._cgeom), self._table.data_ptr(), self._mode_code,
-                                                    work.ctypes.data, n, work.shape[1], self._ptr(comps),
-                                                    self._ptr(norm), self._ptr(grad), cells.data_ptr(), chunk),
-                           "arb_query_host")
+            bounds = [n * i // nrep for i in range(nrep + 1)]
+            futs = [self._pool().submit(reps[i]._host_rows, work, bounds[i], bounds[i + 1], comps, norm, grad)
+                    for i in range(nrep)]
+            cells = [f.result() for f in futs]
         if not direct:
             bad = np.isnan(work[:, :d]).any(axis=1) & ~np.isnan(np.asarray(query[:, :d], dtype=np.float64)).any(axis=1)
             if bad.any():
                 query[np.where(bad)[0]] = np.nan                 # A.py:350-355 (raises for int arrays, as there)
         self._last_cells = cells
         return tuple(None if t is None else t.numpy() for t in (comps, norm, grad))
+
+    _MULTI_MIN_ROWS = 1 << 17   # rows per device below which fanning a batch out costs more than it saves
+
+    def _pool(self):
+        pool = getattr(self, "_thread_pool", None)
+        if pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            pool = self._thread_pool = ThreadPoolExecutor(max_workers=len(self._replicas),
+                                                          thread_name_prefix="arb-replica")
+        return pool
 
     _SMALL_ROWS = 8192        # same threshold as SMALL_ROWS in csrc/arb_host.cu
     _PIN_LIMIT_BYTES = 4 << 30
@@ -494,15 +585,20 @@ class _CubicInterpolator:
         grad = np.empty((n, d)) if mode != "vector" else None
         cells = np.empty(n, dtype=np.int64)
         ptr = lambda a: None if a is None else a.ctypes.data
-        if torch.cuda.current_device() != self._device.index:
+        prev = torch.cuda.current_device()
+        if prev != self._device.index:                           # latency path: no context manager unless needed
             torch.cuda.set_device(self._device)
-        args = (ctypes.byref(self._cgeom), self._planes.data_ptr() if self._table is None else self._table.data_ptr())
-        if self._table is None:
-            rc = self._lib.arb_query_grid_host(*args, self._pitch, self._mode_code, work.ctypes.data, n, work.shape[1],
-                                               ptr(comps), ptr(norm), ptr(grad), cells.ctypes.data, 0)
-        else:
-            rc = self._lib.arb_query_host(*args, self._mode_code, work.ctypes.data, n, work.shape[1],
-                                          ptr(comps), ptr(norm), ptr(grad), cells.ctypes.data, 0)
+        try:
+            args = (ctypes.byref(self._cgeom), self._planes.data_ptr() if self._table is None else self._table.data_ptr())
+            if self._table is None:
+                rc = self._lib.arb_query_grid_host(*args, self._pitch, self._mode_code, work.ctypes.data, n, work.shape[1],
+                                                   ptr(comps), ptr(norm), ptr(grad), cells.ctypes.data, 0)
+            else:
+                rc = self._lib.arb_query_host(*args, self._mode_code, work.ctypes.data, n, work.shape[1],
+                                              ptr(comps), ptr(norm), ptr(grad), cells.ctypes.data, 0)
+        finally:
+            if prev != self._device.index:
+                torch.cuda.set_device(prev)                      # the caller's current device is not ours to change
         _lib.check(rc, "arb_query_host")
         if not direct:
             bad = np.isnan(work[:, :d]).any(axis=1) & ~np.isnan(np.asarray(query[:, :d], dtype=np.float64)).any(axis=1)

@@ -13,8 +13,9 @@ owner is the reference's cell location, ``floor((t - tIntMin) / ht)`` (A.py:1081
 """
 from __future__ import annotations
 
-from typing import Callable, List, Sequence, Tuple
+from typing import Callable, List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
 
@@ -54,10 +55,15 @@ def owner_ranks(coord_slow: torch.Tensor, int_min: float, int_max: float, h: flo
     return torch.where(valid, owner, torch.zeros_like(owner))
 
 
-def route_rows(rows: torch.Tensor, owner: torch.Tensor, group=None):
+def _no_mark(name: str) -> None:
+    pass
+
+
+def route_rows(rows: torch.Tensor, owner: torch.Tensor, group=None, mark: Callable[[str], None] = _no_mark):
     """Send every row of ``rows`` to rank ``owner[row]`` (one all-to-all of the counts, one of the rows).
     Returns ``(received, order, send_split, recv_split)``: ``order`` sorts the caller's rows by owner (what was
-    sent is ``rows[order]``), the splits are what :func:`return_rows` needs to send answers back."""
+    sent is ``rows[order]``), the splits are what :func:`return_rows` needs to send answers back.
+    ``mark(name)`` is called at the end of each phase (sort / counts / permute / alltoall) for profiling."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
     # owners are tiny integers: a 16-bit stable radix sort is two passes instead of eight, the per-owner
@@ -66,39 +72,48 @@ def route_rows(rows: torch.Tensor, owner: torch.Tensor, group=None):
     skey, order = torch.sort(owner.to(torch.int16), stable=True)
     bounds = torch.searchsorted(skey, torch.arange(world + 1, dtype=torch.int16, device=owner.device))
     send_counts = (bounds[1:] - bounds[:-1]).to(torch.int64)
+    mark("sort")
     recv_counts = torch.empty_like(send_counts)
     dist.all_to_all_single(recv_counts, send_counts, group=group)
     send_split = send_counts.tolist()
     recv_split = recv_counts.tolist()
+    mark("counts")
     from ._lib import permute_rows
     sendbuf = permute_rows(rows, order)
+    mark("permute")
     recvbuf = rows.new_empty((sum(recv_split), rows.shape[1]))
     dist.all_to_all_single(recvbuf, sendbuf, recv_split, send_split, group=group)
+    mark("alltoall")
     return recvbuf, order, send_split, recv_split
 
 
-def return_rows(res: torch.Tensor, order: torch.Tensor, send_split, recv_split, group=None) -> torch.Tensor:
+def return_rows(res: torch.Tensor, order: torch.Tensor, send_split, recv_split, group=None,
+                mark: Callable[[str], None] = _no_mark) -> torch.Tensor:
     """Inverse of :func:`route_rows` for per-row results: ``res`` (one row per received row) travels back and is
     put into the caller's original row order."""
     import torch.distributed as dist
     from ._lib import permute_rows
     back = res.new_empty((sum(send_split), res.shape[1]))
     dist.all_to_all_single(back, res.contiguous(), send_split, recv_split, group=group)
-    return permute_rows(back, order, scatter=True)
+    mark("alltoall_back")
+    out = permute_rows(back, order, scatter=True)
+    mark("scatter")
+    return out
 
 
 def exchange_and_query(q: torch.Tensor, owner: torch.Tensor, evaluate: Callable[[torch.Tensor], torch.Tensor],
-                       out_cols: int, group=None) -> torch.Tensor:
+                       out_cols: int, group=None, mark: Callable[[str], None] = _no_mark) -> torch.Tensor:
     """Route rows of ``q`` to their owners, evaluate there, route the results back.
 
     ``evaluate(rows) -> (len(rows), out_cols)`` runs on the receiving rank (the local slab's query
-    kernel).  Returns ``(len(q), out_cols)`` in the caller's row order.  Two all-to-alls, none of
-    them inside the query kernel."""
-    recvbuf, order, send_split, recv_split = route_rows(q, owner, group)
+    kernel).  Returns ``(len(q), out_cols)`` in the caller's row order.  Two all-to-alls of rows (plus one of
+    the per-rank counts), none of them inside the query kernel."""
+    recvbuf, order, send_split, recv_split = route_rows(q, owner, group, mark)
     res = evaluate(recvbuf)
+    mark("kernel")
     if res.shape != (recvbuf.shape[0], out_cols):
         raise ValueError(f"evaluate returned {tuple(res.shape)}, expected {(recvbuf.shape[0], out_cols)}")
-    return return_rows(res, order, send_split, recv_split, group)
+    return return_rows(res, order, send_split, recv_split, group, mark)
 
 
 def push_sharded(pos: torch.Tensor, vel: torch.Tensor, nsteps: int, owner_of: Callable[[torch.Tensor], torch.Tensor],
@@ -197,6 +212,33 @@ def broadcast_ingested(field, d: int, src: int = 0, device=None, group=None):
     return out
 
 
+class ReplicatedInterp:
+    """One process per GPU, the coefficient table replicated: rank ``src`` holds the field, it is ingested once, the
+    dense planes are broadcast (NCCL over NVLink) and every rank builds its own table (cheaper than moving 8-33 GB of
+    coefficients).  ``Query`` takes THIS rank's rows -- numpy or CUDA -- and is exactly the single-GPU call: the
+    reference's return shapes, in-place NaN rows and ``queryInds`` (A.py:177-211, 350-355, 368-370), no collective.
+    Every other attribute is the local interpolator's."""
+
+    def __init__(self, cls, field, *args, group=None, src: int = 0, **kwargs):
+        import torch.distributed as dist
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        device = kwargs.get("device")
+        if device is None and torch.cuda.is_available():
+            device = torch.device("cuda", torch.cuda.current_device())
+        kwargs["device"] = device
+        full = broadcast_ingested(field, cls._d, src=src, device=device, group=group)
+        self.local = cls(full, *args, **kwargs)
+
+    def Query(self, q):
+        return self.local.Query(q)
+
+    def __getattr__(self, name):
+        if name == "local":
+            raise AttributeError(name)
+        return getattr(self.local, name)
+
+
 class SlabShardedInterp:
     """A tricubic/quadcubic whose coefficient table is sharded over the ranks by slowest-axis
     slabs (config 5: 96^3 x 64 'both' = 402 GB over 8 GPUs).  ``Query`` takes this rank's rows and
@@ -222,24 +264,81 @@ class SlabShardedInterp:
         g = self.local._geo
         self._slow = (g.int_min[d - 1], g.int_max[d - 1], g.h[d - 1])
 
-    def Query(self, q: torch.Tensor):
-        """``q``: CUDA tensor (N, >=d) of this rank.  Returns what the local class returns, as CUDA
-        tensors in the caller's row order."""
+    def Query(self, q, timing: Optional[dict] = None):
+        """Drop-in range query over the sharded table (rQuery1/2/3, A.py:1064-1258 / 344-521): ``q`` holds THIS rank's
+        rows, (N, >=d), as a numpy array or a CUDA tensor; returns what the unsharded class returns for them (numpy in ->
+        numpy out, tensor in -> CUDA tensors), in the caller's row order.  Side effects as in the reference: rows with a
+        coordinate outside the volume are overwritten with NaN in the caller's array across all columns
+        (A.py:1069-1076), and ``queryInds`` holds the GLOBAL cell index of every row, ``nc`` for NaN rows
+        (A.py:1088-1090).  Collective: every rank of the group must call it (an empty batch is fine).
+        ``timing``: optional dict that accumulates the milliseconds of each phase -- owner / sort / counts / permute /
+        alltoall / kernel / alltoall_back / scatter / unpack (CUDA events on the current stream)."""
         d, mode = self.d, self.local._mode
-        owner = owner_ranks(q[:, d - 1], *self._slow, self.slabs)
+        dev = self.local._device
+        host = isinstance(q, np.ndarray)
+        if host:
+            if q.ndim != 2 or q.shape[1] < d:
+                raise IndexError(f"query must be (N, >={d})")
+            coords = torch.from_numpy(np.ascontiguousarray(q[:, :d], dtype=np.float64)).to(dev)
+        else:
+            if q.dim() != 2 or q.shape[1] < d:
+                raise IndexError(f"query must be (N, >={d})")
+            coords = q[:, :d].to(device=dev, dtype=torch.float64).contiguous()
+        ev = []
+
+        def mark(name):
+            if timing is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(torch.cuda.current_stream(dev))
+                ev.append((name, e))
+
+        mark("start")
+        g = self.local._geo
+        lo = torch.tensor(g.int_min, dtype=torch.float64, device=dev)
+        hi = torch.tensor(g.int_max, dtype=torch.float64, device=dev)
+        outside = ((coords < lo) | (coords > hi)).any(dim=1)                    # A.py:1069-1076
+        owner = owner_ranks(coords[:, d - 1], *self._slow, self.slabs)
+        mark("owner")
         widths = {"vector": (3,), "norm": (1, d), "both": (3, 1, d)}[mode]
 
         def evaluate(rows):
-            res = self.local.Query(rows[:, :d].contiguous())
+            res = self.local.Query(rows)
             res = res if isinstance(res, tuple) else (res,)
-            return torch.cat(res, dim=1)
+            cells = self.local._last_cells.view(torch.float64).unsqueeze(1)     # int64 bits ride along exactly
+            return torch.cat(list(res) + [cells], dim=1)
 
-        flat = exchange_and_query(q[:, :d].contiguous(), owner, evaluate, sum(widths), self.group)
+        flat = exchange_and_query(coords, owner, evaluate, sum(widths) + 1, self.group, mark)
         outs, col = [], 0
         for w in widths:
-            outs.append(flat[:, col:col + w])
+            outs.append(flat[:, col:col + w].contiguous())
             col += w
+        self._last_cells = flat[:, col].contiguous().view(torch.int64)
+        if host:
+            bad = outside.cpu().numpy()
+            if bad.any():
+                q[np.where(bad)[0]] = np.nan                                    # raises for int arrays, as A.py:1069 does
+            outs = [o.cpu().numpy() for o in outs]
+        elif bool(outside.any()):
+            q[outside.to(q.device)] = float("nan")
+        mark("unpack")
+        if timing is not None:
+            torch.cuda.synchronize(dev)
+            for (_, e0), (name, e1) in zip(ev[:-1], ev[1:]):
+                timing[name + "_ms"] = timing.get(name + "_ms", 0.0) + e0.elapsed_time(e1)
+            timing["total_ms"] = timing.get("total_ms", 0.0) + ev[0][1].elapsed_time(ev[-1][1])
         return outs[0] if len(outs) == 1 else tuple(outs)
+
+    @property
+    def queryInds(self):
+        """Global cell index of every row of the last ``Query`` on this rank; ``nc`` for NaN rows (A.py:1088-1090)."""
+        c = getattr(self, "_last_cells", None)
+        if c is None:
+            raise AttributeError("queryInds is set by the first range query")
+        return c.cpu().numpy()
+
+    @property
+    def nc(self):
+        return self.local.nc
 
     def push(self, pos: torch.Tensor, vel: torch.Tensor, dt, nsteps, kappa, gravity=None) -> int:
         """Fused query + push (``tricubic.push`` / ``quadcubic.push``) over the sharded table: this rank's particles

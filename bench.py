@@ -9,16 +9,18 @@ A "step" is one pass of the query kernel over one batch of Q queries.
     python bench.py [--gpus N] [--steps K] [--warmup W] [--mode norm|vector|both] [--impl reference]
 
 Prints ONE JSON line (rank 0).  Keys follow the driver contract; `roofline`, `cpu_baseline`, `e2e`,
-`clocks` and `gpu_launches` are described in DESIGN.md "Measurement".
+`clocks`, `gpu_launches`, `other_modes` and (N > 1) `sharded` are described in DESIGN.md "Measurement".
 """
 import argparse
 import ctypes
+import importlib.util
 import json
 import os
 import subprocess
 import sys
 import threading
 import time
+import warnings
 
 import numpy as np
 
@@ -44,16 +46,24 @@ def parse():
     ap.add_argument("--e2e-queries", type=int, default=1 << 24, help="queries per step for the host-buffer leg")
     ap.add_argument("--variant", type=int, default=None, help="query-kernel variant (arb_set_query_variant)")
     ap.add_argument("--sweep", default="", help="comma list of variants to time (prints a table to stderr)")
-    ap.add_argument("--cpu-sample", type=int, default=1_000_000)
+    ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="rows of the in-bench oracle parity check")
+    ap.add_argument("--ref-sample", type=int, default=200_000, help="rows of the unmodified-reference cpu_baseline")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--other-modes", action="store_true", help="(default at N=1) also time vector/both, device-resident")
-    ap.add_argument("--no-other-modes", action="store_true", help="skip the vector/both lines")
+    ap.add_argument("--no-other-modes", action="store_true", help="skip the vector/both/quadcubic lines")
+    ap.add_argument("--no-sharded", action="store_true", help="(N > 1) skip the slab-sharded config-5 object")
+    ap.add_argument("--sharded-particles", type=int, default=1 << 22, help="trajectory queries per rank and step")
+    ap.add_argument("--force-port", action="store_true", help="CPU arm: use the numpy port even if the reference is staged")
     return ap.parse_args()
 
 
+def workload_string(grid, mode):
+    """The same string in both arms (the driver compares `config.workload` to decide `same_config`)."""
+    return f"tricubic {grid}^3 analytic vector field, mode={mode} (value+gradient), uniform random in-volume queries"
+
+
 # ----------------------------------------------------------------------------------------
-# synthetic analytic field
+# synthetic analytic fields (SURVEY 8d configs 3 and 5)
 # ----------------------------------------------------------------------------------------
 def analytic_planes(torch, n, device):
     ax = torch.linspace(-1.0, 1.0, n, dtype=torch.float64, device=device)
@@ -67,6 +77,27 @@ def analytic_planes(torch, n, device):
 def analytic_field_rows(torch, n, device):
     ax, (X, Y, Z), (bx, by, bz) = analytic_planes(torch, n, device)
     return ax, torch.stack([t.reshape(-1) for t in (X, Y, Z, bx, by, bz)], dim=1)
+
+
+def analytic_field_rows_numpy(n):
+    ax = np.linspace(-1.0, 1.0, n)
+    Z, Y, X = np.meshgrid(ax, ax, ax, indexing="ij")
+    bx = np.sin(2 * np.pi * X) * np.cos(np.pi * Y) * np.exp(-Z)
+    by = X * X * Y + Z
+    bz = np.cos(X + Y + Z)
+    return np.stack([t.ravel() for t in (X, Y, Z, bx, by, bz)], axis=1)
+
+
+def field4_rows(torch, shape, device):
+    """SURVEY 4 / 8d config 5 seed field: every component non-trivial in all four variables; By carries an explicit
+    x*y*z*t monomial, so the A.py:860 rank-16 term is excited."""
+    axes = [torch.linspace(-1.0, 1.0, m, dtype=torch.float64, device=device) for m in shape[:3]]
+    axes.append(torch.linspace(0.0, 1.0, shape[3], dtype=torch.float64, device=device))
+    T, Z, Y, X = [g.reshape(-1) for g in torch.meshgrid(*reversed(axes), indexing="ij")]
+    bx = torch.sin(2 * X) * torch.cos(3 * Y) * torch.exp(-Z) * torch.cos(2 * T)
+    by = X * X * Y + Z * T + 0.3 * X * Y * Z * T
+    bz = torch.cos(X + Y + Z + T)
+    return axes, torch.stack([X, Y, Z, T, bx, by, bz], dim=1)
 
 
 class ClockSampler(threading.Thread):
@@ -144,22 +175,30 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm), "source": self.source}
 
 
-def bind_to_gpu_numa_node(gpu_index):
-    """Pin this rank to the CPU cores NVML reports as local to its GPU, so the pinned host buffers of the
-    end-to-end leg are allocated on (and copied from) the NUMA node the GPU's PCIe root hangs off."""
+def bind_to_gpu_cores(gpu_index, local_rank, local_world):
+    """Give this rank its OWN cores: the CPUs NVML reports as local to its GPU (the NUMA node its PCIe root hangs
+    off), cut into equal shares among the ranks of the box that report the same set (on a single-node VM every GPU
+    reports all cores -- eight ranks bound to the same 32 cores is no binding at all).  The staging threads of the
+    host-buffer path and the pinned allocations then stay on this rank's cores."""
     try:
         import pynvml
         pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
-        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
-        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1]
-        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
-        if allowed:
-            os.sched_setaffinity(0, allowed)
-            return f"{len(allowed)} cores [{allowed[0]}..{allowed[-1]}]"
-    except Exception:
-        return None
-    return None
+        allowed_now = sorted(os.sched_getaffinity(0))
+
+        def local_cpus(idx):
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+            return tuple(sorted(cpus & set(allowed_now))) or tuple(allowed_now)
+
+        mine = local_cpus(gpu_index)
+        sharers = [r for r in range(local_world) if local_cpus(r) == mine]      # local rank r drives GPU r
+        k, n = sharers.index(local_rank), len(sharers)
+        share = list(mine[len(mine) * k // n: len(mine) * (k + 1) // n]) or list(mine)
+        os.sched_setaffinity(0, share)
+        return f"{len(share)} cores [{share[0]}..{share[-1]}] of {len(mine)} GPU-local, {n} ranks share them"
+    except Exception as e:                                  # noqa: BLE001 -- binding is best effort
+        return f"unbound ({type(e).__name__})"
 
 
 def measured_peak():
@@ -170,18 +209,38 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(mode):
-    """DRAM bytes per query from the committed ncu --set full capture (profiles/roofline_traffic.json)."""
+def ncu_traffic(key):
+    """DRAM bytes per query from the committed ncu --set full captures (profiles/roofline_traffic.json)."""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            return json.load(f).get(mode)
+            return json.load(f).get(key)
     except Exception:
         return None
 
 
 # ----------------------------------------------------------------------------------------
-# CPU arm: the numpy oracle (port of the reference) on the host cores
+# CPU arm.  Preferred: the UNMODIFIED reference module, staged by oracle/stage_reference.py under oracle/_ref
+# (or found in baseline/_ref / $ARB_REFERENCE); fallback: the numpy port in oracle/arb_oracle.py.
 # ----------------------------------------------------------------------------------------
+def load_reference_module():
+    """The reference's own ARBInterp.py as a module object, or None.  Loaded by file path under a private name:
+    the repository root holds drop-in packages of the same names (ARBInterp/, ARBTools/) that must not shadow it."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        from stage_reference import module_path
+    finally:
+        sys.path.pop(0)
+    roots = [os.environ.get("ARB_REFERENCE"), os.path.join(ROOT, "oracle", "_ref"), os.path.join(ROOT, "baseline", "_ref")]
+    for root in roots:
+        path = root and module_path(root)
+        if path:
+            spec = importlib.util.spec_from_file_location("arb_reference_unmodified", path)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            return mod, path
+    return None, None
+
+
 def make_cpu_oracle(n, mode):
     from oracle.arb_oracle import OracleInterp
     ax = np.linspace(-1.0, 1.0, n)
@@ -197,75 +256,112 @@ def make_cpu_oracle(n, mode):
     return OracleInterp.from_planes([ax, ax, ax], vals, mode)
 
 
-def cpu_queries(ora, count, seed):
+def uniform_in_volume(lo, hi, count, seed):
     rng = np.random.default_rng(seed)
-    g = ora.geo
-    q = np.empty((count, 3))
-    for a in range(3):
-        q[:, a] = g.int_min[a] + rng.uniform(0, 1, count) * (g.int_max[a] - g.int_min[a]) * (1 - 1e-12)
+    q = np.empty((count, len(lo)))
+    for a in range(len(lo)):
+        q[:, a] = lo[a] + rng.uniform(0, 1, count) * (hi[a] - lo[a]) * (1 - 1e-12)
     return q
 
 
-def cpu_warm_rate(ora, q, chunk=100_000):
-    """Warm rate: coefficients of the touched cells are filled first (the reference's lazy fill,
-    A.py:376-377), then the timed pass is the reference's rQuery arithmetic only."""
-    t0 = time.perf_counter()
-    for lo in range(0, len(q), chunk):
-        ora.query(q[lo:lo + chunk].copy())
-    cpu_warm_rate.cold = len(q) / (time.perf_counter() - t0)      # first pass: includes the lazy coefficient fill
-    t0 = time.perf_counter()
-    for lo in range(0, len(q), chunk):
-        ora.query(q[lo:lo + chunk].copy())
-    return len(q) / (time.perf_counter() - t0)
+def cpu_queries(ora, count, seed):
+    return uniform_in_volume(ora.geo.int_min, ora.geo.int_max, count, seed)
 
 
-_PARENT_ORACLE = None
+class CpuArm:
+    """One CPU implementation of the path behind a common face: `query(q)` (range query, NaN-masks q in place)."""
+
+    def __init__(self, n, mode, force_port=False):
+        self.n, self.mode = n, mode
+        mod, path = (None, None) if force_port else load_reference_module()
+        if mod is not None:
+            self.kind = "reference"
+            self.what = "unmodified reference module " + os.path.relpath(path, ROOT)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                self.obj = mod.tricubic(analytic_field_rows_numpy(n), "quiet", mode=mode)
+            self.lo = [self.obj.xIntMin, self.obj.yIntMin, self.obj.zIntMin]
+            self.hi = [self.obj.xIntMax, self.obj.yIntMax, self.obj.zIntMax]
+        else:
+            self.kind = "port"
+            self.what = "numpy port oracle/arb_oracle.py (bit-equal to the reference on tests/golden)"
+            self.obj = make_cpu_oracle(n, mode)
+            self.lo, self.hi = self.obj.geo.int_min, self.obj.geo.int_max
+
+    def query(self, q):
+        if self.kind == "reference":
+            with warnings.catch_warnings():                   # NaN -> int cast warning at A.py:370
+                warnings.simplefilter("ignore")
+                return self.obj.Query(q)
+        return self.obj.query(q)
+
+    def passes(self, q, chunk):
+        t0 = time.perf_counter()
+        for lo in range(0, len(q), chunk):
+            self.query(q[lo:lo + chunk].copy())
+        return len(q) / (time.perf_counter() - t0)
+
+
+_PARENT_ARM = None
 
 
 def _worker(args):
-    count, seed, steps, warmup = args
-    ora = _PARENT_ORACLE                               # forked: planes shared copy-on-write
-    q = cpu_queries(ora, count, seed)
-    for lo in range(0, count, 100_000):
-        ora.query(q[lo:lo + 100_000].copy())          # fill
+    idx, per, seed, steps, warmup, chunk = args
+    arm = _PARENT_ARM                                  # forked: field and filled coefficients shared copy-on-write
+    q = uniform_in_volume(arm.lo, arm.hi, per, seed)
     times = []
     for s in range(warmup + steps):
         t0 = time.perf_counter()
-        for lo in range(0, count, 100_000):
-            ora.query(q[lo:lo + 100_000].copy())
+        for lo in range(0, per, chunk):
+            arm.query(q[lo:lo + chunk].copy())
         times.append(time.perf_counter() - t0)
     return times[warmup:]
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (numpy port in oracle/, the
-    reference itself being pure Python that cannot travel to the GPU box) on all host cores."""
+    """--impl reference: the reference's CPU implementation of the path on all host cores -- the unmodified module
+    when it is staged (kind "reference"), else the numpy port (kind "port").  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
-    global _PARENT_ORACLE
+    global _PARENT_ARM
     os.environ["OMP_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = "1"
     cores = len(os.sched_getaffinity(0))
     procs = max(1, min(cores, 256))
-    per = max(20_000, min(200_000, args.cpu_sample // 5))
     n = args.grid
     t0 = time.perf_counter()
-    _PARENT_ORACLE = make_cpu_oracle(n, args.mode)
+    arm = CpuArm(n, args.mode, args.force_port)
+    t_ctor = time.perf_counter() - t0
+    if arm.kind == "reference":
+        # the reference fills coefficients lazily, one Python call per cell (~2e4 cells/s, A.py:376-377): the parent
+        # fills the cells of every worker's sample once (bounded to ~20 s), the workers then time warm passes
+        per = max(5_000, min(50_000, 400_000 // procs))
+        chunk = 50_000
+    else:
+        per = max(20_000, min(200_000, args.cpu_sample // 5))
+        chunk = 100_000
+    seeds = [100 + i for i in range(procs)]
+    t1 = time.perf_counter()
+    for sd in seeds:                                    # lazy fill in the parent (cold pass, untimed by the metric)
+        arm.query(uniform_in_volume(arm.lo, arm.hi, per, sd))
+    cold = procs * per / (time.perf_counter() - t1)
+    _PARENT_ARM = arm
     with mp.get_context("fork").Pool(procs) as pool:
-        res = pool.map(_worker, [(per, 100 + i, args.steps, args.warmup) for i in range(procs)])
+        res = pool.map(_worker, [(i, per, seeds[i], args.steps, args.warmup, chunk) for i in range(procs)])
     wall = time.perf_counter() - t0
     per_step = np.max(np.array(res), axis=0)                     # slowest worker per step
     total_t = float(per_step.sum())
     value = procs * per * args.steps / total_t
-    sample = f"{procs} forked workers x {per} warm queries/step on a {n}^3 grid (steps={args.steps}); wall {wall:.1f}s"
+    sample = (f"{arm.what}: {procs} forked workers x {per} warm queries/step on a {n}^3 grid (steps={args.steps}); "
+              f"constructor {t_ctor:.1f}s, single-process cold pass incl. lazy coefficient fill {cold:.3g} q/s; wall {wall:.1f}s")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"tricubic {args.grid}^3 analytic vector field, mode={args.mode}, uniform random in-volume queries",
-                   "cpu_grid": n},
-        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": procs, "kind": "port", "sample": sample},
+        "config": {"workload": workload_string(args.grid, args.mode), "cpu_grid": n},
+        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": procs, "kind": arm.kind, "sample": sample,
+                         "cold_value": cold},
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -315,12 +411,276 @@ def alloc_outputs(torch, mode, d, n, device):
 
 
 def uniform_queries(torch, obj, n, seed, device):
+    d = obj._d
     g = torch.Generator(device=device)
     g.manual_seed(seed)
-    q = torch.rand(n, 3, generator=g, dtype=torch.float64, device=device)
-    lo = torch.tensor([obj.xIntMin, obj.yIntMin, obj.zIntMin], dtype=torch.float64, device=device)
-    hi = torch.tensor([obj.xIntMax, obj.yIntMax, obj.zIntMax], dtype=torch.float64, device=device)
+    q = torch.rand(n, d, generator=g, dtype=torch.float64, device=device)
+    lo = torch.tensor(obj._geo.int_min, dtype=torch.float64, device=device)
+    hi = torch.tensor(obj._geo.int_max, dtype=torch.float64, device=device)
     return lo + q * (hi - lo) * (1 - 1e-12)
+
+
+def scaled_error(got, ref, d, h, scale):
+    """max |got - ref| / max(|ref|, S) over every output (S/h for gradient columns); NaN masks must agree."""
+    got = got if isinstance(got, tuple) else (got,)
+    ref = ref if isinstance(ref, tuple) else (ref,)
+    worst = 0.0
+    for a, b in zip(got, ref):
+        a, b = np.asarray(a), np.asarray(b)
+        if a.shape != b.shape or not np.array_equal(np.isnan(a), np.isnan(b)):
+            return float("inf")
+        is_grad = b.shape[1] == d and a is got[-1] and len(got) > 1
+        sc = scale / np.asarray(h, dtype=np.float64)[None, :] if is_grad else scale
+        sc = np.broadcast_to(sc, b.shape)
+        ok = ~np.isnan(b)
+        if ok.any():
+            worst = max(worst, float(np.max(np.abs(a[ok] - b[ok]) / np.maximum(np.abs(b[ok]), sc[ok]))))
+    return worst
+
+
+def oracle_sample_check(obj, axes, values, mode, d, nrows, seed, scalar=False, chunk=25_000):
+    """In-run guard: `nrows` uniformly random in-volume queries through the GPU object and through the numpy oracle
+    (compact coefficient store) built on the SAME planes; indices exact, values within 1e-12 scaled."""
+    from oracle.arb_oracle import OracleInterp
+    ora = OracleInterp.from_planes(axes, values, mode, scalar_input=scalar)
+    q = cpu_queries(ora, nrows, seed)
+    scale = max(float(np.abs(v).max()) for v in values.values())
+    worst, idx_ok, finite = 0.0, True, True
+    for lo in range(0, nrows, chunk):
+        qc = q[lo:lo + chunk]
+        ref = ora.query(qc.copy())
+        got = obj.Query(qc.copy())
+        worst = max(worst, scaled_error(got, ref, d, ora.geo.h, scale))
+        idx_ok &= bool(np.array_equal(obj.queryInds, ora.query_inds))
+        finite &= all(bool(np.isfinite(np.asarray(g)).all()) for g in (got if isinstance(got, tuple) else (got,)))
+    return {"n": int(nrows), "max_scaled_err": worst, "tolerance": 1e-12, "indices_equal": idx_ok, "finite": finite,
+            "ok": bool(idx_ok and finite and worst <= 1e-12)}
+
+
+def link_ceiling(torch, dist, device, world, mb=256, reps=6):
+    """What the host<->device links of this box can move when all `world` ranks copy at once: every rank runs
+    `reps` pinned H2D copies and `reps` pinned D2H copies of `mb` MiB concurrently on two streams (cudaMemcpyAsync),
+    between barriers; GB/s = bytes of all ranks / slowest rank's time.  Also each direction alone."""
+    n = mb << 20
+    hin = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    hout = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    din = torch.empty(n, dtype=torch.uint8, device=device)
+    dout = torch.empty(n, dtype=torch.uint8, device=device)
+    s1, s2 = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    out = {}
+    for name, do_in, do_out in (("h2d", True, False), ("d2h", False, True), ("bidir", True, True)):
+        for timed in (False, True):
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps if timed else 1):
+                if do_in:
+                    with torch.cuda.stream(s1):
+                        din.copy_(hin, non_blocking=True)
+                if do_out:
+                    with torch.cuda.stream(s2):
+                        hout.copy_(dout, non_blocking=True)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        out[name + "_gbs"] = world * reps * n * (int(do_in) + int(do_out)) / dt / 1e9
+    return out
+
+
+def time_e2e(torch, dist, device, obj, qnp, steps, warmup, world):
+    """`steps` calls of the public API on a host batch; wall clock between barriers + syncs, max over ranks."""
+    for _ in range(max(1, min(warmup, 2))):
+        res = obj.Query(qnp)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        res = obj.Query(qnp)
+    torch.cuda.synchronize()
+    te = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([te], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        te = float(t.item())
+    res = res if isinstance(res, tuple) else (res,)
+    d2h = sum(r.nbytes for r in res if r is not None)
+    return world * len(qnp) * steps / te, int(qnp.nbytes), int(d2h)
+
+
+# ----------------------------------------------------------------------------------------
+# N > 1: BASELINE configs[4] -- quadcubic 'both', coefficient table t-slab-sharded with halos, trajectory-like
+# queries routed to the owning rank -- with in-run parity (VERDICT r01 item 1)
+# ----------------------------------------------------------------------------------------
+def run_sharded(torch, dist, args, rank, world, device):
+    from arbinterp_b200 import quadcubic
+    from arbinterp_b200.sharding import SlabShardedInterp
+    from oracle.arb_oracle import OracleInterp
+    out = {}
+    rng = np.random.default_rng(5150)
+
+    # ---- (i) small 4-D VECTOR field with an xyzt monomial in every component: routed == unsharded, bit for bit
+    small = (14, 12, 11, 3 * world + 5)
+    ax = [np.linspace(-1, 1, small[0]), np.linspace(-.5, .5, small[1]), np.linspace(0, 2, small[2]),
+          np.linspace(0, 1, small[3])]
+    T, Z, Y, X = [a.ravel() for a in np.meshgrid(ax[3], ax[2], ax[1], ax[0], indexing="ij")]
+    xyzt = X * Y * Z * T
+    fs = np.stack([X, Y, Z, T, np.sin(2 * X) * np.cos(3 * Y) * np.exp(-Z) * np.cos(2 * T) + 0.7 * xyzt,
+                   X * X * Y + Z * T - 0.4 * xyzt, np.cos(X + Y + Z + T) + 1.1 * xyzt], axis=1)
+    whole = quadcubic(fs.copy(), "quiet", mode="both", device=device)
+    sh = SlabShardedInterp(quadcubic, fs if rank == 0 else None, "quiet", mode="both", device=device)
+    lo_s = np.array([a[1] for a in ax]); hi_s = np.array([a[-2] for a in ax])
+    qs = lo_s + rng.uniform(-0.03, 1.03, (20000, 4)) * (hi_s - lo_s)          # ~11 % of the rows leave the volume
+    qs[::97, 1] = np.nan
+    mine = np.ascontiguousarray(qs[rank::world])
+    q_ref, q_got = mine.copy(), mine.copy()
+    ref = whole.Query(q_ref)
+    got = sh.Query(q_got)
+    same = all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got, ref))
+    same &= bool(np.array_equal(sh.queryInds, whole.queryInds)) and bool(np.array_equal(q_got, q_ref, equal_nan=True))
+    flag = torch.tensor([int(same)], dtype=torch.int64, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out["routed_equals_unsharded"] = bool(flag.item())
+    out["small_check"] = {"grid": list(small), "mode": "both", "rows_per_rank": int(len(mine)),
+                          "what": "outputs, queryInds and the in-place NaN rows of SlabShardedInterp.Query(numpy) are "
+                                  "bit-identical to the unsharded quadcubic on the same rank; every component has an "
+                                  "x*y*z*t term (A.py:860 rank-16 term excited)"}
+    del whole, sh
+    torch.cuda.empty_cache()
+
+    # ---- config 5 scaled to the world: 96^3 x nt 'both', 8 cell layers per rank (61 layers = the full 96^3 x 64 at 8)
+    layers = min(61, 8 * world)
+    shape = (96, 96, 96, layers + 3)
+    rows = None
+    crop = None
+    if rank == 0:
+        axes_t, rows = field4_rows(torch, shape, device)
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    obj = SlabShardedInterp(quadcubic, rows, "quiet", mode="both", device=device)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t_build = time.perf_counter() - t0
+    loc = obj.local
+    g = loc._geo
+    if rank == 0:
+        # cropped sub-field straddling the rank 0 / rank 1 slab boundary (coefficients are local to the 4^4 neighbourhood)
+        hi0 = obj.slabs[0][1]
+        win = [(40, 52), (38, 50), (44, 56), (hi0 - 3, hi0 + 5)]               # grid-point windows x, y, z, t
+        r5 = rows.reshape(shape[3], shape[2], shape[1], shape[0], 7)
+        crop = r5[win[3][0]:win[3][1], win[2][0]:win[2][1], win[1][0]:win[1][1], win[0][0]:win[0][1]].reshape(-1, 7).cpu().numpy()
+        full_scale = float(rows[:, 4:].abs().max())
+    del rows
+    torch.cuda.empty_cache()
+    table_gb = torch.tensor([loc.table.numel() * 8 / 1e9], dtype=torch.float64, device=device)
+    tb_max = table_gb.clone()
+    dist.all_reduce(table_gb)
+    dist.all_reduce(tb_max, op=dist.ReduceOp.MAX)
+
+    # ---- (ii) global cell indices against the oracle's locate() on 10^4 rows of the FULL geometry (rank 0's rows)
+    axes_np = [a.cpu().numpy() for a in g.axes]
+    lo = np.array(g.int_min); hi = np.array(g.int_max)
+    if rank == 0:
+        qi = lo + rng.uniform(-0.02, 1.02, (10000, 4)) * (hi - lo)
+        qi[::113, 2] = np.nan
+        qi[5::211, 0] = np.inf
+    else:
+        qi = np.empty((0, 4))
+    qi_in = qi.copy()
+    obj.Query(qi_in)
+    idx_ok = True
+    if rank == 0:
+        loc_ora = OracleInterp.locator(axes_np)
+        q_or = qi.copy()
+        with np.errstate(invalid="ignore"):
+            want, _ = loc_ora.locate(q_or)
+        idx_ok = bool(np.array_equal(obj.queryInds, want)) and bool(np.array_equal(qi_in, q_or, equal_nan=True))
+        out["index_check"] = {"n": 10000, "nan_rows": int((want == loc_ora.geo.nc).sum()), "nc": int(loc_ora.geo.nc)}
+    # ---- (iii) values against the oracle on the cropped sub-field
+    if rank == 0:
+        ora = OracleInterp(crop, 4, mode="both", dense=False)
+        qc = uniform_in_volume(ora.geo.int_min, ora.geo.int_max, 10000, 99)
+    else:
+        qc = np.empty((0, 4))
+    got = obj.Query(qc.copy())
+    crop_err = 0.0
+    if rank == 0:
+        ref = ora.query(qc.copy())
+        crop_err = scaled_error(got, ref, 4, ora.geo.h, full_scale)
+        out["crop_check"] = {"n": 10000, "window_points": [w[1] - w[0] for w in win], "max_scaled_err": crop_err,
+                             "tolerance": 1e-12, "t_layers_spanned": [int(hi0 - 3), int(hi0 + 2)],
+                             "owners_hit": sorted(set(int(v) for v in np.searchsorted(
+                                 [s[1] for s in obj.slabs], np.unique(obj.queryInds // (93 ** 3)), side="right")))}
+    flags = torch.tensor([int(idx_ok), int(crop_err <= 1e-12)], dtype=torch.int64, device=device)
+    dist.broadcast(flags, src=0)
+    out["global_indices_equal_oracle"] = bool(flags[0].item())
+    out["cropped_values_within_1e-12"] = bool(flags[1].item())
+
+    # ---- throughput: trajectory-like queries (P particles per rank, smooth random walk reflected into the volume,
+    # time advancing and wrapping), routed to the slab owners and back
+    n = args.sharded_particles
+    lo_t = torch.tensor(g.int_min, dtype=torch.float64, device=device)
+    hi_t = torch.tensor(g.int_max, dtype=torch.float64, device=device)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(777 + rank)
+    pos = lo_t + torch.rand(n, 4, generator=gen, dtype=torch.float64, device=device) * (hi_t - lo_t) * (1 - 1e-9)
+    vel = (torch.rand(n, 4, generator=gen, dtype=torch.float64, device=device) - 0.5) * (hi_t - lo_t) * 0.02
+    vel[:, 3] = (hi_t[3] - lo_t[3]) * 0.01
+    only_space = torch.tensor([1, 1, 1, 0], dtype=torch.float64, device=device)
+    span = (hi_t - lo_t) * (1 - 1e-9)
+    timing = {}
+    step_ms = []
+    finite = True
+    for step in range(args.warmup + args.steps):
+        pos = pos + vel + 0.002 * (hi_t - lo_t) * torch.randn(n, 4, generator=gen, dtype=torch.float64, device=device) * only_space
+        rel = torch.remainder(pos - lo_t, 2 * span)
+        rel = torch.where(rel > span, 2 * span - rel, rel)
+        rel[:, 3] = torch.remainder(pos[:, 3] - lo_t[3], span[3])
+        q = (lo_t + rel).contiguous()
+        timed = step >= args.warmup
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = obj.Query(q, timing=timing if timed else None)
+        e1.record()
+        torch.cuda.synchronize()
+        if timed:
+            step_ms.append(e0.elapsed_time(e1))
+            finite &= all(bool(torch.isfinite(r).all()) for r in res)
+    t = torch.tensor([sum(step_ms)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_s = float(t.item()) / 1e3
+    ph = torch.tensor([timing.get(k + "_ms", 0.0) for k in
+                       ("owner", "sort", "counts", "permute", "alltoall", "kernel", "alltoall_back", "scatter", "unpack")],
+                      dtype=torch.float64, device=device)
+    dist.all_reduce(ph, op=dist.ReduceOp.MAX)
+    ph = (ph / args.steps).tolist()
+    fl = torch.tensor([int(finite)], dtype=torch.int64, device=device)
+    dist.all_reduce(fl, op=dist.ReduceOp.MIN)
+    rate = world * n * args.steps / total_s
+    out.update({
+        "workload": f"quadcubic {shape[0]}x{shape[1]}x{shape[2]}x{shape[3]} analytic vector field (xyzt term), mode=both, "
+                    f"coefficient table t-slab-sharded over {world} ranks with halo planes, trajectory-like queries "
+                    f"routed to the owning rank and back (BASELINE configs[4]; {layers} of its 61 t layers)",
+        "value": rate, "unit": "queries/s", "queries_per_step_per_gpu": n, "steps": args.steps,
+        "ms_per_step": 1e3 * total_s / args.steps, "slabs": [list(s) for s in obj.slabs],
+        "table_gb_total": float(table_gb.item()), "table_gb_max_per_rank": float(tb_max.item()),
+        "construction_s": t_build, "outputs_finite": bool(fl.item()),
+        "alg_bytes_per_query": ALG_BYTES[(4, "both")],
+        "phase_ms_per_step_max_over_ranks": {
+            "kernel": ph[5], "all_to_all (counts + rows + results)": ph[2] + ph[4] + ph[6],
+            "sort + permute + scatter": ph[1] + ph[3] + ph[7], "owner + unpack": ph[0] + ph[8]},
+        "kernel_frac_of_measured_hbm": (ALG_BYTES[(4, "both")] * n / (ph[5] * 1e-3) / 1e9 / measured_peak()[0]) if ph[5] > 0 else None,
+    })
+    del obj, loc
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_b200(args):
@@ -330,10 +690,11 @@ def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     dist = None
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
-    affinity = bind_to_gpu_numa_node(local) if world > 1 else None
+    affinity = bind_to_gpu_cores(local, local, local_world) if world > 1 else None
     if world > 1:
         import torch.distributed as dist_mod
         dist_mod.init_process_group("nccl", device_id=device)
@@ -344,7 +705,6 @@ def run_b200(args):
 
     # ---- construction (untimed): rank 0 makes the field, NCCL broadcast, every rank builds its replica
     n = args.grid
-    t0 = time.perf_counter()
     rows = analytic_field_rows(torch, n, device)[1] if rank == 0 else None
     if dist is not None:
         from arbinterp_b200.sharding import broadcast_ingested
@@ -392,7 +752,6 @@ def run_b200(args):
     # ---- the coefficient-build kernel on its own (rebuilds the table in place; HBM-write roofline)
     build_info = None
     if rank == 0 and world == 1:
-        import ctypes
         lo, hi = obj._slab
         sub = obj._planes[:, lo:hi + 3].contiguous()
         npts = (ctypes.c_int64 * 4)(*([obj._geo.npts[a] for a in range(d - 1)] + [hi - lo + 3] + [1] * (4 - d)))
@@ -414,11 +773,71 @@ def run_b200(args):
                       "frac_of_measured_hbm": gb / ms * 1e3 / measured_peak()[0],
                       "cell_components_per_s": obj.nc * obj.table.shape[1] / ms * 1e3, "launches": 3}
 
-    # ---- other modes (device-resident), optional
+    # ---- end-to-end leg: public API with HOST numpy buffers, copies inside the timed region.  Headline: ordinary
+    # (pageable) numpy input, what a user of the reference has; `pinned`: the same call on page-locked input.
+    e2e = None
+    if not args.no_e2e:
+        QE = args.e2e_queries
+        q_page = q[:QE].cpu().numpy()                                     # ordinary numpy array
+        qh = torch.empty(QE, 3, dtype=torch.float64, pin_memory=True)
+        qh.copy_(q[:QE])
+        v_page, h2d, d2h = time_e2e(torch, dist, device, obj, q_page, args.steps, args.warmup, world)
+        v_pin, _, _ = time_e2e(torch, dist, device, obj, qh.numpy(), args.steps, args.warmup, world)
+        link = link_ceiling(torch, dist, device, world)
+        bytes_per_q = (h2d + d2h) / QE
+        e2e = {"value": v_page, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "queries_per_step": QE,
+               "api": "tricubic.Query(ordinary pageable numpy float64 [N,3]) -> numpy outputs",
+               "pinned": {"value": v_pin, "api": "the same call with the caller's array page-locked"},
+               "link_ceiling_gbs": link["bidir_gbs"], "link_h2d_only_gbs": link["h2d_gbs"],
+               "link_d2h_only_gbs": link["d2h_gbs"],
+               "link_frac": v_pin * bytes_per_q / 1e9 / link["bidir_gbs"],
+               "link_frac_pageable": v_page * bytes_per_q / 1e9 / link["bidir_gbs"],
+               "link_note": f"ceiling = {world} rank(s) x concurrent pinned cudaMemcpyAsync H2D + D2H, 256 MiB each way, "
+                            "aggregate GB/s over the slowest rank (tools/link_ceiling.py is the stand-alone form); "
+                            "link_frac = e2e bytes moved per second (pinned input) / that ceiling"}
+        del qh, q_page
+
+    # ---- N > 1: single-process multi-GPU drop-in (rank 0 drives every GPU of the job; the other ranks wait)
+    if world > 1 and not args.no_e2e:
+        dist.barrier()
+        if rank == 0:
+            try:
+                from arbinterp_b200.ingest import IngestedField
+                QS = args.e2e_queries
+                planes = analytic_planes(torch, n, device)[2]
+                from arbinterp_b200.ingest import geometry_from_axes
+                ax = torch.linspace(-1.0, 1.0, n, dtype=torch.float64, device=device)
+                multi = tricubic(IngestedField(planes=torch.stack(planes), geo=geometry_from_axes([ax, ax, ax])),
+                                 "quiet", mode=args.mode, devices=list(range(world)))
+                del planes
+                qm = uniform_queries(torch, obj, QS, 4242, device).cpu().numpy()
+                one = obj.Query(qm.copy())
+                many = multi.Query(qm.copy())
+                one = one if isinstance(one, tuple) else (one,)
+                many = many if isinstance(many, tuple) else (many,)
+                same = all(np.array_equal(a, b, equal_nan=True) for a, b in zip(one, many)) and \
+                    bool(np.array_equal(obj.queryInds, multi.queryInds))
+                v_multi, _, _ = time_e2e(torch, None, device, multi, qm, args.steps, args.warmup, 1)
+                e2e["single_process_multi_gpu"] = {
+                    "value": v_multi, "unit": "queries/s", "devices": world, "queries_per_step": QS,
+                    "bit_identical_to_one_gpu": bool(same),
+                    "api": f"tricubic(field, devices=[0..{world - 1}]).Query(pageable numpy) in ONE process, other ranks idle"}
+                del multi
+            except Exception as e:                                   # noqa: BLE001 -- report, do not lose the line
+                e2e["single_process_multi_gpu"] = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.empty_cache()
+        dist.barrier()
+
+    # ---- other modes and the 4-D path (device-resident), each guarded by an oracle sample (N = 1)
     others = {}
     if not args.no_other_modes and rank == 0 and world == 1:
         del obj, outs
         torch.cuda.empty_cache()
+        ax3, _, raw = analytic_planes(torch, n, device)
+        raw_np = [p.cpu().numpy().ravel() for p in raw]
+        ax_np = ax3.cpu().numpy()
+        del raw
         for m in ("vector", "both"):
             if m == args.mode:
                 continue
@@ -430,11 +849,19 @@ def run_b200(args):
             outs2 = alloc_outputs(torch, m, d, Q2, device)
             el, per = time_device(torch, lib, o2, m, d, q[:Q2], outs2, cells[:Q2], args.steps, args.warmup)
             rate = Q2 * args.steps / el
+            vals = dict(x=raw_np[0], y=raw_np[1], z=raw_np[2])
+            if m == "both":
+                vals["n"] = np.linalg.norm(np.stack(raw_np, axis=1), axis=1)          # A.py:74
+            finite = all(bool(torch.isfinite(t_).all()) for t_ in outs2 if t_ is not None)
+            guard = oracle_sample_check(o2, [ax_np] * 3, vals, m, 3, 100_000, 11)
+            guard["timed_outputs_finite"] = finite
             others[m] = {"value": rate, "unit": "queries/s", "alg_bytes_per_query": ALG_BYTES[(d, m)],
                          "achieved_gbs": ALG_BYTES[(d, m)] * rate / 1e9,
                          "frac_of_measured_hbm": ALG_BYTES[(d, m)] * rate / 1e9 / measured_peak()[0],
-                         "queries_per_step": Q2, "table_gb": o2.table.numel() * 8 / 1e9}
-            del o2, outs2
+                         "traffic_bytes_per_query_ncu": ncu_traffic(m),
+                         "queries_per_step": Q2, "table_gb": o2.table.numel() * 8 / 1e9, "parity": guard}
+            assert guard["ok"] and finite, f"parity failure in bench (mode {m}): {guard}"
+            del o2, outs2, vals
             torch.cuda.empty_cache()
         # quadcubic (time-dependent field, 256x256 Lekien-Marsden matrix with the A.py:860 quirk), value + 4-gradient
         from arbinterp_b200 import quadcubic
@@ -442,93 +869,103 @@ def run_b200(args):
         axes = [torch.linspace(-1.0, 1.0, m, dtype=torch.float64, device=device) for m in shape4[:3]]
         axes.append(torch.linspace(0.0, 1.0, shape4[3], dtype=torch.float64, device=device))
         T, Z, Y, X = torch.meshgrid(*reversed(axes), indexing="ij")
-        u = torch.sin(2 * np.pi * X) * torch.cos(np.pi * Y) * torch.exp(-Z) * torch.cos(2 * T) + X * X * Y + Z * (1 + T)
+        u = torch.sin(2 * np.pi * X) * torch.cos(np.pi * Y) * torch.exp(-Z) * torch.cos(2 * T) + X * X * Y + Z * (1 + T) \
+            + 0.25 * X * Y * Z * T
         t1 = time.perf_counter()
         o4 = quadcubic(torch.stack([t.reshape(-1) for t in (X, Y, Z, T, u)], dim=1), "quiet")
         torch.cuda.synchronize()
         t_ctor4 = time.perf_counter() - t1
+        u_np = u.cpu().numpy().ravel()
         del T, Z, Y, X, u
         Q4 = Q // 4
-        g4 = torch.Generator(device=device)
-        g4.manual_seed(4321)
-        lo4 = torch.tensor(o4._geo.int_min, dtype=torch.float64, device=device)
-        hi4 = torch.tensor(o4._geo.int_max, dtype=torch.float64, device=device)
-        q4 = lo4 + torch.rand(Q4, 4, generator=g4, dtype=torch.float64, device=device) * (hi4 - lo4) * (1 - 1e-12)
+        q4 = uniform_queries(torch, o4, Q4, 4321, device)
         outs4 = alloc_outputs(torch, "norm", 4, Q4, device)
         el, per = time_device(torch, lib, o4, "norm", 4, q4, outs4, cells[:Q4], args.steps, args.warmup)
         rate = Q4 * args.steps / el
+        finite = all(bool(torch.isfinite(t_).all()) for t_ in outs4 if t_ is not None)
+        guard = oracle_sample_check(o4, [a.cpu().numpy() for a in axes], {"n": u_np}, "norm", 4, 100_000, 12, scalar=True)
+        guard["timed_outputs_finite"] = finite
         others["quadcubic_norm"] = {"value": rate, "unit": "queries/s", "alg_bytes_per_query": ALG_BYTES[(4, "norm")],
                                     "achieved_gbs": ALG_BYTES[(4, "norm")] * rate / 1e9,
                                     "frac_of_measured_hbm": ALG_BYTES[(4, "norm")] * rate / 1e9 / measured_peak()[0],
+                                    "traffic_bytes_per_query_ncu": ncu_traffic("4d_norm"),
                                     "queries_per_step": Q4, "table_gb": o4.table.numel() * 8 / 1e9,
-                                    "workload": "quadcubic scalar field %dx%dx%dx%d (config 4 stand-in), uniform random "
-                                                "(x,y,z,t) queries" % shape4, "constructor_s": t_ctor4}
+                                    "workload": "quadcubic scalar field %dx%dx%dx%d with an xyzt term (config 4 stand-in), "
+                                                "uniform random (x,y,z,t) queries" % shape4, "constructor_s": t_ctor4,
+                                    "parity": guard}
+        assert guard["ok"] and finite, f"parity failure in bench (quadcubic): {guard}"
         del o4, outs4, q4
         torch.cuda.empty_cache()
         _, rows = analytic_field_rows(torch, n, device)
         obj = tricubic(rows, "quiet", mode=args.mode)
         del rows
 
-    # ---- end-to-end leg: public API with host (pinned) numpy buffers, copies inside the timed region
-    e2e = None
-    if not args.no_e2e:
-        QE = args.e2e_queries
-        qh = torch.empty(QE, 3, dtype=torch.float64, pin_memory=True)
-        qh.copy_(q[:QE])
-        qnp = qh.numpy()
-        for _ in range(max(1, min(args.warmup, 2))):
-            res = obj.Query(qnp)
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            res = obj.Query(qnp)
-        torch.cuda.synchronize()
-        te = time.perf_counter() - t0
-        if dist is not None:
-            t = torch.tensor([te], dtype=torch.float64, device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            te = float(t.item())
-        res = res if isinstance(res, tuple) else (res,)
-        d2h = sum(r.nbytes for r in res if r is not None)
-        e2e = {"value": world * QE * args.steps / te, "unit": "queries/s", "h2d_bytes_per_step": int(qnp.nbytes),
-               "d2h_bytes_per_step": int(d2h), "queries_per_step": QE,
-               "api": "tricubic.Query(numpy float64 [N,3] in pinned host memory) -> numpy outputs"}
+    # ---- N > 1: the slab-sharded config-5 path with in-run parity
+    sharded = None
+    if world > 1 and not args.no_sharded:
+        del outs, cells, q
+        table_gb_main = obj.table.numel() * 8 / 1e9
+        qbytes = Q * 3 * 8
+        del obj
+        obj = None
+        torch.cuda.empty_cache()
+        sharded = run_sharded(torch, dist, args, rank, world, device)
+    else:
+        table_gb_main = obj.table.numel() * 8 / 1e9
+        qbytes = Q * 3 * 8
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    # ---- CPU baseline beside it (rank 0, N=1 only)
+    # ---- CPU baseline beside it (rank 0, N=1 only): the unmodified reference when staged, and the in-bench parity
+    # of 10^6 rows against the numpy oracle (the checker)
     cpu = None
     parity = None
     if world == 1 and not args.no_cpu:
-        ncpu = n
-        ora = make_cpu_oracle(ncpu, args.mode)
+        ora = make_cpu_oracle(n, args.mode)
         qc = cpu_queries(ora, args.cpu_sample, 7)
-        rate = cpu_warm_rate(ora, qc)
-        cpu = {"value": rate, "unit": "queries/s", "cores": 1, "kind": "port",
-               "sample": f"{args.cpu_sample} warm queries (second pass, coefficients cached) through the numpy oracle "
-                         f"on a {ncpu}^3 grid of the same analytic field, single process",
-               "cold_value": cpu_warm_rate.cold,
-               "cold_note": "first pass over the same sample incl. the lazy coefficient fill (A.py:376-377); the port "
-                            "fills touched cells with one batched dgemm, the reference's per-cell Python loop is slower"}
-        # full-size parity on the same sample (oracle as the checker): indices exact, values within 1e-12 scaled
+        t0 = time.perf_counter()
         ref = ora.query(qc.copy())
-        ref = ref if isinstance(ref, tuple) else (ref,)
+        port_cold = len(qc) / (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        for lo_ in range(0, len(qc), 100_000):
+            ora.query(qc[lo_:lo_ + 100_000].copy())
+        port_warm = len(qc) / (time.perf_counter() - t0)
         got = obj.Query(qc.copy())
-        got = got if isinstance(got, tuple) else (got,)
         scale = max(float(np.abs(v).max()) for v in ora.values.values())
-        worst = 0.0
-        for a, b in zip(got, ref):
-            sc = scale / np.array(ora.geo.h)[None, :] if b.shape[1] == d and args.mode != "vector" and a is got[-1] else scale
-            worst = max(worst, float(np.max(np.abs(a - b) / np.maximum(np.abs(b), sc))))
+        worst = scaled_error(got, ref, d, ora.geo.h, scale)
         parity = {"n": int(len(qc)), "max_scaled_err": worst, "tolerance": 1e-12,
                   "indices_equal": bool(np.array_equal(obj.queryInds, ora.query_inds)),
                   "checker": "oracle/arb_oracle.py (numpy restatement, bit-equal to the live reference on tests/golden)"}
         assert parity["indices_equal"] and worst <= 1e-12, f"parity failure in bench: {parity}"
+        del ora, ref
+        arm = CpuArm(n, args.mode, args.force_port)
+        if arm.kind == "reference":
+            qs = uniform_in_volume(arm.lo, arm.hi, args.ref_sample, 8)
+            cold = arm.passes(qs, 50_000)                     # first pass: lazy per-cell coefficient fill (A.py:376-377)
+            warm = arm.passes(qs, 50_000)
+            # the unmodified reference against the GPU path on its own sample
+            r_ref = arm.query(qs.copy())
+            r_got = obj.Query(qs.copy())
+            ref_err = scaled_error(r_got, r_ref, d, [arm.obj.hx, arm.obj.hy, arm.obj.hz], scale)
+            ref_idx = bool(np.array_equal(obj.queryInds, arm.obj.queryInds))
+            assert ref_idx and ref_err <= 1e-12, f"parity failure against the unmodified reference: {ref_err} {ref_idx}"
+            cpu = {"value": warm, "unit": "queries/s", "cores": 1, "kind": "reference",
+                   "sample": f"{args.ref_sample} warm queries (second pass, coefficients cached) through the {arm.what} "
+                             f"on a {n}^3 grid of the same analytic field, single process (the reference is single-threaded)",
+                   "cold_value": cold,
+                   "cold_note": "first pass over the same sample incl. the reference's lazy per-cell coefficient fill (A.py:376-377)",
+                   "parity_vs_gpu": {"n": int(len(qs)), "max_scaled_err": ref_err, "indices_equal": ref_idx},
+                   "port_value": port_warm, "port_cold_value": port_cold,
+                   "port_note": f"the numpy port (oracle/arb_oracle.py) on {args.cpu_sample} rows, warm / cold"}
+        else:
+            cpu = {"value": port_warm, "unit": "queries/s", "cores": 1, "kind": "port",
+                   "sample": f"{args.cpu_sample} warm queries (second pass, coefficients cached) through the numpy oracle "
+                             f"on a {n}^3 grid of the same analytic field, single process (reference not staged under oracle/_ref)",
+                   "cold_value": port_cold}
+        del arm
 
     peak, peak_src = measured_peak()
     alg = ALG_BYTES[(d, args.mode)]
@@ -539,11 +976,10 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"tricubic {n}^3 analytic vector field, mode={args.mode} (value+gradient), "
-                               f"uniform random in-volume queries",
-                   "queries_per_step_per_gpu": Q, "table_gb": obj.table.numel() * 8 / 1e9,
+        "config": {"workload": workload_string(n, args.mode),
+                   "queries_per_step_per_gpu": Q, "table_gb": table_gb_main,
                    "cache": "inputs larger than L2 (query batch %.1f GB, table %.1f GB vs 126 MB L2)" %
-                            (q.numel() * 8 / 1e9, obj.table.numel() * 8 / 1e9),
+                            (qbytes / 1e9, table_gb_main),
                    "parallelism": f"replicated table, queries sharded x{world}",
                    "variant": args.variant if args.variant is not None else 0, "build_s": t_build,
                    "cpu_affinity": affinity},
@@ -561,6 +997,8 @@ def run_b200(args):
         line["build"] = build_info
     if others:
         line["other_modes"] = others
+    if sharded:
+        line["sharded"] = sharded
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

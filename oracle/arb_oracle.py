@@ -151,10 +151,11 @@ class GridGeometry:
         self.nc = len(self.base_point_inds)                       # A.py:568, 1320
 
     @classmethod
-    def from_axes(cls, axes):
+    def from_axes(cls, axes, with_base=True):
         """Geometry of an already sorted full grid given its per-axis coordinates: the same
         expressions as ``__init__`` without materialising and sorting the (N, d+k) row array
-        (used by bench.py at 256^3, where the sort alone takes minutes in numpy)."""
+        (used by bench.py at 256^3, where the sort alone takes minutes in numpy).
+        ``with_base=False`` skips ``basePointInds`` (only ``locate`` is wanted: config 5 has 49 M cells)."""
         self = cls.__new__(cls)
         d = self.d = len(axes)
         self.sorted = None
@@ -165,6 +166,10 @@ class GridGeometry:
         self.h = [np.abs(axes[a][0] - axes[a][1]) for a in range(d)]
         self.int_min = [axes[a][1] for a in range(d)]
         self.int_max = [axes[a][-2] for a in range(d)]
+        if not with_base:
+            self.base_point_inds = None
+            self.nc = int(np.prod(self.ncell_axis))              # A.py:568, 1320: len(basePointInds)
+            return self
         base = sum(self.stride)
         grids = np.meshgrid(*[np.arange(self.ncell_axis[a]) * self.stride[a] for a in reversed(range(d))], indexing="ij")
         self.base_point_inds = (base + sum(grids)).ravel().astype(np.int64)
@@ -258,6 +263,15 @@ class OracleInterp:
             self._cols = {k: np.zeros((self.nmono, 0)) for k in self.values}
             self._have = np.zeros(nc + 1, dtype=bool)
             self._have[-1] = True
+        return self
+
+    @classmethod
+    def locator(cls, axes):
+        """An oracle that can only ``locate`` (bounds mask, global cell index, fractions; A.py:350-373, 1069-1092) on
+        the geometry of the given axes -- for full-size index checks where no host can hold the coefficients."""
+        self = cls.__new__(cls)
+        self.d = len(axes)
+        self.geo = GridGeometry.from_axes([np.asarray(a, dtype=np.float64) for a in axes], with_base=False)
         return self
 
     # ---- coefficients ------------------------------------------------------------

@@ -401,3 +401,97 @@ def test_sharded_push_migration_gloo(tmp_path, world):
         rounds.append(int(z["rounds"]))
         total_lost += int(z["lost"])
     assert 0 < total_lost < n and max(rounds) > 1
+
+
+# ---- drop-in semantics of the sharded / replicated wrappers (CPU stand-in for the CUDA class, gloo, world 2)
+class _OracleBackedQuad:
+    """What SlabShardedInterp / ReplicatedInterp need from ``quadcubic`` -- constructor taking the broadcast
+    IngestedField (+ slab), ``Query(rows)`` on tensors, ``_last_cells``, ``_geo``, ``_mode``, ``_device``, ``nc`` --
+    with the arithmetic done by the numpy oracle, so the routing, the in-place NaN rows and the global ``queryInds``
+    can be checked on CPU."""
+    _d = 4
+
+    def __init__(self, field, *args, slab=None, device=None, mode="vector", **kwargs):
+        from arbinterp_b200.ingest import IngestedField
+        from oracle.arb_oracle import OracleInterp
+        assert isinstance(field, IngestedField) and "quiet" in args
+        geo = field.geo
+        planes = field.planes.numpy()
+        vals = dict(x=planes[0].ravel(), y=planes[1].ravel(), z=planes[2].ravel())
+        vals["n"] = np.linalg.norm(np.stack([vals[k] for k in "xyz"], axis=1), axis=1)
+        self._ora = OracleInterp.from_planes([a.numpy() for a in geo.axes], vals, mode, dense=True)
+        self._geo, self._mode, self._device = geo, mode, torch.device("cpu")
+        self._slab = slab if slab is not None else (0, geo.ncell[3])
+        self.nc = geo.nc
+        self.foreign_rows = 0
+
+    def Query(self, q):
+        r = (q.numpy() if isinstance(q, torch.Tensor) else q)
+        r = np.ascontiguousarray(r[:, :4], dtype=np.float64).copy()
+        res = self._ora.query(r, exact_gemv=True)
+        inds = self._ora.query_inds
+        layer = inds // (self.nc // self._geo.ncell[3])
+        self.foreign_rows += int(((inds < self.nc) & ((layer < self._slab[0]) | (layer >= self._slab[1]))).sum())
+        self._last_cells = torch.from_numpy(inds.astype(np.int64))
+        if isinstance(q, torch.Tensor):
+            return tuple(torch.from_numpy(np.ascontiguousarray(x)) for x in res)
+        if isinstance(q, np.ndarray):
+            q[np.isnan(r).all(axis=1) & ~np.isnan(q[:, :4]).all(axis=1)] = np.nan
+        return res
+
+
+def _dropin_worker(rank, world, port, field, q_all, out_dir):
+    import torch.distributed as dist
+    from arbinterp_b200.sharding import ReplicatedInterp, SlabShardedInterp
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    src = field if rank == 0 else None
+    sh = SlabShardedInterp(_OracleBackedQuad, src, "quiet", mode="both", device="cpu")
+    mine = q_all[rank::world].copy()                         # numpy in, extra columns, rows of every kind
+    before = mine.copy()
+    comps, norms, grads = sh.Query(mine)                     # numpy out
+    assert isinstance(comps, np.ndarray) and sh.local.foreign_rows == 0
+    inds = sh.queryInds.copy()                               # side effect of THIS call (A.py:1088-1090)
+    as_tensor = sh.Query(torch.from_numpy(before.copy()))    # tensor in -> tensors out
+    assert all(isinstance(t, torch.Tensor) for t in as_tensor)
+    f32 = sh.Query(torch.from_numpy(before[:, :4].astype(np.float32)))   # ADVICE r01: float32 rows must not be mis-read
+    sh.Query(np.empty((0, 4)))                               # an empty share is a legal collective call
+    rep = ReplicatedInterp(_OracleBackedQuad, src, "quiet", mode="both", device="cpu")
+    mine2 = before.copy()
+    r2 = rep.Query(mine2)
+    np.savez(os.path.join(out_dir, f"dropin{rank}.npz"), out=np.hstack([comps, norms, grads]), q_after=mine,
+             inds=inds, tens=np.hstack([t.numpy() for t in as_tensor]), f32=np.hstack([t.numpy() for t in f32]),
+             rep=np.hstack(r2), rep_q=mine2, rep_inds=rep.local._last_cells.numpy(), nc=rep.nc)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_and_replicated_query_are_dropin_world2_gloo(tmp_path):
+    """SlabShardedInterp.Query / ReplicatedInterp.Query take THIS rank's rows as numpy and behave like the reference's
+    rQuery3 on them (A.py:1190-1258): same outputs as a single-process evaluation, the caller's out-of-volume rows
+    NaN-overwritten in place across all columns (A.py:1069-1076), queryInds = global cell index, nc for NaN rows
+    (A.py:1088-1090); rows only ever reach the rank that owns their t layer."""
+    import torch.multiprocessing as mp
+    from oracle.arb_oracle import OracleInterp
+    g = load_golden("quad_8x7x7x6")
+    field, q_all = g["field"], g["both_q_in"].copy()
+    assert q_all.shape[1] > 4                                # extra columns present
+    world = 2
+    mp.spawn(_dropin_worker, args=(world, _free_port(), field, q_all, str(tmp_path)), nprocs=world, join=True)
+    ora = OracleInterp(field, 4, mode="both")
+    q_ref = q_all.copy()
+    ref = np.hstack(ora.query(q_ref, exact_gemv=True))
+    assert np.array_equal(q_ref, g["both_q_after"], equal_nan=True)
+    for rank in range(world):
+        z = np.load(tmp_path / f"dropin{rank}.npz")
+        for key in ("out", "tens", "rep"):
+            assert np.array_equal(z[key], ref[rank::world], equal_nan=True), key
+        assert np.array_equal(z["q_after"], g["both_q_after"][rank::world], equal_nan=True)
+        assert np.array_equal(z["rep_q"], g["both_q_after"][rank::world], equal_nan=True)
+        assert np.array_equal(z["inds"], g["both_inds"][rank::world])
+        assert np.array_equal(z["rep_inds"], g["both_inds"][rank::world])
+        assert int(z["nc"]) == int(g["nc"])
+        # float32 coordinates are upcast, not reinterpreted: same NaN pattern, values close to the float64 answer
+        ok = ~np.isnan(z["f32"]).any(axis=1) & ~np.isnan(ref[rank::world]).any(axis=1)
+        assert ok.sum() > 10 and np.abs(z["f32"][ok][:, :4] - ref[rank::world][ok][:, :4]).max() < 1e-3
