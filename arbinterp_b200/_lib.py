@@ -18,6 +18,7 @@ EXPORTED_SYMBOLS = (
     "arb_version", "arb_last_error", "arb_get_matrix",
     "arb_build_coeffs", "arb_build_coeffs_3d", "arb_build_coeffs_4d",
     "arb_query", "arb_query_host", "arb_query_grid", "arb_query_grid_host",
+    "arb_build_nodes", "arb_query_nodes", "arb_query_nodes_host",
     "arb_push", "arb_push_steps", "arb_permute_rows", "arb_set_query_variant", "arb_set_build_variant",
 )
 
@@ -80,6 +81,12 @@ def load():
     lib.arb_query_grid.argtypes = [ctypes.POINTER(ArbGeom), vp, i64, i32, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp]
     lib.arb_query_grid_host.restype = i32
     lib.arb_query_grid_host.argtypes = [ctypes.POINTER(ArbGeom), vp, i64, i32, vp, i64, i64, vp, vp, vp, vp, i64]
+    lib.arb_build_nodes.restype = i32
+    lib.arb_build_nodes.argtypes = [i32, vp, i32, ctypes.POINTER(i64 * 4), i64, vp, vp]
+    lib.arb_query_nodes.restype = i32
+    lib.arb_query_nodes.argtypes = lib.arb_query.argtypes
+    lib.arb_query_nodes_host.restype = i32
+    lib.arb_query_nodes_host.argtypes = lib.arb_query_host.argtypes
     lib.arb_push.restype = i32
     lib.arb_push.argtypes = [ctypes.POINTER(ArbGeom), vp, i32, vp, vp, i64, ctypes.c_double, i64, ctypes.c_double,
                              ctypes.POINTER(ctypes.c_double * 3), vp, vp]

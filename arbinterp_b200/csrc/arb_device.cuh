@@ -21,6 +21,8 @@ struct QueryParams {
     int64_t slab_lo, slab_hi;   // owned layers of the slowest axis
     int64_t total_cells;        // prod(nc): sentinel index (A.py:369)
     int64_t layer_cells;        // prod(nc[0..d-2])
+    int64_t nn[4];              // node table (arb_nodes.cuh): nodes per axis = nc + 1
+    int64_t node_comp_stride;   // doubles between the components of a node table
 };
 
 // --------------------------------------------------------------------------------------

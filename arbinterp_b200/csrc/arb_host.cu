@@ -4,6 +4,7 @@
 // through pinned ring buffers.  The in-place NaN masking of out-of-volume rows (A.py:350-355)
 // is mirrored on the host from a compact list of masked row numbers, so q is never copied back.
 #include <condition_variable>
+#include <deque>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -20,57 +21,87 @@ int current_query_variant();
 int query_grid_device(const arb_geom* g, const double* grid, int64_t pitch_x, int mode, double* q, int64_t N,
                       int64_t ldq, double* out_comps, double* out_norm, double* out_grad, int64_t* out_cell,
                       int64_t* masked_rows, unsigned long long* masked_count, cudaStream_t st);
+int query_nodes_device(const arb_geom* g, const double* nodes, int mode, double* q, int64_t N, int64_t ldq,
+                       double* out_comps, double* out_norm, double* out_grad, int64_t* out_cell, int64_t* masked_rows,
+                       unsigned long long* masked_count, cudaStream_t st);
+
+// one device-side query on whatever `table` is: grid_pitch > 0 = raw grid planes (table-free), < 0 = node table,
+// 0 = cell coefficient table
+static int query_any_device(const arb_geom* g, const double* table, int64_t grid_pitch, int mode, double* q, int64_t N,
+                            int64_t ldq, double* out_comps, double* out_norm, double* out_grad, int64_t* out_cell,
+                            int64_t* masked_rows, unsigned long long* masked_count, cudaStream_t st) {
+    if (grid_pitch > 0)
+        return query_grid_device(g, table, grid_pitch, mode, q, N, ldq, out_comps, out_norm, out_grad, out_cell,
+                                 masked_rows, masked_count, st);
+    if (grid_pitch < 0)
+        return query_nodes_device(g, table, mode, q, N, ldq, out_comps, out_norm, out_grad, out_cell, masked_rows,
+                                  masked_count, st);
+    return query_device(g, table, mode, q, N, ldq, out_comps, out_norm, out_grad, out_cell, masked_rows, masked_count,
+                        st, current_query_variant());
+}
 
 namespace {
 
 constexpr int NSLOT = 3;
 
-// Staging copies between pageable caller memory and the pinned ring are plain memcpy; one thread
-// moves ~10-25 GB/s, less than the PCIe link, so large copies are split over a few helper threads.
+// Staging copies between pageable caller memory and the pinned rings are plain memcpy; one thread moves
+// ~10-25 GB/s, less than the PCIe link, so they run on a few helper threads.  Two forms: copy() splits one
+// copy over the pool and waits (results leaving the ring); submit()/wait() queues a copy and returns, so the
+// query rows of the chunks AHEAD of the one being issued are staged while the caller thread feeds the GPU
+// (round 1 staged each chunk in line: the link idled during every memcpy and a pageable batch ran at 0.3-1.0e9
+// q/s against 1.46e9 for a page-locked one).
 class CopyPool {
   public:
-    void copy(void* dst, const void* src, size_t bytes) {
-        if (bytes < (4u << 20)) { memcpy(dst, src, bytes); return; }
+    struct Ticket { int pending = 0; };          // guarded by the pool mutex
+
+    // queue `bytes` in up to `max_parts` pieces (>= 1 MiB each) and return
+    void submit(void* dst, const void* src, size_t bytes, Ticket* t, int max_parts) {
         ensure_started();
-        if (workers_.empty()) { memcpy(dst, src, bytes); return; }
-        const int parts = (int)workers_.size() + 1;
-        const size_t step = ((bytes / parts) + 4095) & ~(size_t)4095;
+        if (workers_.empty() || bytes == 0) { if (bytes) memcpy(dst, src, bytes); return; }
+        int parts = (int)(bytes >> 20);
+        if (parts > max_parts) parts = max_parts;
+        if (parts < 1) parts = 1;
+        const size_t step = (((bytes + parts - 1) / parts) + 4095) & ~(size_t)4095;
         {
             std::lock_guard<std::mutex> lk(m_);
-            for (int i = 1; i < parts; ++i) {
-                const size_t off = step * i;
-                if (off >= bytes) break;
-                tasks_.push_back({(char*)dst + off, (const char*)src + off, std::min(step, bytes - off)});
-                ++pending_;
+            for (size_t off = 0; off < bytes; off += step) {
+                tasks_.push_back({(char*)dst + off, (const char*)src + off, std::min(step, bytes - off), t});
+                ++t->pending;
             }
         }
         cv_.notify_all();
-        memcpy(dst, src, std::min(step, bytes));
+    }
+    void wait(Ticket* t) {
         std::unique_lock<std::mutex> lk(m_);
-        done_cv_.wait(lk, [&] { return pending_ == 0; });
+        done_cv_.wait(lk, [&] { return t->pending == 0; });
+    }
+    void copy(void* dst, const void* src, size_t bytes) {
+        if (bytes < (4u << 20)) { memcpy(dst, src, bytes); return; }
+        ensure_started();
+        Ticket t;
+        submit(dst, src, bytes, &t, workers_.empty() ? 1 : (int)workers_.size());
+        wait(&t);
     }
 
   private:
-    struct Task { char* dst; const char* src; size_t n; };
+    struct Task { char* dst; const char* src; size_t n; Ticket* t; };
     void ensure_started() {
         if (pid_ == getpid() && started_) return;
         if (pid_ != getpid()) {                    // forked child: the parent's threads do not exist here
-            workers_.clear(); tasks_.clear(); pending_ = 0;   // (already detached)
+            workers_.clear(); tasks_.clear();      // (already detached)
         }
         pid_ = getpid();
         started_ = true;
-        // one memcpy thread moves 10-25 GB/s; a Gen5 x16 link needs ~55 GB/s each way, so the pool grows with the
-        // cores this process may run on (sched_getaffinity: a rank bound to its GPU's cores gets its share, not
-        // the whole box) up to 11 helpers; ARB_COPY_THREADS overrides
+        // the pool grows with the cores this process may run on (sched_getaffinity: a rank bound to its GPU's
+        // cores gets its share, not the whole box), one core is left to the caller thread; ARB_COPY_THREADS overrides
         int allowed = 0;
         cpu_set_t set;
         if (sched_getaffinity(0, sizeof(set), &set) == 0) allowed = CPU_COUNT(&set);
         if (allowed <= 0) allowed = (int)std::thread::hardware_concurrency();
-        int n = allowed - 2;
-        if (n > 11) n = 11;
+        int n = allowed - 1;
+        if (n > 8) n = 8;
         if (n < 1) n = 1;
-        if (const char* e = getenv("ARB_COPY_THREADS")) { const int v = atoi(e); if (v >= 1 && v <= 64) n = v - 1; }
-        if (n < 1) { workers_.clear(); return; }
+        if (const char* e = getenv("ARB_COPY_THREADS")) { const int v = atoi(e); if (v >= 0 && v <= 64) n = v; }
         for (int i = 0; i < n; ++i) {
             workers_.emplace_back([this] {
                 for (;;) {
@@ -78,13 +109,13 @@ class CopyPool {
                     {
                         std::unique_lock<std::mutex> lk(m_);
                         cv_.wait(lk, [&] { return !tasks_.empty(); });
-                        t = tasks_.back();
-                        tasks_.pop_back();
+                        t = tasks_.front();
+                        tasks_.pop_front();
                     }
                     memcpy(t.dst, t.src, t.n);
                     {
                         std::lock_guard<std::mutex> lk(m_);
-                        if (--pending_ == 0) done_cv_.notify_all();
+                        if (--t.t->pending == 0) done_cv_.notify_all();
                     }
                 }
             });
@@ -93,9 +124,8 @@ class CopyPool {
     }
     std::mutex m_;
     std::condition_variable cv_, done_cv_;
-    std::vector<Task> tasks_;
+    std::deque<Task> tasks_;
     std::vector<std::thread> workers_;
-    int pending_ = 0;
     bool started_ = false;
     pid_t pid_ = 0;
 };
@@ -111,7 +141,7 @@ struct Slot {
     int64_t *d_cell = nullptr, *d_rows = nullptr;
     unsigned long long* d_count = nullptr;
     // pinned host staging
-    double *h_q = nullptr, *h_comps = nullptr, *h_norm = nullptr, *h_grad = nullptr;
+    double *h_comps = nullptr, *h_norm = nullptr, *h_grad = nullptr;
     int64_t *h_cell = nullptr, *h_rows = nullptr;
     unsigned long long* h_count = nullptr;
     // in-flight chunk
@@ -119,8 +149,20 @@ struct Slot {
     int64_t off = 0, rows = 0;
 };
 
+// pinned staging ring for pageable query rows: deeper than the stream ring, so the helper threads run
+// NSTAGE - 1 chunks ahead of the chunk being issued; a buffer is refilled once its own H2D copy has finished
+constexpr int NSTAGE = 6;
+struct StageBuf {
+    double* h = nullptr;
+    cudaEvent_t h2d_done = nullptr;
+    bool used = false;
+    CopyPool::Ticket ticket;
+};
+
 struct HostCtx {
     Slot slot[NSLOT];
+    StageBuf stage[NSTAGE];
+    int64_t stage_rows = 0, stage_ldq = 0;
     int64_t cap_rows = 0, cap_ldq = 0;
     int device = -1;
     std::mutex mutex;
@@ -131,11 +173,11 @@ HostCtx g_ctx[16];
 void free_slot(Slot& s) {
     cudaFree(s.d_q); cudaFree(s.d_comps); cudaFree(s.d_norm); cudaFree(s.d_grad); cudaFree(s.d_cell);
     cudaFree(s.d_rows); cudaFree(s.d_count);
-    cudaFreeHost(s.h_q); cudaFreeHost(s.h_comps); cudaFreeHost(s.h_norm); cudaFreeHost(s.h_grad);
+    cudaFreeHost(s.h_comps); cudaFreeHost(s.h_norm); cudaFreeHost(s.h_grad);
     cudaFreeHost(s.h_cell); cudaFreeHost(s.h_rows); cudaFreeHost(s.h_count);
     s.d_q = s.d_comps = s.d_norm = s.d_grad = nullptr;
     s.d_cell = s.d_rows = nullptr; s.d_count = nullptr;
-    s.h_q = s.h_comps = s.h_norm = s.h_grad = nullptr;
+    s.h_comps = s.h_norm = s.h_grad = nullptr;
     s.h_cell = s.h_rows = nullptr; s.h_count = nullptr;
 }
 
@@ -158,7 +200,6 @@ int ensure_capacity(HostCtx& c, int64_t rows, int64_t ldq) {
         ARB_CUDA(cudaMalloc(&s.d_cell, sizeof(int64_t) * rows));
         ARB_CUDA(cudaMalloc(&s.d_rows, sizeof(int64_t) * rows));
         ARB_CUDA(cudaMalloc(&s.d_count, sizeof(unsigned long long)));
-        ARB_CUDA(cudaMallocHost(&s.h_q, sizeof(double) * rows * ldq));
         ARB_CUDA(cudaMallocHost(&s.h_comps, sizeof(double) * rows * 3));
         ARB_CUDA(cudaMallocHost(&s.h_norm, sizeof(double) * rows));
         ARB_CUDA(cudaMallocHost(&s.h_grad, sizeof(double) * rows * 4));
@@ -167,6 +208,22 @@ int ensure_capacity(HostCtx& c, int64_t rows, int64_t ldq) {
         ARB_CUDA(cudaMallocHost(&s.h_count, sizeof(unsigned long long)));
     }
     c.cap_rows = rows; c.cap_ldq = ldq;
+    return 0;
+}
+
+int ensure_stage(HostCtx& c, int64_t rows, int64_t ldq) {
+    if (rows <= c.stage_rows && ldq <= c.stage_ldq) return 0;
+    if (rows < c.stage_rows) rows = c.stage_rows;
+    if (ldq < c.stage_ldq) ldq = c.stage_ldq;
+    c.stage_rows = 0; c.stage_ldq = 0;
+    for (int i = 0; i < NSTAGE; ++i) {
+        StageBuf& b = c.stage[i];
+        if (!b.h2d_done) ARB_CUDA(cudaEventCreateWithFlags(&b.h2d_done, cudaEventDisableTiming));
+        cudaFreeHost(b.h);
+        b.h = nullptr; b.used = false;
+        ARB_CUDA(cudaMallocHost(&b.h, sizeof(double) * rows * ldq));
+    }
+    c.stage_rows = rows; c.stage_ldq = ldq;
     return 0;
 }
 
@@ -275,15 +332,9 @@ int query_host_small(const arb_geom* g, const double* table, int64_t grid_pitch,
         // caller keeps them on the device)
         int64_t* z_cell = cell ? (cell_dev ? cell : reinterpret_cast<int64_t*>(c.h + o_cell)) : nullptr;
         double* zq = reinterpret_cast<double*>(c.h + o_q);
-        int zrc;
-        if (grid_pitch > 0)
-            zrc = query_grid_device(g, table, grid_pitch, mode, zq, N, ldq, reinterpret_cast<double*>(c.h + o_comps),
-                                    reinterpret_cast<double*>(c.h + o_norm), reinterpret_cast<double*>(c.h + o_grad),
-                                    z_cell, nullptr, nullptr, c.stream);
-        else
-            zrc = query_device(g, table, mode, zq, N, ldq, reinterpret_cast<double*>(c.h + o_comps),
-                               reinterpret_cast<double*>(c.h + o_norm), reinterpret_cast<double*>(c.h + o_grad), z_cell,
-                               nullptr, nullptr, c.stream, current_query_variant());
+        const int zrc = query_any_device(g, table, grid_pitch, mode, zq, N, ldq, reinterpret_cast<double*>(c.h + o_comps),
+                                         reinterpret_cast<double*>(c.h + o_norm), reinterpret_cast<double*>(c.h + o_grad),
+                                         z_cell, nullptr, nullptr, c.stream);
         if (zrc) return zrc;
         ARB_CUDA(cudaStreamSynchronize(c.stream));
         if (comps) memcpy(comps, c.h + o_comps, sizeof(double) * N * 3);
@@ -297,17 +348,10 @@ int query_host_small(const arb_geom* g, const double* table, int64_t grid_pitch,
     ARB_CUDA(cudaMemcpyAsync(c.d, c.h, o_count + 8, cudaMemcpyHostToDevice, c.stream));
     int64_t* d_cell = cell ? (cell_dev ? cell : reinterpret_cast<int64_t*>(c.d + o_cell)) : nullptr;
     double* dq = reinterpret_cast<double*>(c.d + o_q);
-    int rc;
-    if (grid_pitch > 0)
-        rc = query_grid_device(g, table, grid_pitch, mode, dq, N, ldq, reinterpret_cast<double*>(c.d + o_comps),
-                               reinterpret_cast<double*>(c.d + o_norm), reinterpret_cast<double*>(c.d + o_grad), d_cell,
-                               reinterpret_cast<int64_t*>(c.d + o_rows),
-                               reinterpret_cast<unsigned long long*>(c.d + o_count), c.stream);
-    else
-        rc = query_device(g, table, mode, dq, N, ldq, reinterpret_cast<double*>(c.d + o_comps),
-                          reinterpret_cast<double*>(c.d + o_norm), reinterpret_cast<double*>(c.d + o_grad), d_cell,
-                          reinterpret_cast<int64_t*>(c.d + o_rows), reinterpret_cast<unsigned long long*>(c.d + o_count),
-                          c.stream, current_query_variant());
+    const int rc = query_any_device(g, table, grid_pitch, mode, dq, N, ldq, reinterpret_cast<double*>(c.d + o_comps),
+                                    reinterpret_cast<double*>(c.d + o_norm), reinterpret_cast<double*>(c.d + o_grad), d_cell,
+                                    reinterpret_cast<int64_t*>(c.d + o_rows),
+                                    reinterpret_cast<unsigned long long*>(c.d + o_count), c.stream);
     if (rc) return rc;
     const size_t back_end = (cell && !cell_dev) ? o_rows : o_cell;
     ARB_CUDA(cudaMemcpyAsync(c.h + o_count, c.d + o_count, back_end - o_count, cudaMemcpyDeviceToHost, c.stream));
@@ -334,6 +378,10 @@ namespace arb {
 namespace {
 // error exit of the pipelined path: nothing may stay in flight that still points at this call's buffers
 int abandon(HostCtx& ctx, int rc) {
+    for (int i = 0; i < NSTAGE; ++i) {             // helper threads still read the caller's rows
+        g_pool.wait(&ctx.stage[i].ticket);
+        ctx.stage[i].used = false;
+    }
     for (int i = 0; i < NSLOT; ++i) {
         if (ctx.slot[i].stream) cudaStreamSynchronize(ctx.slot[i].stream);
         ctx.slot[i].busy = false;
@@ -383,12 +431,31 @@ static int query_host_impl(const arb_geom* g, const double* table, int64_t grid_
     std::lock_guard<std::mutex> lock(ctx.mutex);
     int rc = ensure_capacity(ctx, chunk_rows, ldq);
     if (rc) return rc;
+    if (!c.q_pinned) {
+        rc = ensure_stage(ctx, chunk_rows, ldq);
+        if (rc) return rc;
+    }
 
 #define ARB_CUDA_OR_ABANDON(expr)                                  \
     do {                                                            \
         int _rc = ::arb::check_cuda((expr), #expr);                 \
         if (_rc) return abandon(ctx, _rc);                          \
     } while (0)
+    const int64_t nchunks = (N + chunk_rows - 1) / chunk_rows;
+    // pageable rows: chunk j is staged into ring buffer j % NSTAGE by the helper threads, NSTAGE - 1 chunks ahead
+    auto stage_chunk = [&](int64_t j) -> int {
+        StageBuf& b = ctx.stage[j % NSTAGE];
+        if (b.used) ARB_CUDA(cudaEventSynchronize(b.h2d_done));
+        const int64_t o = j * chunk_rows, n = (N - o < chunk_rows) ? (N - o) : chunk_rows;
+        g_pool.submit(b.h, q_host + o * ldq, sizeof(double) * n * ldq, &b.ticket, 2);
+        b.used = true;
+        return 0;
+    };
+    if (!c.q_pinned)
+        for (int64_t j = 0; j < nchunks && j < NSTAGE - 1; ++j) {
+            rc = stage_chunk(j);
+            if (rc) return abandon(ctx, rc);
+        }
     int64_t chunk = 0;
     for (int64_t off = 0; off < N; off += chunk_rows, ++chunk) {
         Slot& s = ctx.slot[chunk % NSLOT];
@@ -396,16 +463,22 @@ static int query_host_impl(const arb_geom* g, const double* table, int64_t grid_
         if (rc) return abandon(ctx, rc);
         const int64_t n = (N - off < chunk_rows) ? (N - off) : chunk_rows;
         const double* src = q_host + off * ldq;
-        if (!c.q_pinned) { g_pool.copy(s.h_q, src, sizeof(double) * n * ldq); src = s.h_q; }
+        StageBuf* sb = nullptr;
+        if (!c.q_pinned) {
+            if (chunk + NSTAGE - 1 < nchunks) {
+                rc = stage_chunk(chunk + NSTAGE - 1);
+                if (rc) return abandon(ctx, rc);
+            }
+            sb = &ctx.stage[chunk % NSTAGE];
+            g_pool.wait(&sb->ticket);
+            src = sb->h;
+        }
         ARB_CUDA_OR_ABANDON(cudaMemcpyAsync(s.d_q, src, sizeof(double) * n * ldq, cudaMemcpyHostToDevice, s.stream));
+        if (sb) ARB_CUDA_OR_ABANDON(cudaEventRecord(sb->h2d_done, s.stream));
         ARB_CUDA_OR_ABANDON(cudaMemsetAsync(s.d_count, 0, sizeof(unsigned long long), s.stream));
         int64_t* cell_dst = c.cell ? (c.cell_on_device ? c.cell + off : s.d_cell) : nullptr;
-        if (grid_pitch > 0)
-            rc = query_grid_device(g, table, grid_pitch, mode, s.d_q, n, ldq, s.d_comps, s.d_norm, s.d_grad, cell_dst,
-                                   s.d_rows, s.d_count, s.stream);
-        else
-            rc = query_device(g, table, mode, s.d_q, n, ldq, s.d_comps, s.d_norm, s.d_grad, cell_dst, s.d_rows,
-                              s.d_count, s.stream, current_query_variant());
+        rc = query_any_device(g, table, grid_pitch, mode, s.d_q, n, ldq, s.d_comps, s.d_norm, s.d_grad, cell_dst,
+                              s.d_rows, s.d_count, s.stream);
         if (rc) return abandon(ctx, rc);
         if (c.comps)
             ARB_CUDA_OR_ABANDON(cudaMemcpyAsync(c.comps_pinned ? c.comps + off * 3 : s.h_comps, s.d_comps, sizeof(double) * n * 3,
@@ -427,6 +500,7 @@ static int query_host_impl(const arb_geom* g, const double* table, int64_t grid_
         rc = retire(ctx.slot[i], c);
         if (rc) return abandon(ctx, rc);
     }
+    for (int i = 0; i < NSTAGE; ++i) ctx.stage[i].used = false;     // every H2D has completed (retire waited)
     return 0;
 }
 
@@ -434,6 +508,13 @@ extern "C" int arb_query_host(const arb_geom* g, const double* table, int mode, 
                               double* out_comps_host, double* out_norm_host, double* out_grad_host,
                               int64_t* out_cell_host, int64_t chunk_rows) {
     return query_host_impl(g, table, 0, mode, q_host, N, ldq, out_comps_host, out_norm_host, out_grad_host,
+                           out_cell_host, chunk_rows);
+}
+
+extern "C" int arb_query_nodes_host(const arb_geom* g, const double* nodes, int mode, double* q_host, int64_t N,
+                                    int64_t ldq, double* out_comps_host, double* out_norm_host, double* out_grad_host,
+                                    int64_t* out_cell_host, int64_t chunk_rows) {
+    return query_host_impl(g, nodes, -1, mode, q_host, N, ldq, out_comps_host, out_norm_host, out_grad_host,
                            out_cell_host, chunk_rows);
 }
 

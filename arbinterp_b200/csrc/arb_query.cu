@@ -22,8 +22,11 @@
 //             nested Horner scheme (LDS.128, conflict-free by a 16-byte slot skew).
 //   2  DIRECT: one query per thread reading its block straight from global memory
 //             (32 uncoalesced LDG.128 per component); kept as the naive baseline.
+#include <atomic>
+#include <mutex>
 #include "arb_device.cuh"
 #include "arb_gridfree.cuh"
+#include "arb_nodes.cuh"
 
 namespace arb {
 
@@ -242,16 +245,35 @@ __global__ void __launch_bounds__(THREADS) query_bulk_kernel(const QueryParams p
 // other.  DEDUP: lanes of a warp that want the same block elect one leader to fetch it and read
 // the leader's slot (warp-level binning by cell; free for clustered queries such as particle
 // bunches, one MATCH instruction of overhead for random ones).
-template <int D, int MODE, int THREADS, bool DEDUP, bool LOOPC = false>
-__global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams p) {
+// SLOTS < 32 (clustered batches: cell-sorted rows, particle bunches, trajectories): the distinct blocks a warp item
+// needs are numbered 0..K-1 and land in a ring of only SLOTS slots per warp (pass p fetches and evaluates the lanes
+// whose block number is in [p SLOTS, (p+1) SLOTS)), so a warp costs SLOTS x 528 B of shared memory instead of 16.5 KB
+// and 2-3 times as many warps are resident.  A clustered item has K <= SLOTS and takes one pass with every lane
+// evaluating; what limits it is not DRAM any more but the latency of the locate -> fetch -> evaluate chain per warp,
+// which the extra warps hide.  Uniformly random rows (K = 32) take 32 / SLOTS half-empty passes -- the launcher picks
+// SLOTS from a sortedness probe of the batch (probe_kernel).
+// PREFETCH: the coordinates of the warp's NEXT item are loaded while the current item's blocks are in flight.
+// FETCH_LDGSTS: a slot is filled by ONE warp-wide cp.async (32 lanes x 16 bytes, SASS LDGSTS) whose addresses come from
+// the owning lane over shuffles, instead of a per-lane cp.async.bulk -- the bulk copies take uniform registers, so
+// the compiler issues them in a serial ELECT / R2UR / UBLKCP loop (one trip per lane), while the LDGSTS loop has no
+// chain between its trips; it is also the only form that can gather a slot from several segments.
+// KIND_NODES: `table` is a node (Hermite) table (arb_nodes.cuh): a 3-D slot is the 4 x-pairs of corner nodes
+// (4 segments of 128 B), a 4-D slot the 2 x-pairs (cy = 0, 1) of one (cz, ct) (2 segments of 256 B); the four lanes
+// of a 4-D query own (cz, ct) and their shares add up.  QUIRK4 reproduces A.py:860 there.
+constexpr int KIND_CELLS = 0, KIND_NODES = 1;
+template <int D, int MODE, int THREADS, bool DEDUP, bool LOOPC = false, int SLOTS = 32, bool PREFETCH = false,
+          bool FETCH_LDGSTS = false, int KIND = KIND_CELLS, bool QUIRK4 = true>
+__global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams p, const int* __restrict__ gate, int gate_want) {
+    static_assert(KIND == KIND_CELLS || FETCH_LDGSTS, "node slots are gathered from several segments");
     constexpr int C = MODE == 0 ? 3 : (MODE == 1 ? 1 : 4);
     constexpr int SL = (D == 4) ? 4 : 1;          // tricubic blocks per component
     constexpr int QPW = 32 / SL;                  // queries per warp item
-    constexpr int NM = 64 * SL;
     constexpr uint32_t BYTES = 512;
     constexpr uint32_t SLOT = BYTES + 16;         // skew keeps LDS.128 conflict-free across lanes
+    static_assert(SLOTS == 32 || DEDUP, "the compact slot ring numbers the de-duplicated blocks");
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bars[THREADS / 32];
+    if (gate && *gate != gate_want) return;       // two launches, the probe's verdict picks the one that runs
 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int qi = lane / SL, sl = lane % SL;
@@ -261,6 +283,13 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
         fence_mbar_init();
     }
     __syncwarp();
+    unsigned char* const ring = smem + (size_t)wid * SLOTS * SLOT;
+    // LDGSTS: where this lane's 16 bytes of a slot come from, relative to the slot's first byte in global memory
+    int64_t lane_src = lane * 16;
+    if (KIND == KIND_NODES) {
+        if (D == 3) lane_src = (((lane >> 4) * p.nn[1] + ((lane >> 3) & 1)) * p.nn[0]) * 64 + (lane & 7) * 16;
+        else lane_src = (lane >> 4) * p.nn[0] * 128 + (lane & 15) * 16;
+    }
     const int64_t warp_global = ((int64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * THREADS) >> 5;
     const int64_t nbatch = (p.N + QPW - 1) / QPW;
@@ -268,42 +297,127 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
     // query); otherwise (batch, component) pairs are separate items (more independent items in flight).
     const int64_t nitem = LOOPC ? nbatch : nbatch * C;
     uint32_t phase = 0;
+    double cnext[D];
+    if (PREFETCH) {
+        const int64_t n0 = (LOOPC ? warp_global : warp_global / C) * QPW + qi;
+#pragma unroll
+        for (int a = 0; a < D; ++a) cnext[a] = (warp_global < nitem && n0 < p.N) ? p.q[n0 * p.ldq + a] : 0.0;
+    }
     for (int64_t item = warp_global; item < nitem; item += nwarps) {
         const int64_t batch = LOOPC ? item : item / C;
         const int64_t n = batch * QPW + qi;
         Located<D> L;
         L.ok = false; L.masked = false; L.cell_global = 0; L.cell_local = 0;
-        if (n < p.N) L = locate<D>(p, n);
+        if (PREFETCH) {
+            if (n < p.N) L = locate_coords<D>(p, cnext);
+        } else {
+            if (n < p.N) L = locate<D>(p, n);
+        }
 #pragma unroll 1
       for (int ci = 0; ci < (LOOPC ? C : 1); ++ci) {
         const int comp = LOOPC ? ci : (int)(item - batch * C);
         const int64_t blk = (L.cell_local * C + comp) * SL + sl;      // 512-byte block number in the table
         int src_lane = lane;
-        bool fetch = L.ok;
+        bool leader = L.ok;
         if (DEDUP) {
             const unsigned peers = __match_any_sync(0xffffffffu, L.ok ? blk : (int64_t)(-1 - lane));
             src_lane = __ffs(peers) - 1;
-            fetch = L.ok && (src_lane == lane);
+            leader = L.ok && (src_lane == lane);
         }
-        const unsigned fmask = __ballot_sync(0xffffffffu, fetch);
-        if (lane == 0) mbar_expect_tx(bar, (uint32_t)__popc(fmask) * BYTES);
-        __syncwarp();
-        unsigned char* slot = smem + (size_t)(wid * 32 + lane) * SLOT;
-        if (fetch) bulk_g2s(slot, p.table + blk * 64, BYTES, bar);
+        int myslot = src_lane, mypass = 0, npass = 1;
+        if (SLOTS < 32) {
+            const unsigned lm = __ballot_sync(0xffffffffu, leader);
+            const int number = __popc(lm & ((1u << lane) - 1u));          // leaders: their block's number
+            const int mine = __shfl_sync(0xffffffffu, number, src_lane);
+            mypass = L.ok ? mine / SLOTS : 0;
+            myslot = mine % SLOTS;
+            npass = (__popc(lm) + SLOTS - 1) / SLOTS;
+            if (npass < 1) npass = 1;
+        }
         if (comp == 0 && sl == 0 && n < p.N) {
             if (p.out_cell) p.out_cell[n] = L.cell_global;
             if (L.masked) mask_row_in_place(p, n);
         }
-        mbar_wait(bar, phase);
-        phase ^= 1;
-        const double* cb = reinterpret_cast<const double*>(smem + (size_t)(wid * 32 + src_lane) * SLOT);
         const bool grad_comp = (MODE == 1) || (MODE == 2 && comp == 3);     // warp-uniform
         double g[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-        if (L.ok) {
-            if (grad_comp) eval_value_grad<3, true>(cb, L.frac, g);
-            else g[0] = eval_value<3, true>(cb, L.frac);
+        double f15[4] = {0.0, 0.0, 0.0, 0.0};                               // 4-D nodes: fxyzt of this lane's corners
+        const double* cb = reinterpret_cast<const double*>(ring + (size_t)myslot * SLOT);
+        const double* src = p.table + blk * 64;
+        if (KIND == KIND_NODES) {
+            if (D == 3) {
+                src = p.table + comp * p.node_comp_stride + ((L.idx[2] * p.nn[1] + L.idx[1]) * p.nn[0] + L.idx[0]) * 8;
+            } else {
+                const int64_t iz = L.idx[2] + (sl & 1), it = L.idx[D - 1] + (sl >> 1);
+                src = p.table + comp * p.node_comp_stride +
+                      (((it * p.nn[2] + iz) * p.nn[1] + L.idx[1]) * p.nn[0] + L.idx[0]) * 16;
+            }
         }
-        if (D == 4) {
+#pragma unroll 1
+        for (int pass = 0; pass < npass; ++pass) {
+            const bool active = (SLOTS == 32) || (mypass == pass);
+            const bool fetch = leader && active;
+            const unsigned fmask = __ballot_sync(0xffffffffu, fetch);
+            if (FETCH_LDGSTS) {
+                const unsigned long long src0 = reinterpret_cast<unsigned long long>(src);
+                const uint32_t dst0 = smem_u32(ring + (size_t)myslot * SLOT);
+                for (unsigned m = fmask; m; m &= m - 1) {
+                    const int o = __ffs(m) - 1;
+                    const unsigned long long s0 = __shfl_sync(0xffffffffu, src0, o);
+                    const uint32_t d0 = __shfl_sync(0xffffffffu, dst0, o);
+                    cp_async_16(d0 + lane * 16, reinterpret_cast<const char*>(s0) + lane_src);
+                }
+            } else {
+                if (lane == 0) mbar_expect_tx(bar, (uint32_t)__popc(fmask) * BYTES);
+                __syncwarp();
+                if (fetch) bulk_g2s(ring + (size_t)myslot * SLOT, src, BYTES, bar);
+            }
+            if (PREFETCH && pass == 0 && ci == 0) {       // next item's coordinates: in flight during the wait
+                const int64_t nx_item = item + nwarps;
+                const int64_t n1 = (LOOPC ? nx_item : nx_item / C) * QPW + qi;
+                if (nx_item < nitem && n1 < p.N) {
+#pragma unroll
+                    for (int a = 0; a < D; ++a) cnext[a] = p.q[n1 * p.ldq + a];
+                }
+            }
+            if (FETCH_LDGSTS) {
+                cp_async_wait_all();
+                __syncwarp();
+            } else {
+                mbar_wait(bar, phase);
+                phase ^= 1;
+            }
+            if (L.ok && active) {
+                if (KIND == KIND_NODES) {
+                    if (D == 3) {
+                        if (grad_comp) nodes::eval3<true>(cb, L.frac, g);
+                        else nodes::eval3<false>(cb, L.frac, g);
+                    } else {
+                        if (grad_comp) nodes::eval4_lane<true, false>(cb, sl & 1, sl >> 1, L.frac, 0.0, g);
+                        else nodes::eval4_lane<false, false>(cb, sl & 1, sl >> 1, L.frac, 0.0, g);
+                        if (QUIRK4) { f15[0] = cb[15]; f15[1] = cb[31]; f15[2] = cb[47]; f15[3] = cb[63]; }
+                    }
+                } else {
+                    if (grad_comp) eval_value_grad<3, true>(cb, L.frac, g);
+                    else g[0] = eval_value<3, true>(cb, L.frac);
+                }
+            }
+            __syncwarp();   // every lane is done with the slots before the next copies land
+        }
+        if (D == 4 && KIND == KIND_NODES) {
+            if (QUIRK4) {       // A.py:860: the fxyzt slot of corner c holds fxyzt(c - 1); the lane before owns c - 1 of our first corner
+                const double up = __shfl_up_sync(0xffffffffu, f15[3], 1);
+                if (grad_comp) nodes::quirk4_lane<true>(f15, sl ? up : 0.0, sl & 1, sl >> 1, L.frac, g);
+                else nodes::quirk4_lane<false>(f15, sl ? up : 0.0, sl & 1, sl >> 1, L.frac, g);
+            }
+            const int nred = grad_comp ? 5 : 1;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                if (i < nred) {
+                    g[i] += __shfl_xor_sync(0xffffffffu, g[i], 1);
+                    g[i] += __shfl_xor_sync(0xffffffffu, g[i], 2);
+                }
+            }
+        } else if (D == 4) {
             const double s = L.frac[D - 1];
             const double w = pow_sel(s, sl), dw = dpow_sel(s, sl);
             g[4] = g[0] * dw;
@@ -328,8 +442,29 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
                 for (int a = 0; a < D; ++a) p.out_grad[n * D + a] = L.ok ? __ddiv_rn(g[1 + a], p.h[a]) : nan;
             }
         }
-        __syncwarp();   // every lane is done with the slots before the next item's copies land
       }
+    }
+}
+
+// Sortedness probe: 64 windows of 33 consecutive rows spread over the batch; a lane compares the cell of its row
+// with the next row's.  *verdict = 1 when at least half of the sampled neighbours share a cell (cell-sorted or
+// bunched batches: on average a warp item then needs <= 16 distinct blocks), else 0.
+template <int D>
+__global__ void __launch_bounds__(256) probe_kernel(const QueryParams p, int* verdict) {
+    __shared__ int hits[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int same = 0;
+    for (int w = wid; w < 64; w += 8) {
+        const int64_t base = (p.N - 33) * (int64_t)w / 63;
+        const Located<D> a = locate<D>(p, base + lane), b = locate<D>(p, base + lane + 1);
+        same += __popc(__ballot_sync(0xffffffffu, a.cell_global == b.cell_global && a.ok));
+    }
+    if (lane == 0) hits[wid] = same;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int i = 0; i < 8; ++i) tot += hits[i];
+        *verdict = (tot >= 64 * 32 / 2) ? 1 : 0;
     }
 }
 
@@ -652,17 +787,48 @@ static int launch_bulk(const QueryParams& p, cudaStream_t st) {
     return check_cuda(cudaGetLastError(), "query_bulk_kernel launch");
 }
 
-template <int D, int MODE, int THREADS, bool DEDUP, bool LOOPC = false>
-static int launch_block(const QueryParams& p, cudaStream_t st) {
+template <int D, int MODE, int THREADS, bool DEDUP, bool LOOPC = false, int SLOTS = 32, bool PREFETCH = false,
+          bool FETCH_LDGSTS = false, int KIND = KIND_CELLS, bool QUIRK4 = true>
+static int launch_block(const QueryParams& p, cudaStream_t st, const int* gate = nullptr, int gate_want = 0) {
     constexpr int C = MODE == 0 ? 3 : (MODE == 1 ? 1 : 4);
     constexpr int QPW = (D == 4) ? 8 : 32;
-    const size_t smem = (size_t)THREADS * 528;
-    auto k = query_block_kernel<D, MODE, THREADS, DEDUP, LOOPC>;
+    const size_t smem = (size_t)(THREADS / 32) * SLOTS * 528;
+    auto k = query_block_kernel<D, MODE, THREADS, DEDUP, LOOPC, SLOTS, PREFETCH, FETCH_LDGSTS, KIND, QUIRK4>;
     static LaunchCache cache = {};
     const int64_t items = ((p.N + QPW - 1) / QPW) * (LOOPC ? 1 : C);
     const int grid = persistent_grid(k, THREADS, smem, (items + THREADS / 32 - 1) / (THREADS / 32), cache);
-    k<<<grid, THREADS, smem, st>>>(p);
+    k<<<grid, THREADS, smem, st>>>(p, gate, gate_want);
     return check_cuda(cudaGetLastError(), "query_block_kernel launch");
+}
+
+// One verdict word per launch, taken round-robin from a small per-device ring (launches of one stream are ordered;
+// the host-buffer path keeps three streams busy, far fewer than the ring holds).
+static int* probe_word() {
+    static int* ring[16] = {};
+    static std::atomic<unsigned> next{0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    int*& r = ring[dev & 15];
+    if (!r) {
+        static std::mutex m;
+        std::lock_guard<std::mutex> lk(m);
+        if (!r && cudaMalloc(&r, 256 * sizeof(int)) != cudaSuccess) { cudaGetLastError(); r = nullptr; return nullptr; }
+    }
+    return r + (next.fetch_add(1) & 255u);
+}
+
+// Default launch: large batches are probed for clustering on the device and the matching kernel runs (the other
+// launch returns at once); no host synchronisation.
+template <int D, int MODE, bool LOOPC, int SLOTS>
+static int launch_auto(const QueryParams& p, cudaStream_t st) {
+    int* word = (p.N >= (1 << 16)) ? probe_word() : nullptr;
+    if (!word) return launch_block<D, MODE, 128, true, LOOPC>(p, st);
+    probe_kernel<D><<<1, 256, 0, st>>>(p, word);
+    int rc = check_cuda(cudaGetLastError(), "probe_kernel launch");
+    if (rc) return rc;
+    rc = launch_block<D, MODE, 128, true, LOOPC>(p, st, word, 0);
+    if (rc) return rc;
+    return launch_block<D, MODE, 128, true, LOOPC, SLOTS, true>(p, st, word, 1);
 }
 
 template <int D, int C, int MODE>
@@ -691,11 +857,28 @@ static int dispatch_variant(const QueryParams& p, cudaStream_t st, int variant) 
         case 22: return launch_block<D, MODE, 192, true>(p, st);
         case 23: return launch_block<D, MODE, 384, true>(p, st);
         case 30: return launch_block<D, MODE, 128, true, true>(p, st);
-        default:
-            // 4-D: one locate per query and its components fetched in turn (+8 % in 'both');
-            // 3-D: (batch, component) items are independent (profiles/r01_variant_sweep.log)
+        case 24: return launch_block<D, MODE, 128, true, D == 4, 32, true>(p, st);      // default + coordinate prefetch
+        case 40: return launch_block<D, MODE, 128, true, D == 4, 16>(p, st);            // compact slot rings, forced
+        case 41: return launch_block<D, MODE, 128, true, D == 4, 12>(p, st);
+        case 42: return launch_block<D, MODE, 128, true, D == 4, 8>(p, st);
+        case 43: return launch_block<D, MODE, 128, true, D == 4, 16, true>(p, st);
+        case 44: return launch_block<D, MODE, 128, true, D == 4, 12, true>(p, st);
+        case 45: return launch_block<D, MODE, 128, true, D == 4, 8, true>(p, st);
+        case 60: return launch_block<D, MODE, 128, true, D == 4, 32, false, true>(p, st);  // warp-wide LDGSTS instead of bulk copies
+        case 61: return launch_block<D, MODE, 128, true, D == 4, 32, true, true>(p, st);
+        case 62: return launch_block<D, MODE, 128, true, D == 4, 16, true, true>(p, st);
+        case 63: return launch_block<D, MODE, 128, true, D == 4, 12, true, true>(p, st);
+        case 50: return launch_auto<D, MODE, D == 4, 16>(p, st);                        // probe picks 32 or 16 slots
+        case 51: return launch_auto<D, MODE, D == 4, 12>(p, st);
+        case 25:    // round-1 default: 32 slots per warp, no probe
             if constexpr (D == 4) return launch_block<D, MODE, 128, true, true>(p, st);
             else return launch_block<D, MODE, 128, true, false>(p, st);
+        default:
+            // batches of >= 2^16 rows are probed for clustering on the device: 32 slots per warp for scattered rows
+            // (4-D: one locate per query and its components fetched in turn, +8 % in 'both'; 3-D: (batch, component)
+            // items are independent, profiles/r01_variant_sweep.log), 16-slot rings + coordinate prefetch for
+            // clustered ones (profiles/r02_cluster_bench.log)
+            return launch_auto<D, MODE, D == 4, 16>(p, st);
     }
 }
 
@@ -727,6 +910,11 @@ int fill_params(const char* who, const arb_geom* g, bool need_table, const doubl
         p.total_cells *= g->ncell[a];
         if (a < g->d - 1) p.layer_cells *= g->ncell[a];
     }
+    p.node_comp_stride = (g->d == 3) ? 8 : 16;
+    for (int a = 0; a < 4; ++a) {
+        p.nn[a] = (a < g->d) ? g->ncell[a] + 1 : 1;
+        p.node_comp_stride *= p.nn[a];
+    }
     p.slab_lo = g->slab_lo; p.slab_hi = g->slab_hi;
     if (p.slab_lo < 0 || p.slab_hi > g->ncell[g->d - 1] || p.slab_lo >= p.slab_hi) {
         set_error("%s: bad slab [%lld,%lld)", who, (long long)p.slab_lo, (long long)p.slab_hi);
@@ -750,6 +938,41 @@ int query_device(const arb_geom* g, const double* table, int mode, double* q, in
     if (mode == ARB_MODE_VECTOR) return dispatch_variant<4, 3, 0>(p, st, variant);
     if (mode == ARB_MODE_NORM) return dispatch_variant<4, 1, 1>(p, st, variant);
     return dispatch_variant<4, 4, 2>(p, st, variant);
+}
+
+// Node (Hermite) table queries (arb_nodes.cuh).  variant: 0 = default, 1 = without coordinate prefetch,
+// 2 = compact 16-slot rings.
+template <int D, int MODE>
+static int dispatch_nodes(const QueryParams& p, cudaStream_t st, int variant, bool quirk) {
+    constexpr bool LC = (D == 4);
+    if (D == 4 && !quirk) return launch_block<D, MODE, 128, true, LC, 32, true, true, KIND_NODES, false>(p, st);
+    switch (variant) {
+        case 71: return launch_block<D, MODE, 128, true, LC, 32, false, true, KIND_NODES>(p, st);
+        case 72: return launch_block<D, MODE, 128, true, LC, 16, true, true, KIND_NODES>(p, st);
+        case 73: return launch_block<D, MODE, 128, false, LC, 32, true, true, KIND_NODES>(p, st);
+        default: return launch_block<D, MODE, 128, true, LC, 32, true, true, KIND_NODES>(p, st);
+    }
+}
+
+int query_nodes_device(const arb_geom* g, const double* nodes, int mode, double* q, int64_t N, int64_t ldq,
+                       double* out_comps, double* out_norm, double* out_grad, int64_t* out_cell, int64_t* masked_rows,
+                       unsigned long long* masked_count, cudaStream_t st) {
+    QueryParams p;
+    const int rc = fill_params("arb_query_nodes", g, true, nodes, mode, q, N, ldq, out_comps, out_norm, out_grad,
+                               out_cell, masked_rows, masked_count, p);
+    if (rc) return rc < 0 ? 0 : rc;
+    if (g->slab_lo != 0 || g->slab_hi != g->ncell[g->d - 1]) { set_error("arb_query_nodes: slabs are not supported (a node table is small enough to replicate)"); return 1; }
+    if (reinterpret_cast<uintptr_t>(nodes) & 15) { set_error("arb_query_nodes: node table must be 16-byte aligned"); return 1; }
+    const bool quirk = !(g->flags & ARB_GEOM_FIXED_D4);
+    const int v = g_query_variant;
+    if (g->d == 3) {
+        if (mode == ARB_MODE_VECTOR) return dispatch_nodes<3, 0>(p, st, v, quirk);
+        if (mode == ARB_MODE_NORM) return dispatch_nodes<3, 1>(p, st, v, quirk);
+        return dispatch_nodes<3, 2>(p, st, v, quirk);
+    }
+    if (mode == ARB_MODE_VECTOR) return dispatch_nodes<4, 0>(p, st, v, quirk);
+    if (mode == ARB_MODE_NORM) return dispatch_nodes<4, 1>(p, st, v, quirk);
+    return dispatch_nodes<4, 2>(p, st, v, quirk);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -862,6 +1085,13 @@ int arb_query_grid(const arb_geom* g, const double* grid, int64_t pitch_x, int m
                    unsigned long long* masked_count, void* stream) {
     return arb::query_grid_device(g, grid, pitch_x, mode, q, N, ldq, out_comps, out_norm, out_grad, out_cell,
                                   masked_rows, masked_count, (cudaStream_t)stream);
+}
+
+int arb_query_nodes(const arb_geom* g, const double* nodes, int mode, double* q, int64_t N, int64_t ldq,
+                    double* out_comps, double* out_norm, double* out_grad, int64_t* out_cell, int64_t* masked_rows,
+                    unsigned long long* masked_count, void* stream) {
+    return arb::query_nodes_device(g, nodes, mode, q, N, ldq, out_comps, out_norm, out_grad, out_cell, masked_rows,
+                                   masked_count, (cudaStream_t)stream);
 }
 
 int arb_query(const arb_geom* g, const double* table, int mode, double* q, int64_t N, int64_t ldq, double* out_comps,

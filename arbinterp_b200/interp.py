@@ -18,6 +18,8 @@ Differences a user can observe, all documented in DESIGN.md:
   * ``tricubic(..., table=False)`` / ``quadcubic(..., table=False)`` keep no coefficient table at all and
     evaluate every query from its 4^d grid neighbourhood (for fields that change often; CHANGELOG.md:9 of the
     reference); the 4-D form adds the rank-16 term that reproduces A.py:860 unless ``fixed_d4=True``;
+  * ``tricubic(..., table='nodes')`` / ``quadcubic(..., table='nodes')`` keep a node (Hermite) table instead: the
+    central-difference values of every grid point, 8x / 16x smaller than the cell table (csrc/arb_nodes.cuh);
   * ``save(path)`` / ``load(path)`` persist the coefficient table;
   * ``tricubic(field, devices=[0, 1, ...])`` keeps one replica of the table per listed GPU in this process and
     fans numpy range queries out over them (sharding.ReplicatedInterp / SlabShardedInterp are the
@@ -123,7 +125,15 @@ class _CubicInterpolator:
             raise ValueError(f"slab {slab} outside the {nslow} cell layers of the slowest axis")
         self._slab = (lo, hi)
         self._table_free = kwargs.get("table", True) is False
-        if self._table_free:
+        self._nodes = None
+        if isinstance(kwargs.get("table"), str):
+            if kwargs["table"] != "nodes":
+                raise ValueError("table must be True (cell coefficients), False (no table) or 'nodes' (Hermite node table)")
+            if (lo, hi) != (0, nslow):
+                raise ValueError("table='nodes' is available for unsharded interpolators only (it is small enough to replicate)")
+            self._table = None
+            self._build_nodes()
+        elif self._table_free:
             if (lo, hi) != (0, nslow):
                 raise ValueError("table=False is available for unsharded interpolators only")
             self._table = None
@@ -200,7 +210,9 @@ class _CubicInterpolator:
         for rep in getattr(self, "_replicas", [self])[1:]:
             rep.update_values(planes.T.to(rep._device), order="grid")
         del planes, dense
-        if self._table is None:
+        if self._nodes is not None:
+            self._build_nodes()
+        elif self._table is None:
             if self._pitch != geo.npts[0]:
                 self._planes = torch.nn.functional.pad(self._planes, (0, 1)).contiguous()
             torch.cuda.current_stream(self._device).synchronize()   # see __init__: lib streams do not order against torch's
@@ -304,6 +316,7 @@ class _CubicInterpolator:
             self._raw = None
             self._replicas = [self]
             self._table_free = False
+            self._nodes = None
             shape = tuple(int(v) for v in header["table_shape"])
             # the header is untrusted input: the table shape must be the one this geometry, slab and mode imply,
             # and the file must actually hold that many bytes, before anything is allocated
@@ -335,6 +348,30 @@ class _CubicInterpolator:
         self.queryInd = None
         self._bind_mode()
         return self
+
+    def _build_nodes(self):
+        """Node (Hermite) table ``[C][nt-2][nz-2][ny-2][nx-2][2^d]`` (csrc/arb_nodes.cuh): the central-difference
+        values f, fx, fy, fxy, ... of every interior grid point -- the rows of the reference's D matrix
+        (A.py:129-173 / 762-876) -- 8x / 16x smaller than the cell table, same answers to round-off."""
+        d, geo = self._d, self._geo
+        ncomp = self._planes.shape[0]
+        shape = [ncomp] + [geo.npts[a] - 2 for a in reversed(range(d))] + [2 ** d]
+        if self._nodes is None or list(self._nodes.shape) != shape:
+            self._nodes = torch.empty(shape, dtype=torch.float64, device=self._device)
+        n = (ctypes.c_int64 * 4)(*([geo.npts[a] for a in range(d)] + [1] * (4 - d)))
+        with torch.cuda.device(self._device):
+            stream = torch.cuda.current_stream(self._device).cuda_stream
+            _lib.check(self._lib.arb_build_nodes(d, self._planes.data_ptr(), ncomp, ctypes.byref(n), geo.npts[0],
+                                                  self._nodes.data_ptr(), stream), "arb_build_nodes")
+            torch.cuda.current_stream(self._device).synchronize()      # see _build_table
+        self._make_cgeom()
+
+    @property
+    def nodes(self) -> torch.Tensor:
+        """Device node table of a ``table='nodes'`` interpolator."""
+        if self._nodes is None:
+            raise AttributeError("this interpolator was not built with table='nodes'")
+        return self._nodes
 
     def _build_table(self):
         d, geo = self._d, self._geo
@@ -482,7 +519,11 @@ class _CubicInterpolator:
         cells = torch.empty(n, dtype=torch.int64, device=self._device)
         with torch.cuda.device(self._device):
             stream = torch.cuda.current_stream(self._device).cuda_stream
-            if self._table is None:
+            if self._nodes is not None:
+                _lib.check(self._lib.arb_query_nodes(ctypes.byref(self._cgeom), self._nodes.data_ptr(), self._mode_code,
+                                                     work.data_ptr(), n, work.shape[1], self._ptr(comps), self._ptr(norm),
+                                                     self._ptr(grad), cells.data_ptr(), None, None, stream), "arb_query_nodes")
+            elif self._table is None:
                 _lib.check(self._lib.arb_query_grid(ctypes.byref(self._cgeom), self._planes.data_ptr(), self._pitch,
                                                     self._mode_code, work.data_ptr(), n, work.shape[1],
                                                     self._ptr(comps), self._ptr(norm), self._ptr(grad),
@@ -523,7 +564,11 @@ class _CubicInterpolator:
             cells = torch.empty(n, dtype=torch.int64, device=dev)        # stays in HBM; read back lazily
             chunk = int(os.environ.get("ARB_HOST_CHUNK_ROWS", "0"))
             qptr = work.ctypes.data + lo * work.strides[0]
-            if self._table is None:
+            if self._nodes is not None:
+                _lib.check(self._lib.arb_query_nodes_host(ctypes.byref(self._cgeom), self._nodes.data_ptr(), self._mode_code,
+                                                          qptr, n, work.shape[1], row(comps), row(norm), row(grad),
+                                                          cells.data_ptr(), chunk), "arb_query_nodes_host")
+            elif self._table is None:
                 _lib.check(self._lib.arb_query_grid_host(ctypes.byref(self._cgeom), self._planes.data_ptr(), self._pitch,
                                                          self._mode_code, qptr, n, work.shape[1],
                                                          row(comps), row(norm), row(grad),
@@ -589,8 +634,12 @@ class _CubicInterpolator:
         if prev != self._device.index:                           # latency path: no context manager unless needed
             torch.cuda.set_device(self._device)
         try:
-            args = (ctypes.byref(self._cgeom), self._planes.data_ptr() if self._table is None else self._table.data_ptr())
-            if self._table is None:
+            args = (ctypes.byref(self._cgeom), self._nodes.data_ptr() if self._nodes is not None else
+                    self._planes.data_ptr() if self._table is None else self._table.data_ptr())
+            if self._nodes is not None:
+                rc = self._lib.arb_query_nodes_host(*args, self._mode_code, work.ctypes.data, n, work.shape[1],
+                                                    ptr(comps), ptr(norm), ptr(grad), cells.ctypes.data, 0)
+            elif self._table is None:
                 rc = self._lib.arb_query_grid_host(*args, self._pitch, self._mode_code, work.ctypes.data, n, work.shape[1],
                                                    ptr(comps), ptr(norm), ptr(grad), cells.ctypes.data, 0)
             else:

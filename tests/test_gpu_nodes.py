@@ -1,0 +1,203 @@
+"""GPU tier (-m gpu): the node (Hermite) table -- ``tricubic / quadcubic(..., table='nodes')``,
+csrc/arb_nodes.cuh + the KIND_NODES / LDGSTS form of query_block_kernel -- against the golden vectors of the live
+reference, the numpy oracle, and the cell-table path; and the new query-kernel variants (compact slot rings,
+coordinate prefetch, LDGSTS fetch, sortedness probe) against the golden vectors.
+
+Same bar as tests/test_gpu_parity.py: indices and NaN masks exact, values within 1e-12 scaled."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from test_gpu_parity import (CASES, _analytic_field3, _analytic_field4, _check_outputs, _cls, _golden_ref, _scales,
+                             _uniform_queries)
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.mark.parametrize("name,d,modes", CASES)
+def test_node_table_golden(name, d, modes):
+    """Golden vectors of the live reference (in-volume, out-of-volume, NaN, +-inf rows, extra query columns); the 4-D
+    cases carry an xyzt term, so the A.py:860 correction of the node path is exercised."""
+    g = load_golden(name)
+    for mode in modes:
+        kw = {} if mode == "scalar" else {"mode": mode}
+        obj = _cls(d)(g["field"].copy(), "quiet", table="nodes", **kw)
+        q = g[mode + "_q_in"].copy()
+        res = obj.Query(q)
+        _check_outputs(res, _golden_ref(g, mode), mode, g["field"], d, g["h"], f"{name}/{mode}/nodes")
+        assert np.array_equal(q, g[mode + "_q_after"], equal_nan=True)
+        assert np.array_equal(obj.queryInds, g[mode + "_inds"])
+        with pytest.raises(AttributeError):
+            obj.table
+        npts = [int(v) + 3 for v in g["ncell_axis"]]
+        ncomp = {"vector": 3, "norm": 1, "both": 4, "scalar": 1}[mode]
+        assert list(obj.nodes.shape) == [ncomp] + [n - 2 for n in reversed(npts)] + [2 ** d]
+    with pytest.raises(ValueError):
+        _cls(d)(g["field"].copy(), "quiet", table="nodes", slab=(0, 1))
+    with pytest.raises(ValueError):
+        _cls(d)(g["field"].copy(), "quiet", table="cells")
+
+
+def test_node_values_are_the_rows_of_D():
+    """The stored node values are D applied at the node (A.py:129-173): f, fx = (f[+1] - f[-1]) / 2, fxy, ... in
+    tau = tx + 2 ty + 4 tz order."""
+    from arbinterp_b200 import tricubic
+    rng = np.random.default_rng(5)
+    nx, ny, nz = 9, 7, 8
+    field = _analytic_field3(nx, ny, nz)
+    vals = rng.standard_normal(nx * ny * nz)
+    field = np.concatenate([field[:, :3], vals[:, None]], axis=1)
+    obj = tricubic(field, "quiet", table="nodes")
+    got = obj.nodes.cpu().numpy()[0]                       # [nz-2][ny-2][nx-2][8]
+    f = vals.reshape(nz, ny, nx)
+    c = (slice(1, -1),) * 3
+    dx = lambda a: 0.5 * (a[:, :, 2:] - a[:, :, :-2])
+    dy = lambda a: 0.5 * (a[:, 2:, :] - a[:, :-2, :])
+    dz = lambda a: 0.5 * (a[2:, :, :] - a[:-2, :, :])
+    want = {0: f[c], 1: dx(f)[1:-1, 1:-1], 2: dy(f)[1:-1, :, 1:-1], 3: dx(dy(f))[1:-1], 4: dz(f)[:, 1:-1, 1:-1],
+            5: dx(dz(f))[:, 1:-1], 6: dy(dz(f))[:, :, 1:-1], 7: dx(dy(dz(f)))}
+    for tau, w in want.items():
+        assert np.allclose(got[..., tau], w, rtol=0, atol=1e-14), tau
+
+
+@pytest.mark.parametrize("mode", ["vector", "norm", "both"])
+@pytest.mark.parametrize("shape", [(37, 26, 23), (20, 41, 17)])
+def test_node_table_oracle_parity_3d(mode, shape):
+    from arbinterp_b200 import tricubic
+    from oracle.arb_oracle import OracleInterp
+    rng = np.random.default_rng(4321)
+    field = _analytic_field3(*shape, rng=rng)
+    obj = tricubic(field.copy(), "quiet", mode=mode, table="nodes")
+    q = _uniform_queries(obj, 3, 100_000, rng, extra=2)
+    q[::97, 1] = 5.0
+    q[::1013, 2] = np.nan
+    ora = OracleInterp(field, 3, mode=mode)
+    q_ref = q.copy()
+    ref = ora.query(q_ref)
+    ref = ref if isinstance(ref, tuple) else (ref,)
+    q_gpu = q.copy()
+    res = obj.Query(q_gpu)
+    worst = _check_outputs(res, ref, mode, field, 3, ora.geo.h, f"nodes 3d {shape} {mode}")
+    assert np.array_equal(q_gpu, q_ref, equal_nan=True)
+    assert np.array_equal(obj.queryInds, ora.query_inds)
+    assert worst < 1e-13
+    # device tensors and the host path agree bit for bit
+    dev = obj.Query(torch.from_numpy(q.copy()).cuda())
+    dev = dev if isinstance(dev, tuple) else (dev,)
+    res = res if isinstance(res, tuple) else (res,)
+    for x, y in zip(res, dev):
+        assert np.array_equal(x, y.cpu().numpy(), equal_nan=True)
+
+
+@pytest.mark.parametrize("fixed", [False, True])
+@pytest.mark.parametrize("mode", ["vector", "norm", "both"])
+def test_node_table_quadcubic_matches_cell_table(mode, fixed):
+    """4-D node path against the cell-table path on a field with an xyzt monomial: quirk and fixed_d4 answers differ
+    by ~1e-6, each must match its own table; and the quirk one must match the oracle."""
+    from arbinterp_b200 import quadcubic
+    rng = np.random.default_rng(31)
+    field = _analytic_field4(13, 9, 8, 7, rng=rng)
+    a = quadcubic(field.copy(), "quiet", mode=mode, fixed_d4=fixed)
+    b = quadcubic(field.copy(), "quiet", mode=mode, fixed_d4=fixed, table="nodes")
+    q = _uniform_queries(a, 4, 50_000, rng, extra=1)
+    q[::53, 3] = -1.0
+    qa, qb = q.copy(), q.copy()
+    ra, rb = a.Query(qa), b.Query(qb)
+    h = [a.hx, a.hy, a.hz, a.ht]
+    ra = ra if isinstance(ra, tuple) else (ra,)
+    _check_outputs(rb, ra, mode, field, 4, h, f"nodes vs cells 4d {mode} fixed={fixed}")
+    assert np.array_equal(qa, qb, equal_nan=True) and np.array_equal(a.queryInds, b.queryInds)
+    if not fixed:
+        from oracle.arb_oracle import OracleInterp
+        ora = OracleInterp(field, 4, mode=mode)
+        ref = ora.query(q[:10_000].copy())
+        ref = ref if isinstance(ref, tuple) else (ref,)
+        got = b.Query(q[:10_000].copy())
+        _check_outputs(got, ref, mode, field, 4, ora.geo.h, f"nodes vs oracle 4d {mode}")
+        assert np.array_equal(b.queryInds, ora.query_inds)
+
+
+def test_node_table_quirk_is_visible():
+    from arbinterp_b200 import quadcubic
+    field = _analytic_field4(9, 8, 8, 7)[:, [0, 1, 2, 3, 5]]          # the column with the x*y*z*t monomial
+    a = quadcubic(field.copy(), "quiet", table="nodes")
+    b = quadcubic(field.copy(), "quiet", table="nodes", fixed_d4=True)
+    rng = np.random.default_rng(3)
+    q = _uniform_queries(a, 4, 5000, rng)
+    va, _ = a.Query(q.copy())
+    vb, _ = b.Query(q.copy())
+    assert 1e-9 < np.abs(va - vb).max() < 1e-2
+
+
+@pytest.mark.parametrize("d", [3, 4])
+def test_node_table_update_values_and_small_batches(d):
+    """update_values() rebuilds the node table in place; single points, the zero-copy path (<= 256 rows) and the
+    latency path (<= 8192 rows) go through arb_query_nodes_host."""
+    rng = np.random.default_rng(8)
+    field = _analytic_field3(11, 9, 10, rng=rng) if d == 3 else _analytic_field4(8, 7, 6, 7, rng=rng)
+    obj = _cls(d)(field.copy(), "quiet", mode="both", table="nodes")
+    ref_obj = _cls(d)(field.copy(), "quiet", mode="both")
+    q = _uniform_queries(obj, d, 3000, rng)
+    h = [getattr(obj, "h" + c) for c in "xyzt"[:d]]
+    for n in (1, 20, 300, 3000):
+        _check_outputs(obj.Query(q[:n].copy()), ref_obj.Query(q[:n].copy()), "both", field, d, h, f"nodes small {n}")
+    one = obj.Query(q[0].copy())
+    want = ref_obj.Query(q[0].copy())
+    assert np.allclose(one[0], want[0], rtol=1e-12) and np.isclose(one[1], want[1], rtol=1e-12)
+    new_vals = field[:, d:] * 1.5 + 0.25
+    obj.update_values(new_vals)
+    fresh = _cls(d)(np.concatenate([field[:, :d], new_vals], axis=1), "quiet", mode="both", table="nodes")
+    for x, y in zip(obj.Query(q.copy()), fresh.Query(q.copy())):
+        assert np.array_equal(x, y, equal_nan=True)
+
+
+@pytest.mark.parametrize("variant", [24, 40, 41, 42, 43, 44, 45, 50, 51, 60, 61, 62, 63])
+@pytest.mark.parametrize("name,d,modes", CASES)
+def test_round2_kernel_variants_golden(name, d, modes, variant, cuda_lib):
+    """Compact slot rings (16 / 12 / 8 slots per warp, multi-pass when a warp item needs more blocks), coordinate
+    prefetch, the probed launch and the LDGSTS fetch answer like the default kernel."""
+    g = load_golden(name)
+    old = cuda_lib.arb_set_query_variant(variant)
+    try:
+        for mode in modes:
+            kw = {} if mode == "scalar" else {"mode": mode}
+            obj = _cls(d)(g["field"].copy(), "quiet", **kw)
+            q = g[mode + "_q_in"].copy()
+            res = obj.Query(q)
+            _check_outputs(res, _golden_ref(g, mode), mode, g["field"], d, g["h"], f"{name}/{mode}/v{variant}")
+            assert np.array_equal(q, g[mode + "_q_after"], equal_nan=True)
+            assert np.array_equal(obj.queryInds, g[mode + "_inds"])
+    finally:
+        cuda_lib.arb_set_query_variant(old)
+
+
+@pytest.mark.parametrize("variant", [40, 42, 50, 62, 71, 72, 73])
+def test_round2_variants_bit_identical_on_large_batches(variant, cuda_lib):
+    """2^20 rows (random, cell-sorted, bunched; masked and NaN rows mixed in): every variant of the cell-table kernel
+    does the same arithmetic as the default one, so outputs and indices are equal bit for bit -- whichever launch the
+    sortedness probe picks.  Variants 7x select the node-table kernel's forms and are compared with its default."""
+    from arbinterp_b200 import tricubic
+    rng = np.random.default_rng(17)
+    field = _analytic_field3(45, 38, 41, rng=rng)
+    obj = tricubic(field.copy(), "quiet", mode="both", **({"table": "nodes"} if variant >= 70 else {}))
+    n = 1 << 20
+    q = torch.from_numpy(_uniform_queries(obj, 3, n, rng)).cuda()
+    q[::1001] = 9.0
+    q[5::4099, 1] = float("nan")
+    obj.Query(q.clone())
+    order = torch.argsort(obj._last_cells)
+    centre = q[:64].mean(dim=0)
+    bunch = (centre + 0.05 * torch.randn(n, 3, dtype=torch.float64, device="cuda") * float(obj.hx)).contiguous()
+    for name, qq in (("random", q), ("sorted", q[order].contiguous()), ("bunch", bunch)):
+        base = obj.Query(qq.clone())
+        base_cells = obj._last_cells.clone()
+        old = cuda_lib.arb_set_query_variant(variant)
+        try:
+            got = obj.Query(qq.clone())
+        finally:
+            cuda_lib.arb_set_query_variant(old)
+        assert torch.equal(obj._last_cells, base_cells), name
+        for a, b in zip(got, base):
+            assert torch.equal(a.view(torch.int64), b.view(torch.int64)), (name, variant)
