@@ -1,8 +1,9 @@
 // Node (Hermite) table build: the 2^d central-difference values f, fx, fy, fxy, ... of every interior grid node
 // (the rows of the reference's D matrix, A.py:129-173 / 762-876, applied at the node instead of at the corners of
 // every cell).  One thread per (node, component): 3^d neighbourhood reads served by L1/L2 (the grid is read once
-// from HBM), 64 / 128 contiguous bytes written per thread with 16-byte streaming stores -- an HBM-write stream of
-// 8 (16) x the grid size, 8x / 16x smaller than the cell table the separable build kernels write.
+// from HBM), 64 / 128 contiguous bytes written per thread with 16-byte streaming stores (3-D: twice, every node is
+// the right half of one x-pair and the left half of the next) -- an HBM-write stream of 16 x the grid size, 4x (3-D) /
+// 16x (4-D) smaller than the cell table the separable build kernels write.
 #include "arb_common.cuh"
 #include "arb_nodes.cuh"
 
@@ -28,9 +29,25 @@ __global__ void __launch_bounds__(256) build_nodes_kernel(const double* __restri
         auto get = [&](int dx, int dy, int dz, int dt) { return __ldg(centre + dx + dy * sy + dz * sz + dt * st); };
         double v[T];
         nodes::node_stencil<D>(get, v);
-        double* dst = out + i * T;
+        if (D == 4) {
+            double* dst = out + i * T;
 #pragma unroll
-        for (int k = 0; k < T; k += 2) stg_stream_d2(dst + k, v[k], v[k + 1]);
+            for (int k = 0; k < T; k += 2) stg_stream_d2(dst + k, v[k], v[k + 1]);
+        } else {
+            // 3-D: x-pairs.  Pair ix holds nodes ix, ix + 1 in 128 aligned bytes, so a query's four rows are whole
+            // 128-byte lines (a 64-byte node at an odd position would make the L2 fill two lines for one: measured
+            // 730 instead of 536 DRAM bytes per query, profiles/r02_nodes3d_norm_ncu.txt before this layout)
+            const int64_t npair = m0 - 1;
+            double* row = out + ((c * m2 + z) * m1 + y) * npair * 16;
+            if (x < npair) {
+#pragma unroll
+                for (int k = 0; k < T; k += 2) stg_stream_d2(row + x * 16 + k, v[k], v[k + 1]);
+            }
+            if (x > 0) {
+#pragma unroll
+                for (int k = 0; k < T; k += 2) stg_stream_d2(row + (x - 1) * 16 + 8 + k, v[k], v[k + 1]);
+            }
+        }
     }
 }
 
@@ -40,7 +57,7 @@ int build_nodes_device(int d, const double* grid, int ncomp, const int64_t* npts
     for (int a = 0; a < d; ++a)
         if (npts[a] < 4) { set_error("arb_build_nodes: axis %d has %lld points, need >= 4", a, (long long)npts[a]); return 1; }
     if (pitch_x < npts[0]) { set_error("arb_build_nodes: pitch_x < nx"); return 1; }
-    if (reinterpret_cast<uintptr_t>(out) & 15) { set_error("arb_build_nodes: node table must be 16-byte aligned"); return 1; }
+    if (reinterpret_cast<uintptr_t>(out) & 127) { set_error("arb_build_nodes: node table must be 128-byte aligned"); return 1; }
     int64_t total = ncomp;
     for (int a = 0; a < d; ++a) total *= npts[a] - 2;
     int64_t blocks = (total + 255) / 256;

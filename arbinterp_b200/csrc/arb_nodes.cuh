@@ -1,7 +1,8 @@
 // Node (Hermite) table: instead of the 4^d monomial coefficients of every CELL (512 B / 2 KB per cell and
 // component) store the 2^d derivative values of every grid NODE -- f, fx, fy, fxy, ... as central differences in
 // unit-cell coordinates, i.e. exactly the rows of the reference's D matrix (A.py:129-173, 762-876) -- 64 B / 128 B
-// per node and component: 8x / 16x less memory, and neighbouring cells share their nodes in L2.
+// per node and component: 4x (3-D, nodes stored as aligned x-pairs) / 16x (4-D) less memory, and neighbouring cells
+// share their nodes in L2.
 //
 // The Lekien-Marsden polynomial of a cell is the tensor-product cubic Hermite interpolant of the b-vector
 // (that is what alpha = inv(B) b says, A.py:112-125,175), so a query can be evaluated straight from the 2^d corner
@@ -14,8 +15,11 @@
 // corner 0).  The nodes store the true fxyzt; the evaluation adds  sum_c Phi_c (fxyzt(c-1) - fxyzt(c)),
 // Phi_c = h1cx(u) h1cy(v) h1cz(w) h1ct(s) -- the same rank-16 term as arb_build_sep.cuh / arb_gridfree.cuh.
 //
-// Layout: table [C][nt'][nz'][ny'][nx'][T], n' = n - 2 nodes per axis (grid points 1..n-2, node i = grid point i+1,
-// so cell (ix, iy, ..) has corners at nodes (ix + cx, iy + cy, ..)), T = 2^d, tau = tx + 2 ty + 4 tz (+ 8 tt).
+// Layout: n' = n - 2 nodes per axis (grid points 1..n-2, node i = grid point i+1, so cell (ix, iy, ..) has corners at
+// nodes (ix + cx, iy + cy, ..)), T = 2^d values per node, tau = tx + 2 ty + 4 tz (+ 8 tt).
+//   4-D: [C][nt'][nz'][ny'][nx'][16]          (128 B per node: an x-pair is two whole 128-byte lines wherever it starts)
+//   3-D: [C][nz'][ny'][nx' - 1 x-pairs][2][8] (64 B per node: pair ix = nodes ix, ix + 1 stored together, 128 B aligned --
+//        every node twice, so that no x-pair straddles two lines; 4x smaller than the cell table instead of 8x)
 // A query's slot in shared memory is  [cz][cy][cx][tau]  (3-D, 64 doubles) or, per lane (cz, ct) of a 4-D query,
 // [cy][cx][tau] (64 doubles).  Everything here is __host__ __device__ so tests/host_emul/nodes_host_emul.cu runs it
 // on the CPU against alpha = A f.

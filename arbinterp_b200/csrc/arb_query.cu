@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(THREADS) query_bulk_kernel(const QueryParams p
 // the compiler issues them in a serial ELECT / R2UR / UBLKCP loop (one trip per lane), while the LDGSTS loop has no
 // chain between its trips; it is also the only form that can gather a slot from several segments.
 // KIND_NODES: `table` is a node (Hermite) table (arb_nodes.cuh): a 3-D slot is the 4 x-pairs of corner nodes
-// (4 segments of 128 B), a 4-D slot the 2 x-pairs (cy = 0, 1) of one (cz, ct) (2 segments of 256 B); the four lanes
+// (4 segments of 128 B, stored as 128-byte-aligned pairs), a 4-D slot the 2 x-pairs (cy = 0, 1) of one (cz, ct) (2 segments of 256 B); the four lanes
 // of a 4-D query own (cz, ct) and their shares add up.  QUIRK4 reproduces A.py:860 there.
 constexpr int KIND_CELLS = 0, KIND_NODES = 1;
 template <int D, int MODE, int THREADS, bool DEDUP, bool LOOPC = false, int SLOTS = 32, bool PREFETCH = false,
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
     // LDGSTS: where this lane's 16 bytes of a slot come from, relative to the slot's first byte in global memory
     int64_t lane_src = lane * 16;
     if (KIND == KIND_NODES) {
-        if (D == 3) lane_src = (((lane >> 4) * p.nn[1] + ((lane >> 3) & 1)) * p.nn[0]) * 64 + (lane & 7) * 16;
+        if (D == 3) lane_src = (((lane >> 4) * p.nn[1] + ((lane >> 3) & 1)) * p.nc[0]) * 128 + (lane & 7) * 16;
         else lane_src = (lane >> 4) * p.nn[0] * 128 + (lane & 15) * 16;
     }
     const int64_t warp_global = ((int64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
         const double* src = p.table + blk * 64;
         if (KIND == KIND_NODES) {
             if (D == 3) {
-                src = p.table + comp * p.node_comp_stride + ((L.idx[2] * p.nn[1] + L.idx[1]) * p.nn[0] + L.idx[0]) * 8;
+                src = p.table + comp * p.node_comp_stride + ((L.idx[2] * p.nn[1] + L.idx[1]) * p.nc[0] + L.idx[0]) * 16;
             } else {
                 const int64_t iz = L.idx[2] + (sl & 1), it = L.idx[D - 1] + (sl >> 1);
                 src = p.table + comp * p.node_comp_stride +
@@ -358,13 +358,19 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
             const bool fetch = leader && active;
             const unsigned fmask = __ballot_sync(0xffffffffu, fetch);
             if (FETCH_LDGSTS) {
-                const unsigned long long src0 = reinterpret_cast<unsigned long long>(src);
-                const uint32_t dst0 = smem_u32(ring + (size_t)myslot * SLOT);
-                for (unsigned m = fmask; m; m &= m - 1) {
-                    const int o = __ffs(m) - 1;
-                    const unsigned long long s0 = __shfl_sync(0xffffffffu, src0, o);
-                    const uint32_t d0 = __shfl_sync(0xffffffffu, dst0, o);
-                    cp_async_16(d0 + lane * 16, reinterpret_cast<const char*>(s0) + lane_src);
+                // one shuffle per slot: the owner's source as a 32-bit count of 16-byte units from the table base
+                // (tables < 64 GB), the destination packed beside it when the ring is compact; the 32 trips are
+                // unrolled and independent of each other (warp-uniform predicate from the ballot)
+                const uint32_t src16 = (uint32_t)((reinterpret_cast<const char*>(src) - reinterpret_cast<const char*>(p.table)) >> 4);
+                const char* const lane_base = reinterpret_cast<const char*>(p.table) + lane_src;
+                const uint32_t ring0 = smem_u32(ring) + lane * 16;
+#pragma unroll 8
+                for (int o = 0; o < 32; ++o) {
+                    if ((fmask >> o) & 1u) {
+                        const uint32_t s16 = __shfl_sync(0xffffffffu, src16, o);
+                        const uint32_t slot_o = (SLOTS == 32) ? (uint32_t)o : (uint32_t)__shfl_sync(0xffffffffu, myslot, o);
+                        cp_async_16(ring0 + slot_o * SLOT, lane_base + ((size_t)s16 << 4));
+                    }
                 }
             } else {
                 if (lane == 0) mbar_expect_tx(bar, (uint32_t)__popc(fmask) * BYTES);
@@ -910,10 +916,11 @@ int fill_params(const char* who, const arb_geom* g, bool need_table, const doubl
         p.total_cells *= g->ncell[a];
         if (a < g->d - 1) p.layer_cells *= g->ncell[a];
     }
-    p.node_comp_stride = (g->d == 3) ? 8 : 16;
+    // node table (arb_nodes.cuh): 3-D [C][nz-2][ny-2][nx-3 x-pairs][2][8], 4-D [C][nt-2][nz-2][ny-2][nx-2][16]
+    p.node_comp_stride = 16;
     for (int a = 0; a < 4; ++a) {
         p.nn[a] = (a < g->d) ? g->ncell[a] + 1 : 1;
-        p.node_comp_stride *= p.nn[a];
+        p.node_comp_stride *= (a == 0 && g->d == 3) ? g->ncell[0] : p.nn[a];
     }
     p.slab_lo = g->slab_lo; p.slab_hi = g->slab_hi;
     if (p.slab_lo < 0 || p.slab_hi > g->ncell[g->d - 1] || p.slab_lo >= p.slab_hi) {
@@ -962,7 +969,7 @@ int query_nodes_device(const arb_geom* g, const double* nodes, int mode, double*
                                out_cell, masked_rows, masked_count, p);
     if (rc) return rc < 0 ? 0 : rc;
     if (g->slab_lo != 0 || g->slab_hi != g->ncell[g->d - 1]) { set_error("arb_query_nodes: slabs are not supported (a node table is small enough to replicate)"); return 1; }
-    if (reinterpret_cast<uintptr_t>(nodes) & 15) { set_error("arb_query_nodes: node table must be 16-byte aligned"); return 1; }
+    if (reinterpret_cast<uintptr_t>(nodes) & 127) { set_error("arb_query_nodes: node table must be 128-byte aligned"); return 1; }
     const bool quirk = !(g->flags & ARB_GEOM_FIXED_D4);
     const int v = g_query_variant;
     if (g->d == 3) {

@@ -19,7 +19,7 @@ Differences a user can observe, all documented in DESIGN.md:
     evaluate every query from its 4^d grid neighbourhood (for fields that change often; CHANGELOG.md:9 of the
     reference); the 4-D form adds the rank-16 term that reproduces A.py:860 unless ``fixed_d4=True``;
   * ``tricubic(..., table='nodes')`` / ``quadcubic(..., table='nodes')`` keep a node (Hermite) table instead: the
-    central-difference values of every grid point, 8x / 16x smaller than the cell table (csrc/arb_nodes.cuh);
+    central-difference values of every grid point, 4x / 16x smaller than the cell table (csrc/arb_nodes.cuh);
   * ``save(path)`` / ``load(path)`` persist the coefficient table;
   * ``tricubic(field, devices=[0, 1, ...])`` keeps one replica of the table per listed GPU in this process and
     fans numpy range queries out over them (sharding.ReplicatedInterp / SlabShardedInterp are the
@@ -350,12 +350,16 @@ class _CubicInterpolator:
         return self
 
     def _build_nodes(self):
-        """Node (Hermite) table ``[C][nt-2][nz-2][ny-2][nx-2][2^d]`` (csrc/arb_nodes.cuh): the central-difference
-        values f, fx, fy, fxy, ... of every interior grid point -- the rows of the reference's D matrix
-        (A.py:129-173 / 762-876) -- 8x / 16x smaller than the cell table, same answers to round-off."""
+        """Node (Hermite) table (csrc/arb_nodes.cuh): the central-difference values f, fx, fy, fxy, ... of every
+        interior grid point -- the rows of the reference's D matrix (A.py:129-173 / 762-876).  4-D:
+        ``[C][nt-2][nz-2][ny-2][nx-2][16]``, 16x smaller than the cell table; 3-D: ``[C][nz-2][ny-2][nx-3][2][8]``
+        (x-adjacent nodes stored as 128-byte-aligned pairs), 4x smaller.  Same answers to round-off."""
         d, geo = self._d, self._geo
         ncomp = self._planes.shape[0]
-        shape = [ncomp] + [geo.npts[a] - 2 for a in reversed(range(d))] + [2 ** d]
+        if d == 3:          # aligned x-pairs: [C][nz-2][ny-2][nx-3][2][8]
+            shape = [ncomp, geo.npts[2] - 2, geo.npts[1] - 2, geo.npts[0] - 3, 2, 8]
+        else:
+            shape = [ncomp] + [geo.npts[a] - 2 for a in reversed(range(d))] + [16]
         if self._nodes is None or list(self._nodes.shape) != shape:
             self._nodes = torch.empty(shape, dtype=torch.float64, device=self._device)
         n = (ctypes.c_int64 * 4)(*([geo.npts[a] for a in range(d)] + [1] * (4 - d)))

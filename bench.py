@@ -621,6 +621,19 @@ def run_sharded(torch, dist, args, rank, world, device):
     out["global_indices_equal_oracle"] = bool(flags[0].item())
     out["cropped_values_within_1e-12"] = bool(flags[1].item())
 
+    # ---- the same field as a REPLICATED node (Hermite) table (csrc/arb_nodes.cuh): 16x smaller than the cell table,
+    # so every rank holds all of it and answers its own rows with no exchange at all
+    from arbinterp_b200.sharding import ReplicatedInterp
+    rows = field4_rows(torch, shape, device)[1] if rank == 0 else None
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    rep = ReplicatedInterp(quadcubic, rows, "quiet", mode="both", table="nodes", device=device)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t_build_nodes = time.perf_counter() - t0
+    del rows
+    torch.cuda.empty_cache()
+
     # ---- throughput: trajectory-like queries (P particles per rank, smooth random walk reflected into the volume,
     # time advancing and wrapping), routed to the slab owners and back
     n = args.sharded_particles
@@ -635,6 +648,7 @@ def run_sharded(torch, dist, args, rank, world, device):
     span = (hi_t - lo_t) * (1 - 1e-9)
     timing = {}
     step_ms = []
+    node_ms = []
     finite = True
     for step in range(args.warmup + args.steps):
         pos = pos + vel + 0.002 * (hi_t - lo_t) * torch.randn(n, 4, generator=gen, dtype=torch.float64, device=device) * only_space
@@ -650,9 +664,25 @@ def run_sharded(torch, dist, args, rank, world, device):
         res = obj.Query(q, timing=timing if timed else None)
         e1.record()
         torch.cuda.synchronize()
+        dist.barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        res_n = rep.Query(q)
+        e3.record()
+        torch.cuda.synchronize()
         if timed:
             step_ms.append(e0.elapsed_time(e1))
+            node_ms.append(e2.elapsed_time(e3))
             finite &= all(bool(torch.isfinite(r).all()) for r in res)
+    # the two answers to the last step's rows agree (cell table, routed / node table, local)
+    m = min(n, 200_000)
+    node_err = scaled_error(tuple(r[:m].cpu().numpy() for r in res_n), tuple(r[:m].cpu().numpy() for r in res), 4,
+                            g.h, float(torch.stack([r.abs().max() for r in res[:2]]).max()))
+    same_cells = bool(torch.equal(rep.local._last_cells, obj._last_cells))
+    tn = torch.tensor([sum(node_ms), node_err, float(not same_cells)], dtype=torch.float64, device=device)
+    dist.all_reduce(tn, op=dist.ReduceOp.MAX)
+    node_s, node_err, cells_differ = float(tn[0]) / 1e3, float(tn[1]), bool(tn[2] > 0)
+    node_gb = rep.local.nodes.numel() * 8 / 1e9
     t = torch.tensor([sum(step_ms)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_s = float(t.item()) / 1e3
@@ -677,8 +707,17 @@ def run_sharded(torch, dist, args, rank, world, device):
             "kernel": ph[5], "all_to_all (counts + rows + results)": ph[2] + ph[4] + ph[6],
             "sort + permute + scatter": ph[1] + ph[3] + ph[7], "owner + unpack": ph[0] + ph[8]},
         "kernel_frac_of_measured_hbm": (ALG_BYTES[(4, "both")] * n / (ph[5] * 1e-3) / 1e9 / measured_peak()[0]) if ph[5] > 0 else None,
+        "replicated_node_table": {
+            "what": "the same field as a node (Hermite) table replicated on every rank (quadcubic(table='nodes') via "
+                    "sharding.ReplicatedInterp): each rank answers its own rows, no exchange; same queries as above",
+            "value": world * n * args.steps / node_s, "unit": "queries/s", "ms_per_step": 1e3 * node_s / args.steps,
+            "node_table_gb_per_rank": node_gb, "construction_s": t_build_nodes,
+            "speedup_over_slab_sharded": total_s / node_s,
+            "frac_of_measured_hbm": ALG_BYTES[(4, "both")] * n * args.steps / node_s / 1e9 / measured_peak()[0],
+            "max_scaled_diff_vs_slab_sharded": node_err, "tolerance": 1e-12, "cell_indices_equal": not cells_differ,
+            "ok": bool(node_err <= 1e-12 and not cells_differ)},
     })
-    del obj, loc
+    del obj, loc, rep
     torch.cuda.empty_cache()
     return out
 
@@ -798,11 +837,22 @@ def run_b200(args):
                             "link_frac = e2e bytes moved per second (pinned input) / that ceiling"}
         del qh, q_page
 
-    # ---- N > 1: single-process multi-GPU drop-in (rank 0 drives every GPU of the job; the other ranks wait)
+    # ---- N > 1: single-process multi-GPU drop-in (rank 0 drives every GPU of the job; the other ranks wait on a
+    # CPU-side (gloo) barrier -- an NCCL barrier would keep a spinning kernel of THEIR context on the GPUs rank 0 is
+    # about to use, and two contexts time-slice a GPU)
     if world > 1 and not args.no_e2e:
-        dist.barrier()
+        torch.cuda.synchronize()
+        cpu_group = dist.new_group(backend="gloo")
+        dist.barrier(group=cpu_group)
         if rank == 0:
             try:
+                # the other ranks are idle now: this process may use every core of the box (threads inherit the mask)
+                all_cores = set(range(os.cpu_count()))
+                for tid in os.listdir("/proc/self/task"):
+                    try:
+                        os.sched_setaffinity(int(tid), all_cores)
+                    except OSError:
+                        pass
                 from arbinterp_b200.ingest import IngestedField
                 QS = args.e2e_queries
                 planes = analytic_planes(torch, n, device)[2]
@@ -819,15 +869,19 @@ def run_b200(args):
                 same = all(np.array_equal(a, b, equal_nan=True) for a, b in zip(one, many)) and \
                     bool(np.array_equal(obj.queryInds, multi.queryInds))
                 v_multi, _, _ = time_e2e(torch, None, device, multi, qm, args.steps, args.warmup, 1)
+                qpin = torch.empty(QS, 3, dtype=torch.float64, pin_memory=True)
+                qpin.copy_(torch.from_numpy(qm))
+                v_multi_pin, _, _ = time_e2e(torch, None, device, multi, qpin.numpy(), args.steps, args.warmup, 1)
                 e2e["single_process_multi_gpu"] = {
                     "value": v_multi, "unit": "queries/s", "devices": world, "queries_per_step": QS,
+                    "pinned": {"value": v_multi_pin, "api": "the same call with the caller's array page-locked"},
                     "bit_identical_to_one_gpu": bool(same),
                     "api": f"tricubic(field, devices=[0..{world - 1}]).Query(pageable numpy) in ONE process, other ranks idle"}
                 del multi
             except Exception as e:                                   # noqa: BLE001 -- report, do not lose the line
                 e2e["single_process_multi_gpu"] = {"error": f"{type(e).__name__}: {e}"}
             torch.cuda.empty_cache()
-        dist.barrier()
+        dist.barrier(group=cpu_group)
 
     # ---- other modes and the 4-D path (device-resident), each guarded by an oracle sample (N = 1)
     others = {}

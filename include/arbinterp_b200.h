@@ -124,13 +124,14 @@ int arb_query_grid_host(const arb_geom* g, const double* grid, int64_t pitch_x, 
                         int64_t ldq, double* out_comps_host, double* out_norm_host, double* out_grad_host,
                         int64_t* out_cell_host, int64_t chunk_rows);
 
-/* Node (Hermite) table -- an 8x (3-D) / 16x (4-D) smaller alternative to the cell coefficient table with the same
+/* Node (Hermite) table -- a 4x (3-D) / 16x (4-D) smaller alternative to the cell coefficient table with the same
  * answers to round-off: the 2^d central-difference values (f, fx, fy, fxy, ... = the rows of the reference's D
  * matrix, A.py:129-173 / 762-876) of every interior grid node; a query evaluates the tensor-product cubic Hermite
  * interpolant of its 2^d corner nodes, which is the polynomial alpha = inv(B) D f describes (A.py:112-125, 175),
  * including the A.py:860 term in 4-D unless ARB_GEOM_FIXED_D4 is set.  Replaces calcCoefficients* + rQuery* together.
  *   grid  : device [ncomp][nt][nz][ny][pitch_x] as for arb_build_coeffs (pitch_x >= nx)
- *   nodes : device [ncomp][nt-2][nz-2][ny-2][nx-2][2^d], 16-byte aligned
+ *   nodes : device, 128-byte aligned.  d = 4: [ncomp][nt-2][nz-2][ny-2][nx-2][16];
+ *           d = 3: [ncomp][nz-2][ny-2][nx-3][2][8] -- x-adjacent nodes i, i+1 stored as aligned pairs (every node twice)
  * arb_query_nodes / arb_query_nodes_host take the node table where arb_query / arb_query_host take the cell table;
  * every other argument, the outputs, the in-place NaN rows and the cell indices are the same.  No slabs. */
 int arb_build_nodes(int d, const double* grid, int ncomp, const int64_t* npts, int64_t pitch_x, double* nodes,

@@ -33,7 +33,10 @@ def test_node_table_golden(name, d, modes):
             obj.table
         npts = [int(v) + 3 for v in g["ncell_axis"]]
         ncomp = {"vector": 3, "norm": 1, "both": 4, "scalar": 1}[mode]
-        assert list(obj.nodes.shape) == [ncomp] + [n - 2 for n in reversed(npts)] + [2 ** d]
+        if d == 3:
+            assert list(obj.nodes.shape) == [ncomp, npts[2] - 2, npts[1] - 2, npts[0] - 3, 2, 8]
+        else:
+            assert list(obj.nodes.shape) == [ncomp] + [n - 2 for n in reversed(npts)] + [16]
     with pytest.raises(ValueError):
         _cls(d)(g["field"].copy(), "quiet", table="nodes", slab=(0, 1))
     with pytest.raises(ValueError):
@@ -50,7 +53,9 @@ def test_node_values_are_the_rows_of_D():
     vals = rng.standard_normal(nx * ny * nz)
     field = np.concatenate([field[:, :3], vals[:, None]], axis=1)
     obj = tricubic(field, "quiet", table="nodes")
-    got = obj.nodes.cpu().numpy()[0]                       # [nz-2][ny-2][nx-2][8]
+    pairs = obj.nodes.cpu().numpy()[0]                     # [nz-2][ny-2][nx-3][2][8]: pair i = nodes i, i + 1
+    assert np.array_equal(pairs[:, :, 1:, 0], pairs[:, :, :-1, 1])
+    got = np.concatenate([pairs[:, :, :, 0], pairs[:, :, -1:, 1]], axis=2)          # [nz-2][ny-2][nx-2][8]
     f = vals.reshape(nz, ny, nx)
     c = (slice(1, -1),) * 3
     dx = lambda a: 0.5 * (a[:, :, 2:] - a[:, :, :-2])
