@@ -18,7 +18,7 @@ EXPORTED_SYMBOLS = (
     "arb_version", "arb_last_error", "arb_get_matrix",
     "arb_build_coeffs", "arb_build_coeffs_3d", "arb_build_coeffs_4d",
     "arb_query", "arb_query_host", "arb_query_grid", "arb_query_grid_host",
-    "arb_build_nodes", "arb_query_nodes", "arb_query_nodes_host",
+    "arb_build_nodes", "arb_query_nodes", "arb_query_nodes_host", "arb_query_gridil", "arb_query_gridil_host",
     "arb_push", "arb_push_steps", "arb_permute_rows", "arb_set_query_variant", "arb_set_build_variant",
 )
 
@@ -87,6 +87,10 @@ def load():
     lib.arb_query_nodes.argtypes = lib.arb_query.argtypes
     lib.arb_query_nodes_host.restype = i32
     lib.arb_query_nodes_host.argtypes = lib.arb_query_host.argtypes
+    lib.arb_query_gridil.restype = i32
+    lib.arb_query_gridil.argtypes = lib.arb_query.argtypes
+    lib.arb_query_gridil_host.restype = i32
+    lib.arb_query_gridil_host.argtypes = lib.arb_query_host.argtypes
     lib.arb_push.restype = i32
     lib.arb_push.argtypes = [ctypes.POINTER(ArbGeom), vp, i32, vp, vp, i64, ctypes.c_double, i64, ctypes.c_double,
                              ctypes.POINTER(ctypes.c_double * 3), vp, vp]

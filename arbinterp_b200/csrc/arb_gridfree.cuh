@@ -130,6 +130,48 @@ ARB_HD void plane_partial(const unsigned char* box, int off, int rj, int rk, con
     }
 }
 
+// 3-D table-free, interleaved components: one lane = z-plane k of the 4x4x4 neighbourhood, slot [j][i][c]
+// (c = 0..3: Bx, By, Bz, |B|) -> this lane's share of out[0..2] = the components and (BOTH) out[3] = |B|,
+// out[4..6] = its partials; the four lanes (k = 0..3) add up.  A == M (x) M (x) M.
+template <bool BOTH>
+ARB_HD void plane_il(const double* slot, int k, const double* f, double* out) {
+    double wx[4], dwx[4], wy[4], dwy[4], wz[4], dwz[4];
+    catmull_rom(f[0], wx, dwx);
+    catmull_rom(f[1], wy, dwy);
+    catmull_rom(f[2], wz, dwz);
+    double P[4] = {0.0, 0.0, 0.0, 0.0}, Px = 0.0, Py = 0.0;
+    ARB_UNROLL
+    for (int j = 0; j < 4; ++j) {
+        double pp[4] = {0.0, 0.0, 0.0, 0.0}, dp = 0.0;
+        ARB_UNROLL
+        for (int i = 0; i < 4; ++i) {
+            const Pair2 a = *reinterpret_cast<const Pair2*>(slot + (j * 4 + i) * 4);
+            const Pair2 b = *reinterpret_cast<const Pair2*>(slot + (j * 4 + i) * 4 + 2);
+            pp[0] = fma_(a.x, wx[i], pp[0]);
+            pp[1] = fma_(a.y, wx[i], pp[1]);
+            pp[2] = fma_(b.x, wx[i], pp[2]);
+            if (BOTH) {
+                pp[3] = fma_(b.y, wx[i], pp[3]);
+                dp = fma_(b.y, dwx[i], dp);
+            }
+        }
+        ARB_UNROLL
+        for (int c = 0; c < (BOTH ? 4 : 3); ++c) P[c] = fma_(wy[j], pp[c], P[c]);
+        if (BOTH) {
+            Px = fma_(wy[j], dp, Px);
+            Py = fma_(dwy[j], pp[3], Py);
+        }
+    }
+    const double wk = sel4(wz, k);
+    out[0] = wk * P[0]; out[1] = wk * P[1]; out[2] = wk * P[2];
+    if (BOTH) {
+        out[3] = wk * P[3];
+        out[4] = wk * Px;
+        out[5] = wk * Py;
+        out[6] = sel4(dwz, k) * P[3];
+    }
+}
+
 // Quirk term of one ct before the t factor: c[0] = sum_c3 hx hy hz e[c3], c[1..3] = its partials in u, v, w.
 // g = fxyzt at the 8 corners of this ct, g7prev = fxyzt(corner 7 of ct-1) for ct = 1, 0 for ct = 0.
 template <bool GRAD>

@@ -26,14 +26,21 @@ int query_nodes_device(const arb_geom* g, const double* nodes, int mode, double*
                        double* out_comps, double* out_norm, double* out_grad, int64_t* out_cell, int64_t* masked_rows,
                        unsigned long long* masked_count, cudaStream_t st);
 
-// one device-side query on whatever `table` is: grid_pitch > 0 = raw grid planes (table-free), < 0 = node table,
-// 0 = cell coefficient table
+int query_gridil_device(const arb_geom* g, const double* packed, int mode, double* q, int64_t N, int64_t ldq,
+                        double* out_comps, double* out_norm, double* out_grad, int64_t* out_cell, int64_t* masked_rows,
+                        unsigned long long* masked_count, cudaStream_t st);
+
+// one device-side query on whatever `table` is: grid_pitch > 0 = raw grid planes (table-free), -1 = node table,
+// -2 = component-interleaved grid (table-free 'vector' / 'both'), 0 = cell coefficient table
 static int query_any_device(const arb_geom* g, const double* table, int64_t grid_pitch, int mode, double* q, int64_t N,
                             int64_t ldq, double* out_comps, double* out_norm, double* out_grad, int64_t* out_cell,
                             int64_t* masked_rows, unsigned long long* masked_count, cudaStream_t st) {
     if (grid_pitch > 0)
         return query_grid_device(g, table, grid_pitch, mode, q, N, ldq, out_comps, out_norm, out_grad, out_cell,
                                  masked_rows, masked_count, st);
+    if (grid_pitch == -2)
+        return query_gridil_device(g, table, mode, q, N, ldq, out_comps, out_norm, out_grad, out_cell, masked_rows,
+                                   masked_count, st);
     if (grid_pitch < 0)
         return query_nodes_device(g, table, mode, q, N, ldq, out_comps, out_norm, out_grad, out_cell, masked_rows,
                                   masked_count, st);
@@ -524,6 +531,13 @@ extern "C" int arb_query_nodes_host(const arb_geom* g, const double* nodes, int 
                                     int64_t ldq, double* out_comps_host, double* out_norm_host, double* out_grad_host,
                                     int64_t* out_cell_host, int64_t chunk_rows) {
     return query_host_impl(g, nodes, -1, mode, q_host, N, ldq, out_comps_host, out_norm_host, out_grad_host,
+                           out_cell_host, chunk_rows);
+}
+
+extern "C" int arb_query_gridil_host(const arb_geom* g, const double* packed, int mode, double* q_host, int64_t N,
+                                     int64_t ldq, double* out_comps_host, double* out_norm_host, double* out_grad_host,
+                                     int64_t* out_cell_host, int64_t chunk_rows) {
+    return query_host_impl(g, packed, -2, mode, q_host, N, ldq, out_comps_host, out_norm_host, out_grad_host,
                            out_cell_host, chunk_rows);
 }
 

@@ -15,7 +15,8 @@ __global__ void __launch_bounds__(256) build_nodes_kernel(const double* __restri
                                                           double* __restrict__ out) {
     constexpr int T = (D == 3) ? 8 : 16;
     const int64_t m0 = nx - 2, m1 = ny - 2, m2 = nz - 2, m3 = (D == 4) ? nt - 2 : 1;
-    const int64_t per_comp = m0 * m1 * m2 * m3, total = per_comp * ncomp;
+    const bool interleaved = (D == 3 && ncomp >= 3);      // [node][4][8]: Bx, By, Bz, |B| (zeros when ncomp == 3)
+    const int64_t per_comp = m0 * m1 * m2 * m3, total = per_comp * (interleaved ? 4 : ncomp);
     const int64_t sy = pitch_x, sz = pitch_x * ny, st = pitch_x * ny * nz;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t c = i / per_comp;
@@ -28,8 +29,17 @@ __global__ void __launch_bounds__(256) build_nodes_kernel(const double* __restri
                                (y + 1) * sy + (x + 1);
         auto get = [&](int dx, int dy, int dz, int dt) { return __ldg(centre + dx + dy * sy + dz * sz + dt * st); };
         double v[T];
-        nodes::node_stencil<D>(get, v);
-        if (D == 4) {
+        if (c < ncomp) {
+            nodes::node_stencil<D>(get, v);
+        } else {
+#pragma unroll
+            for (int k = 0; k < T; ++k) v[k] = 0.0;
+        }
+        if (interleaved) {
+            double* dst = out + ((i - c * per_comp) * 4 + c) * 8;
+#pragma unroll
+            for (int k = 0; k < T; k += 2) stg_stream_d2(dst + k, v[k], v[k + 1]);
+        } else if (D == 4) {
             double* dst = out + i * T;
 #pragma unroll
             for (int k = 0; k < T; k += 2) stg_stream_d2(dst + k, v[k], v[k + 1]);
@@ -58,7 +68,7 @@ int build_nodes_device(int d, const double* grid, int ncomp, const int64_t* npts
         if (npts[a] < 4) { set_error("arb_build_nodes: axis %d has %lld points, need >= 4", a, (long long)npts[a]); return 1; }
     if (pitch_x < npts[0]) { set_error("arb_build_nodes: pitch_x < nx"); return 1; }
     if (reinterpret_cast<uintptr_t>(out) & 127) { set_error("arb_build_nodes: node table must be 128-byte aligned"); return 1; }
-    int64_t total = ncomp;
+    int64_t total = (d == 3 && ncomp >= 3) ? 4 : ncomp;
     for (int a = 0; a < d; ++a) total *= npts[a] - 2;
     int64_t blocks = (total + 255) / 256;
     const int64_t cap = (int64_t)num_sms() * 16;

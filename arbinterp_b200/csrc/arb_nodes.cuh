@@ -148,6 +148,37 @@ ARB_HD void eval3(const double* slot, const double* f, double* g) {
     if (GRAD) { g[1] = gu; g[2] = gv; g[3] = gw; }
 }
 
+// 3-D, interleaved components, one lane = one row (cy, cz): slot [cx][c][8] (c = 0..3: Bx, By, Bz, |B|) -> this lane's
+// share of out[0..2] = the three components, and (BOTH) out[3] = |B|, out[4..6] = its partials; four lanes add up.
+template <bool BOTH>
+ARB_HD void eval3_row(const double* slot, int cy, int cz, const double* f, double* out) {
+    const Basis bx = hermite(f[0]), by = hermite(f[1]), bz = hermite(f[2]);
+    const double yv = cy ? by.v[1] : by.v[0], ys = cy ? by.s[1] : by.s[0];
+    const double zv = cz ? bz.v[1] : bz.v[0], zs = cz ? bz.s[1] : bz.s[0];
+    const double w[4] = {yv * zv, ys * zv, yv * zs, ys * zs};                    // index ty + 2 tz
+    ARB_UNROLL
+    for (int c = 0; c < (BOTH ? 4 : 3); ++c) {
+        double acc = 0.0, accu = 0.0, accv = 0.0, accw = 0.0;
+        ARB_UNROLL
+        for (int m = 0; m < 4; ++m) {
+            const Pair2 a = *reinterpret_cast<const Pair2*>(slot + c * 8 + 2 * m);
+            const Pair2 b = *reinterpret_cast<const Pair2*>(slot + 32 + c * 8 + 2 * m);
+            const double X = fma_(b.y, bx.s[1], fma_(b.x, bx.v[1], fma_(a.y, bx.s[0], a.x * bx.v[0])));
+            acc = fma_(X, w[m], acc);
+            if (BOTH && c == 3) {
+                const double dyv = cy ? by.dv[1] : by.dv[0], dys = cy ? by.ds[1] : by.ds[0];
+                const double dzv = cz ? bz.dv[1] : bz.dv[0], dzs = cz ? bz.ds[1] : bz.ds[0];
+                const double Xu = fma_(b.y, bx.ds[1], fma_(b.x, bx.dv[1], fma_(a.y, bx.ds[0], a.x * bx.dv[0])));
+                accu = fma_(Xu, w[m], accu);
+                accv = fma_(X, ((m & 1) ? dys : dyv) * ((m >> 1) ? zs : zv), accv);
+                accw = fma_(X, ((m & 1) ? ys : yv) * ((m >> 1) ? dzs : dzv), accw);
+            }
+        }
+        out[c] = acc;
+        if (BOTH && c == 3) { out[4] = accu; out[5] = accv; out[6] = accw; }
+    }
+}
+
 // 4-D quirk term of one lane: f15 = fxyzt of the lane's corners (cx, cy) = (0,0), (1,0), (0,1), (1,1) in reference
 // order c = cx + 2 cy + 4 cz + 8 ct; e[c] = fxyzt(c - 1) - fxyzt(c); prev15 = fxyzt of corner (1, 1) of the lane before
 // (cz + 2 ct - 1), 0 for the first lane.  Adds to g.

@@ -260,13 +260,21 @@ __global__ void __launch_bounds__(THREADS) query_bulk_kernel(const QueryParams p
 // KIND_NODES: `table` is a node (Hermite) table (arb_nodes.cuh): a 3-D slot is the 4 x-pairs of corner nodes
 // (4 segments of 128 B, stored as 128-byte-aligned pairs), a 4-D slot the 2 x-pairs (cy = 0, 1) of one (cz, ct) (2 segments of 256 B); the four lanes
 // of a 4-D query own (cz, ct) and their shares add up.  QUIRK4 reproduces A.py:860 there.
-constexpr int KIND_CELLS = 0, KIND_NODES = 1;
+// KIND_NODES_IL / KIND_GRID_IL (3-D, modes 'vector' and 'both'): the components are interleaved in memory, so one
+// gather serves all of them and its pieces are 512 / 128 contiguous bytes instead of 128 / 32.  Four lanes own a
+// query, one 512-byte slot each, and their shares of every output add up over two shuffle steps:
+//   NODES_IL: node table [nz-2][ny-2][nx-2][4][8]; lane (cy, cz) holds the x-pair of nodes of its row (one segment);
+//   GRID_IL : raw grid   [nz][ny][nx][4] (table-free); lane k holds z-plane k of the 4x4x4 neighbourhood (4 segments
+//             of 128 B = the four x-neighbours of all components).
+constexpr int KIND_CELLS = 0, KIND_NODES = 1, KIND_NODES_IL = 2, KIND_GRID_IL = 3;
 template <int D, int MODE, int THREADS, bool DEDUP, bool LOOPC = false, int SLOTS = 32, bool PREFETCH = false,
           bool FETCH_LDGSTS = false, int KIND = KIND_CELLS, bool QUIRK4 = true>
 __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams p, const int* __restrict__ gate, int gate_want) {
     static_assert(KIND == KIND_CELLS || FETCH_LDGSTS, "node slots are gathered from several segments");
-    constexpr int C = MODE == 0 ? 3 : (MODE == 1 ? 1 : 4);
-    constexpr int SL = (D == 4) ? 4 : 1;          // tricubic blocks per component
+    constexpr bool QUAD = (KIND == KIND_NODES_IL || KIND == KIND_GRID_IL);
+    static_assert(!QUAD || (D == 3 && MODE != 1), "interleaved layouts: 3-D 'vector' / 'both'");
+    constexpr int C = QUAD ? 1 : (MODE == 0 ? 3 : (MODE == 1 ? 1 : 4));      // separately fetched components
+    constexpr int SL = (D == 4 || QUAD) ? 4 : 1;  // 512-byte slots (lanes) per query and component
     constexpr int QPW = 32 / SL;                  // queries per warp item
     constexpr uint32_t BYTES = 512;
     constexpr uint32_t SLOT = BYTES + 16;         // skew keeps LDS.128 conflict-free across lanes
@@ -290,6 +298,7 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
         if (D == 3) lane_src = (((lane >> 4) * p.nn[1] + ((lane >> 3) & 1)) * p.nc[0]) * 128 + (lane & 7) * 16;
         else lane_src = (lane >> 4) * p.nn[0] * 128 + (lane & 15) * 16;
     }
+    if (KIND == KIND_GRID_IL) lane_src = (lane >> 3) * (p.nc[0] + 3) * 32 + (lane & 7) * 16;      // row j = lane / 8
     const int64_t warp_global = ((int64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * THREADS) >> 5;
     const int64_t nbatch = (p.N + QPW - 1) / QPW;
@@ -338,8 +347,10 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
             if (p.out_cell) p.out_cell[n] = L.cell_global;
             if (L.masked) mask_row_in_place(p, n);
         }
-        const bool grad_comp = (MODE == 1) || (MODE == 2 && comp == 3);     // warp-uniform
-        double g[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        const bool grad_comp = (MODE == 1) || (MODE == 2 && (QUAD || comp == 3));     // warp-uniform
+        double g[QUAD ? 7 : 5];
+#pragma unroll
+        for (int i = 0; i < (QUAD ? 7 : 5); ++i) g[i] = 0.0;
         double f15[4] = {0.0, 0.0, 0.0, 0.0};                               // 4-D nodes: fxyzt of this lane's corners
         const double* cb = reinterpret_cast<const double*>(ring + (size_t)myslot * SLOT);
         const double* src = p.table + blk * 64;
@@ -352,6 +363,10 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
                       (((it * p.nn[2] + iz) * p.nn[1] + L.idx[1]) * p.nn[0] + L.idx[0]) * 16;
             }
         }
+        if (KIND == KIND_NODES_IL)      // lane (cy, cz) = (sl & 1, sl >> 1): nodes (ix, ix + 1) of its row, 2 x 256 B
+            src = p.table + (((L.idx[2] + (sl >> 1)) * p.nn[1] + L.idx[1] + (sl & 1)) * p.nn[0] + L.idx[0]) * 32;
+        if (KIND == KIND_GRID_IL)       // lane k = sl: rows (iy .. iy + 3) of grid plane iz + k, 4 x-points x 4 components each
+            src = p.table + (((L.idx[2] + sl) * (p.nc[1] + 3) + L.idx[1]) * (p.nc[0] + 3) + L.idx[0]) * 4;
 #pragma unroll 1
         for (int pass = 0; pass < npass; ++pass) {
             const bool active = (SLOTS == 32) || (mypass == pass);
@@ -393,7 +408,11 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
                 phase ^= 1;
             }
             if (L.ok && active) {
-                if (KIND == KIND_NODES) {
+                if constexpr (KIND == KIND_NODES_IL) {
+                    nodes::eval3_row<MODE == 2>(cb, sl & 1, sl >> 1, L.frac, g);
+                } else if constexpr (KIND == KIND_GRID_IL) {
+                    gridfree::plane_il<MODE == 2>(cb, sl, L.frac, g);
+                } else if (KIND == KIND_NODES) {
                     if (D == 3) {
                         if (grad_comp) nodes::eval3<true>(cb, L.frac, g);
                         else nodes::eval3<false>(cb, L.frac, g);
@@ -409,7 +428,13 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
             }
             __syncwarp();   // every lane is done with the slots before the next copies land
         }
-        if (D == 4 && KIND == KIND_NODES) {
+        if constexpr (QUAD) {
+#pragma unroll
+            for (int i = 0; i < (MODE == 2 ? 7 : 3); ++i) {
+                g[i] += __shfl_xor_sync(0xffffffffu, g[i], 1);
+                g[i] += __shfl_xor_sync(0xffffffffu, g[i], 2);
+            }
+        } else if (D == 4 && KIND == KIND_NODES) {
             if (QUIRK4) {       // A.py:860: the fxyzt slot of corner c holds fxyzt(c - 1); the lane before owns c - 1 of our first corner
                 const double up = __shfl_up_sync(0xffffffffu, f15[3], 1);
                 if (grad_comp) nodes::quirk4_lane<true>(f15, sl ? up : 0.0, sl & 1, sl >> 1, L.frac, g);
@@ -438,7 +463,18 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
                 }
             }
         }
-        if (n < p.N && sl == 0) {
+        if constexpr (QUAD) {
+            if (n < p.N && sl == 0) {
+                const double nan = qnan();
+#pragma unroll
+                for (int c = 0; c < 3; ++c) p.out_comps[n * 3 + c] = L.ok ? g[c] : nan;
+                if (MODE == 2) {
+                    p.out_norm[n] = L.ok ? g[3] : nan;
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) p.out_grad[n * 3 + a] = L.ok ? __ddiv_rn(g[4 + a], p.h[a]) : nan;
+                }
+            }
+        } else if (n < p.N && sl == 0) {
             const double nan = qnan();
             if (!grad_comp) {
                 p.out_comps[n * 3 + comp] = L.ok ? g[0] : nan;
@@ -796,8 +832,9 @@ static int launch_bulk(const QueryParams& p, cudaStream_t st) {
 template <int D, int MODE, int THREADS, bool DEDUP, bool LOOPC = false, int SLOTS = 32, bool PREFETCH = false,
           bool FETCH_LDGSTS = false, int KIND = KIND_CELLS, bool QUIRK4 = true>
 static int launch_block(const QueryParams& p, cudaStream_t st, const int* gate = nullptr, int gate_want = 0) {
-    constexpr int C = MODE == 0 ? 3 : (MODE == 1 ? 1 : 4);
-    constexpr int QPW = (D == 4) ? 8 : 32;
+    constexpr bool QUAD = (KIND == KIND_NODES_IL || KIND == KIND_GRID_IL);
+    constexpr int C = QUAD ? 1 : (MODE == 0 ? 3 : (MODE == 1 ? 1 : 4));
+    constexpr int QPW = (D == 4 || QUAD) ? 8 : 32;
     const size_t smem = (size_t)(THREADS / 32) * SLOTS * 528;
     auto k = query_block_kernel<D, MODE, THREADS, DEDUP, LOOPC, SLOTS, PREFETCH, FETCH_LDGSTS, KIND, QUIRK4>;
     static LaunchCache cache = {};
@@ -952,13 +989,42 @@ int query_device(const arb_geom* g, const double* table, int mode, double* q, in
 template <int D, int MODE>
 static int dispatch_nodes(const QueryParams& p, cudaStream_t st, int variant, bool quirk) {
     constexpr bool LC = (D == 4);
-    if (D == 4 && !quirk) return launch_block<D, MODE, 128, true, LC, 32, true, true, KIND_NODES, false>(p, st);
-    switch (variant) {
-        case 71: return launch_block<D, MODE, 128, true, LC, 32, false, true, KIND_NODES>(p, st);
-        case 72: return launch_block<D, MODE, 128, true, LC, 16, true, true, KIND_NODES>(p, st);
-        case 73: return launch_block<D, MODE, 128, false, LC, 32, true, true, KIND_NODES>(p, st);
-        default: return launch_block<D, MODE, 128, true, LC, 32, true, true, KIND_NODES>(p, st);
+    if constexpr (D == 3 && MODE != 1) {       // 'vector' / 'both': components interleaved, four lanes per query
+        switch (variant) {
+            case 71: return launch_block<D, MODE, 128, true, true, 32, false, true, KIND_NODES_IL>(p, st);
+            case 72: return launch_block<D, MODE, 128, true, true, 16, true, true, KIND_NODES_IL>(p, st);
+            case 73: return launch_block<D, MODE, 128, false, true, 32, true, true, KIND_NODES_IL>(p, st);
+            default: return launch_block<D, MODE, 128, true, true, 32, true, true, KIND_NODES_IL>(p, st);
+        }
+    } else {
+        if (D == 4 && !quirk) return launch_block<D, MODE, 128, true, LC, 32, true, true, KIND_NODES, false>(p, st);
+        switch (variant) {
+            case 71: return launch_block<D, MODE, 128, true, LC, 32, false, true, KIND_NODES>(p, st);
+            case 72: return launch_block<D, MODE, 128, true, LC, 16, true, true, KIND_NODES>(p, st);
+            case 73: return launch_block<D, MODE, 128, false, LC, 32, true, true, KIND_NODES>(p, st);
+            default: return launch_block<D, MODE, 128, true, LC, 32, true, true, KIND_NODES>(p, st);
+        }
     }
+}
+
+// Table-free 3-D 'vector' / 'both' on the component-interleaved grid [nz][ny][nx][4] (Bx, By, Bz, |B| or 0).
+int query_gridil_device(const arb_geom* g, const double* packed, int mode, double* q, int64_t N, int64_t ldq,
+                        double* out_comps, double* out_norm, double* out_grad, int64_t* out_cell, int64_t* masked_rows,
+                        unsigned long long* masked_count, cudaStream_t st) {
+    QueryParams p;
+    const int rc = fill_params("arb_query_gridil", g, true, packed, mode, q, N, ldq, out_comps, out_norm, out_grad,
+                               out_cell, masked_rows, masked_count, p);
+    if (rc) return rc < 0 ? 0 : rc;
+    if (g->d != 3 || mode == ARB_MODE_NORM) { set_error("arb_query_gridil: 3-D 'vector' / 'both' only"); return 1; }
+    if (g->slab_lo != 0 || g->slab_hi != g->ncell[2]) { set_error("arb_query_gridil: slabs are not supported"); return 1; }
+    if (reinterpret_cast<uintptr_t>(packed) & 31) { set_error("arb_query_gridil: grid must be 32-byte aligned"); return 1; }
+    const int v = g_query_variant;
+    if (mode == ARB_MODE_VECTOR) {
+        if (v == 73) return launch_block<3, 0, 128, false, true, 32, true, true, KIND_GRID_IL>(p, st);
+        return launch_block<3, 0, 128, true, true, 32, true, true, KIND_GRID_IL>(p, st);
+    }
+    if (v == 73) return launch_block<3, 2, 128, false, true, 32, true, true, KIND_GRID_IL>(p, st);
+    return launch_block<3, 2, 128, true, true, 32, true, true, KIND_GRID_IL>(p, st);
 }
 
 int query_nodes_device(const arb_geom* g, const double* nodes, int mode, double* q, int64_t N, int64_t ldq,
@@ -1092,6 +1158,13 @@ int arb_query_grid(const arb_geom* g, const double* grid, int64_t pitch_x, int m
                    unsigned long long* masked_count, void* stream) {
     return arb::query_grid_device(g, grid, pitch_x, mode, q, N, ldq, out_comps, out_norm, out_grad, out_cell,
                                   masked_rows, masked_count, (cudaStream_t)stream);
+}
+
+int arb_query_gridil(const arb_geom* g, const double* packed, int mode, double* q, int64_t N, int64_t ldq,
+                     double* out_comps, double* out_norm, double* out_grad, int64_t* out_cell, int64_t* masked_rows,
+                     unsigned long long* masked_count, void* stream) {
+    return arb::query_gridil_device(g, packed, mode, q, N, ldq, out_comps, out_norm, out_grad, out_cell, masked_rows,
+                                    masked_count, (cudaStream_t)stream);
 }
 
 int arb_query_nodes(const arb_geom* g, const double* nodes, int mode, double* q, int64_t N, int64_t ldq,

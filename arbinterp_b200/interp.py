@@ -126,6 +126,7 @@ class _CubicInterpolator:
         self._slab = (lo, hi)
         self._table_free = kwargs.get("table", True) is False
         self._nodes = None
+        self._packed = None
         if isinstance(kwargs.get("table"), str):
             if kwargs["table"] != "nodes":
                 raise ValueError("table must be True (cell coefficients), False (no table) or 'nodes' (Hermite node table)")
@@ -141,6 +142,8 @@ class _CubicInterpolator:
             self._pitch = nx + (nx & 1)                           # TMA needs 16-byte row strides
             if self._pitch != nx:
                 self._planes = torch.nn.functional.pad(self._planes, (0, 1)).contiguous()
+            self._use_packed = d == 3 and mode in ("vector", "both") and kwargs.get("interleave", True)
+            self._pack_planes()
             self._make_cgeom()
             # the planes were written by torch ops on the current stream; numpy queries run on the library's own
             # non-blocking streams, which do not order against it -- finish the writes here (as _build_table does)
@@ -215,6 +218,7 @@ class _CubicInterpolator:
         elif self._table is None:
             if self._pitch != geo.npts[0]:
                 self._planes = torch.nn.functional.pad(self._planes, (0, 1)).contiguous()
+            self._pack_planes()
             torch.cuda.current_stream(self._device).synchronize()   # see __init__: lib streams do not order against torch's
         else:
             self._build_table()
@@ -317,6 +321,7 @@ class _CubicInterpolator:
             self._replicas = [self]
             self._table_free = False
             self._nodes = None
+            self._packed = None
             shape = tuple(int(v) for v in header["table_shape"])
             # the header is untrusted input: the table shape must be the one this geometry, slab and mode imply,
             # and the file must actually hold that many bytes, before anything is allocated
@@ -349,14 +354,30 @@ class _CubicInterpolator:
         self._bind_mode()
         return self
 
+    def _pack_planes(self):
+        """Table-free 3-D 'vector' / 'both': the component-interleaved grid ``[nz][ny][nx][4]`` (Bx, By, Bz, |B| or 0)
+        the query kernel gathers from -- one 128-byte piece per neighbourhood row serves every component."""
+        if not getattr(self, "_use_packed", False):
+            self._packed = None
+            return
+        nx = self._geo.npts[0]
+        comps = [self._planes[c, ..., :nx] for c in range(self._planes.shape[0])]
+        if len(comps) == 3:
+            comps.append(torch.zeros_like(comps[0]))
+        self._packed = torch.stack(comps, dim=-1).contiguous()
+
     def _build_nodes(self):
         """Node (Hermite) table (csrc/arb_nodes.cuh): the central-difference values f, fx, fy, fxy, ... of every
         interior grid point -- the rows of the reference's D matrix (A.py:129-173 / 762-876).  4-D:
-        ``[C][nt-2][nz-2][ny-2][nx-2][16]``, 16x smaller than the cell table; 3-D: ``[C][nz-2][ny-2][nx-3][2][8]``
-        (x-adjacent nodes stored as 128-byte-aligned pairs), 4x smaller.  Same answers to round-off."""
+        ``[C][nt-2][nz-2][ny-2][nx-2][16]``, 16x smaller than the cell table; 3-D one component:
+        ``[1][nz-2][ny-2][nx-3][2][8]`` (x-adjacent nodes stored as 128-byte-aligned pairs), 4x smaller; 3-D 'vector' /
+        'both': ``[nz-2][ny-2][nx-2][4][8]`` (the components of a node together), 6x / 8x smaller.  Same answers to
+        round-off."""
         d, geo = self._d, self._geo
         ncomp = self._planes.shape[0]
-        if d == 3:          # aligned x-pairs: [C][nz-2][ny-2][nx-3][2][8]
+        if d == 3 and ncomp >= 3:       # components of a node together: [nz-2][ny-2][nx-2][4][8]
+            shape = [geo.npts[2] - 2, geo.npts[1] - 2, geo.npts[0] - 2, 4, 8]
+        elif d == 3:                    # aligned x-pairs: [1][nz-2][ny-2][nx-3][2][8]
             shape = [ncomp, geo.npts[2] - 2, geo.npts[1] - 2, geo.npts[0] - 3, 2, 8]
         else:
             shape = [ncomp] + [geo.npts[a] - 2 for a in reversed(range(d))] + [16]
@@ -527,6 +548,10 @@ class _CubicInterpolator:
                 _lib.check(self._lib.arb_query_nodes(ctypes.byref(self._cgeom), self._nodes.data_ptr(), self._mode_code,
                                                      work.data_ptr(), n, work.shape[1], self._ptr(comps), self._ptr(norm),
                                                      self._ptr(grad), cells.data_ptr(), None, None, stream), "arb_query_nodes")
+            elif self._packed is not None:
+                _lib.check(self._lib.arb_query_gridil(ctypes.byref(self._cgeom), self._packed.data_ptr(), self._mode_code,
+                                                      work.data_ptr(), n, work.shape[1], self._ptr(comps), self._ptr(norm),
+                                                      self._ptr(grad), cells.data_ptr(), None, None, stream), "arb_query_gridil")
             elif self._table is None:
                 _lib.check(self._lib.arb_query_grid(ctypes.byref(self._cgeom), self._planes.data_ptr(), self._pitch,
                                                     self._mode_code, work.data_ptr(), n, work.shape[1],
@@ -572,6 +597,10 @@ class _CubicInterpolator:
                 _lib.check(self._lib.arb_query_nodes_host(ctypes.byref(self._cgeom), self._nodes.data_ptr(), self._mode_code,
                                                           qptr, n, work.shape[1], row(comps), row(norm), row(grad),
                                                           cells.data_ptr(), chunk), "arb_query_nodes_host")
+            elif self._packed is not None:
+                _lib.check(self._lib.arb_query_gridil_host(ctypes.byref(self._cgeom), self._packed.data_ptr(), self._mode_code,
+                                                           qptr, n, work.shape[1], row(comps), row(norm), row(grad),
+                                                           cells.data_ptr(), chunk), "arb_query_gridil_host")
             elif self._table is None:
                 _lib.check(self._lib.arb_query_grid_host(ctypes.byref(self._cgeom), self._planes.data_ptr(), self._pitch,
                                                          self._mode_code, qptr, n, work.shape[1],
@@ -639,10 +668,14 @@ class _CubicInterpolator:
             torch.cuda.set_device(self._device)
         try:
             args = (ctypes.byref(self._cgeom), self._nodes.data_ptr() if self._nodes is not None else
+                    self._packed.data_ptr() if self._packed is not None else
                     self._planes.data_ptr() if self._table is None else self._table.data_ptr())
             if self._nodes is not None:
                 rc = self._lib.arb_query_nodes_host(*args, self._mode_code, work.ctypes.data, n, work.shape[1],
                                                     ptr(comps), ptr(norm), ptr(grad), cells.ctypes.data, 0)
+            elif self._packed is not None:
+                rc = self._lib.arb_query_gridil_host(*args, self._mode_code, work.ctypes.data, n, work.shape[1],
+                                                     ptr(comps), ptr(norm), ptr(grad), cells.ctypes.data, 0)
             elif self._table is None:
                 rc = self._lib.arb_query_grid_host(*args, self._pitch, self._mode_code, work.ctypes.data, n, work.shape[1],
                                                    ptr(comps), ptr(norm), ptr(grad), cells.ctypes.data, 0)

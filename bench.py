@@ -705,7 +705,8 @@ def run_sharded(torch, dist, args, rank, world, device):
         "alg_bytes_per_query": ALG_BYTES[(4, "both")],
         "phase_ms_per_step_max_over_ranks": {
             "kernel": ph[5], "all_to_all (counts + rows + results)": ph[2] + ph[4] + ph[6],
-            "sort + permute + scatter": ph[1] + ph[3] + ph[7], "owner + unpack": ph[0] + ph[8]},
+            "sort + permute + scatter": ph[1] + ph[3] + ph[7], "owner + unpack": ph[0] + ph[8],
+            "each": dict(zip(("owner", "sort", "counts", "permute", "alltoall", "kernel", "alltoall_back", "scatter", "unpack"), ph))},
         "kernel_frac_of_measured_hbm": (ALG_BYTES[(4, "both")] * n / (ph[5] * 1e-3) / 1e9 / measured_peak()[0]) if ph[5] > 0 else None,
         "replicated_node_table": {
             "what": "the same field as a node (Hermite) table replicated on every rank (quadcubic(table='nodes') via "
@@ -733,7 +734,7 @@ def run_b200(args):
     dist = None
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
-    affinity = bind_to_gpu_cores(local, local, local_world) if world > 1 else None
+    affinity = bind_to_gpu_cores(local, local, local_world) if (world > 1 and not os.environ.get("ARB_NO_BIND")) else None
     if world > 1:
         import torch.distributed as dist_mod
         dist_mod.init_process_group("nccl", device_id=device)

@@ -131,7 +131,9 @@ int arb_query_grid_host(const arb_geom* g, const double* grid, int64_t pitch_x, 
  * including the A.py:860 term in 4-D unless ARB_GEOM_FIXED_D4 is set.  Replaces calcCoefficients* + rQuery* together.
  *   grid  : device [ncomp][nt][nz][ny][pitch_x] as for arb_build_coeffs (pitch_x >= nx)
  *   nodes : device, 128-byte aligned.  d = 4: [ncomp][nt-2][nz-2][ny-2][nx-2][16];
- *           d = 3: [ncomp][nz-2][ny-2][nx-3][2][8] -- x-adjacent nodes i, i+1 stored as aligned pairs (every node twice)
+ *           d = 3, ncomp = 1: [nz-2][ny-2][nx-3][2][8] -- x-adjacent nodes i, i+1 stored as aligned pairs (every node twice);
+ *           d = 3, ncomp = 3 or 4 ('vector' / 'both'): [nz-2][ny-2][nx-2][4][8] -- the components of a node together
+ *           (Bx, By, Bz, |B|; the 4th block is zero for ncomp = 3), so one gather serves all of them
  * arb_query_nodes / arb_query_nodes_host take the node table where arb_query / arb_query_host take the cell table;
  * every other argument, the outputs, the in-place NaN rows and the cell indices are the same.  No slabs. */
 int arb_build_nodes(int d, const double* grid, int ncomp, const int64_t* npts, int64_t pitch_x, double* nodes,
@@ -142,6 +144,17 @@ int arb_query_nodes(const arb_geom* g, const double* nodes, int mode, double* q,
 int arb_query_nodes_host(const arb_geom* g, const double* nodes, int mode, double* q_host, int64_t N, int64_t ldq,
                          double* out_comps_host, double* out_norm_host, double* out_grad_host, int64_t* out_cell_host,
                          int64_t chunk_rows);
+
+/* Table-free 3-D 'vector' / 'both' queries on a component-interleaved grid: packed = device [nz][ny][nx][4]
+ * (Bx, By, Bz, |B| -- the 4th value is not read in mode VECTOR), 32-byte aligned; g->ncomp = 3 or 4 as for arb_query_grid.
+ * One 128-byte piece per grid row of the neighbourhood serves every component (arb_query_grid: one 48-byte piece per
+ * row and component).  Same outputs and conventions as arb_query_grid. */
+int arb_query_gridil(const arb_geom* g, const double* packed, int mode, double* q, int64_t N, int64_t ldq,
+                     double* out_comps, double* out_norm, double* out_grad, int64_t* out_cell, int64_t* masked_rows,
+                     unsigned long long* masked_count, void* stream);
+int arb_query_gridil_host(const arb_geom* g, const double* packed, int mode, double* q_host, int64_t N, int64_t ldq,
+                          double* out_comps_host, double* out_norm_host, double* out_grad_host, int64_t* out_cell_host,
+                          int64_t chunk_rows);
 
 /* Fused query + push: nsteps velocity-Verlet steps of dv/dt = kappa * grad(value)(x) + gravity for N
  * particles resident in device memory, the gradient being what Query2/Query3 return (A.py:452, 519)

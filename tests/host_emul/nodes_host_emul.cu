@@ -95,6 +95,67 @@ static double run(const int64_t (&n)[4], int nq, uint64_t seed) {
     return worst;
 }
 
+// 3-D interleaved-component forms: nodes::eval3_row (four (cy, cz) lanes) and gridfree::plane_il (four z-plane lanes)
+// on four random component grids, against alpha = A f per component.
+static double run_interleaved(const int64_t (&n)[3], int nq, uint64_t seed, bool grid_form) {
+    const int64_t npt = n[0] * n[1] * n[2];
+    std::vector<double> grid((size_t)npt * 4);
+    for (double& x : grid) x = 2.0 * rnd(seed) - 1.0;
+    auto at = [&](int c, int64_t x, int64_t y, int64_t z) { return grid[(size_t)c * npt + (z * n[1] + y) * n[0] + x]; };
+    const int64_t m0 = n[0] - 2, m1 = n[1] - 2, m2 = n[2] - 2;
+    std::vector<double> tab((size_t)m0 * m1 * m2 * 32);                   // [node][4][8]
+    for (int64_t z = 0; z < m2; ++z)
+        for (int64_t y = 0; y < m1; ++y)
+            for (int64_t x = 0; x < m0; ++x)
+                for (int c = 0; c < 4; ++c) {
+                    auto get = [&](int dx, int dy, int dz, int) { return at(c, x + 1 + dx, y + 1 + dy, z + 1 + dz); };
+                    node_stencil<3>(get, &tab[(((size_t)z * m1 + y) * m0 + x) * 32 + c * 8]);
+                }
+    std::vector<double> A(64 * 64);
+    make_A(3, 0, A.data());
+    double worst = 0.0;
+    for (int qn = 0; qn < nq; ++qn) {
+        int64_t c0[3];
+        double fr[3];
+        for (int a = 0; a < 3; ++a) { c0[a] = (int64_t)(rnd(seed) * (n[a] - 3)); fr[a] = rnd(seed); }
+        double got[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (int sl = 0; sl < 4; ++sl) {
+            alignas(16) double slot[64];
+            double part[7];
+            if (grid_form) {
+                for (int j = 0; j < 4; ++j)
+                    for (int i = 0; i < 4; ++i)
+                        for (int c = 0; c < 4; ++c) slot[(j * 4 + i) * 4 + c] = at(c, c0[0] + i, c0[1] + j, c0[2] + sl);
+                gridfree::plane_il<true>(slot, sl, fr, part);
+            } else {
+                memcpy(slot, &tab[((((size_t)c0[2] + (sl >> 1)) * m1 + c0[1] + (sl & 1)) * m0 + c0[0]) * 32], 64 * sizeof(double));
+                eval3_row<true>(slot, sl & 1, sl >> 1, fr, part);
+            }
+            for (int i = 0; i < 7; ++i) got[i] += part[i];
+        }
+        for (int c = 0; c < 4; ++c) {
+            double f[64], ref[4] = {0, 0, 0, 0}, mag[4] = {0, 0, 0, 0};
+            for (int m = 0; m < 64; ++m) f[m] = at(c, c0[0] + (m & 3), c0[1] + ((m >> 2) & 3), c0[2] + (m >> 4));
+            for (int m = 0; m < 64; ++m) {
+                double al = 0.0;
+                for (int k = 0; k < 64; ++k) al += A[m * 64 + k] * f[k];
+                const int e[3] = {m & 3, (m >> 2) & 3, m >> 4};
+                double pw[3], dpw[3];
+                for (int a = 0; a < 3; ++a) { pw[a] = std::pow(fr[a], e[a]); dpw[a] = e[a] ? e[a] * std::pow(fr[a], e[a] - 1) : 0.0; }
+                const double t[4] = {pw[0] * pw[1] * pw[2], dpw[0] * pw[1] * pw[2], pw[0] * dpw[1] * pw[2], pw[0] * pw[1] * dpw[2]};
+                for (int i = 0; i < 4; ++i) { ref[i] += al * t[i]; mag[i] += std::fabs(al * t[i]); }
+            }
+            const int nout = (c == 3) ? 4 : 1;
+            for (int i = 0; i < nout; ++i) {
+                const double g = (i == 0) ? got[c] : got[3 + i];
+                const double err = std::fabs(g - ref[i]) / std::fmax(mag[i], 1.0);
+                if (!(err <= worst)) worst = err;
+            }
+        }
+    }
+    return worst;
+}
+
 int main() {
     int bad = 0;
     auto report = [&](const char* name, double e) {
@@ -108,5 +169,9 @@ int main() {
     report("4d nodes 5x6x4x7 quirk", run<4, true>({5, 6, 4, 7}, 400, 25));
     report("4d nodes 4x4x4x4 quirk", run<4, true>({4, 4, 4, 4}, 50, 26));
     report("4d nodes 9x8x7x6 fixed", run<4, false>({9, 8, 7, 6}, 400, 27));
+    report("3d interleaved nodes 9x8x7", run_interleaved({9, 8, 7}, 400, 28, false));
+    report("3d interleaved nodes 4x4x4", run_interleaved({4, 4, 4}, 50, 29, false));
+    report("3d interleaved grid 9x8x7", run_interleaved({9, 8, 7}, 400, 30, true));
+    report("3d interleaved grid 5x4x6", run_interleaved({5, 4, 6}, 200, 31, true));
     return bad;
 }

@@ -33,7 +33,9 @@ def test_node_table_golden(name, d, modes):
             obj.table
         npts = [int(v) + 3 for v in g["ncell_axis"]]
         ncomp = {"vector": 3, "norm": 1, "both": 4, "scalar": 1}[mode]
-        if d == 3:
+        if d == 3 and ncomp >= 3:
+            assert list(obj.nodes.shape) == [npts[2] - 2, npts[1] - 2, npts[0] - 2, 4, 8]
+        elif d == 3:
             assert list(obj.nodes.shape) == [ncomp, npts[2] - 2, npts[1] - 2, npts[0] - 3, 2, 8]
         else:
             assert list(obj.nodes.shape) == [ncomp] + [n - 2 for n in reversed(npts)] + [16]
@@ -122,6 +124,48 @@ def test_node_table_quadcubic_matches_cell_table(mode, fixed):
         got = b.Query(q[:10_000].copy())
         _check_outputs(got, ref, mode, field, 4, ora.geo.h, f"nodes vs oracle 4d {mode}")
         assert np.array_equal(b.queryInds, ora.query_inds)
+
+
+@pytest.mark.parametrize("mode", ["vector", "both"])
+def test_table_free_interleaved_grid(mode):
+    """Table-free 3-D 'vector' / 'both' on the component-interleaved grid (arb_query_gridil, the default) against the
+    per-component TMA-box kernel (interleave=False), the cell table and the oracle; odd nx, NaN / out-of-volume rows,
+    device tensors, update_values."""
+    from arbinterp_b200 import tricubic
+    from oracle.arb_oracle import OracleInterp
+    rng = np.random.default_rng(707)
+    field = _analytic_field3(37, 26, 23, rng=rng)
+    cells = tricubic(field.copy(), "quiet", mode=mode)
+    il = tricubic(field.copy(), "quiet", mode=mode, table=False)
+    pl = tricubic(field.copy(), "quiet", mode=mode, table=False, interleave=False)
+    assert il._packed is not None and pl._packed is None
+    q = _uniform_queries(cells, 3, 150_000, rng, extra=1)
+    q[::101, 0] = -9.0
+    q[::977, 2] = np.nan
+    h = [cells.hx, cells.hy, cells.hz]
+    outs = {}
+    for name, obj in (("cells", cells), ("il", il), ("pl", pl)):
+        qq = q.copy()
+        r = obj.Query(qq)
+        outs[name] = (r if isinstance(r, tuple) else (r,), qq, obj.queryInds)
+    for name in ("il", "pl"):
+        _check_outputs(outs[name][0], outs["cells"][0], mode, field, 3, h, f"table-free {name} vs cells {mode}")
+        assert np.array_equal(outs[name][1], outs["cells"][1], equal_nan=True)
+        assert np.array_equal(outs[name][2], outs["cells"][2])
+    ora = OracleInterp(field, 3, mode=mode)
+    ref = ora.query(q[:20_000].copy())
+    ref = ref if isinstance(ref, tuple) else (ref,)
+    _check_outputs(il.Query(q[:20_000].copy()), ref, mode, field, 3, ora.geo.h, f"table-free interleaved vs oracle {mode}")
+    dev = il.Query(torch.from_numpy(q.copy()).cuda())
+    dev = dev if isinstance(dev, tuple) else (dev,)
+    for x, y in zip(outs["il"][0], dev):
+        assert np.array_equal(x, y.cpu().numpy(), equal_nan=True)
+    new_vals = field[:, 3:] * 0.5 - 0.125
+    il.update_values(new_vals)
+    fresh = tricubic(np.concatenate([field[:, :3], new_vals], axis=1), "quiet", mode=mode, table=False)
+    a, b = il.Query(q.copy()), fresh.Query(q.copy())
+    for x, y in zip(a if isinstance(a, tuple) else (a,), b if isinstance(b, tuple) else (b,)):
+        assert np.array_equal(x, y, equal_nan=True)
 
 
 def test_node_table_quirk_is_visible():

@@ -1,0 +1,60 @@
+#!/usr/bin/env python
+"""Table-free 3-D 'vector' / 'both': the component-interleaved grid (arb_query_gridil, LDGSTS gather, four lanes per
+query) against the per-component TMA-box kernel (arb_query_grid) and the cell-table path; 256^3 and 128^3, uniformly
+random and cell-sorted batches."""
+import ctypes
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from arbinterp_b200 import tricubic  # noqa: E402
+from tools.perf_sweep import field_rows  # noqa: E402
+
+dev = torch.device("cuda", 0)
+
+
+def rate(obj, q, steps=5, warmup=2):
+    for _ in range(warmup):
+        obj.Query(q)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        obj.Query(q)
+    e1.record()
+    torch.cuda.synchronize()
+    return q.shape[0] * steps / (e0.elapsed_time(e1) / 1e3)
+
+
+g = torch.Generator(device=dev)
+g.manual_seed(3)
+n = int(os.environ.get("ARB_N", str(1 << 24)))
+for grid in (256, 128):
+    for mode in ("vector", "both", "norm"):
+        rows = field_rows((grid,) * 3, dev)
+        cells = tricubic(rows, "quiet", mode=mode)
+        lo = torch.tensor(cells._geo.int_min, dtype=torch.float64, device=dev)
+        hi = torch.tensor(cells._geo.int_max, dtype=torch.float64, device=dev)
+        q = lo + torch.rand(n, 3, generator=g, dtype=torch.float64, device=dev) * (hi - lo) * (1 - 1e-12)
+        cells.Query(q)
+        qs = q[torch.argsort(cells._last_cells)].contiguous()
+        base = {"uniform random": rate(cells, q), "cell-sorted": rate(cells, qs)}
+        tgb = cells.table.numel() * 8 / 1e9
+        del cells
+        torch.cuda.empty_cache()
+        forms = [("planes + TMA boxes", dict(table=False, interleave=False))]
+        if mode != "norm":
+            forms.append(("interleaved grid", dict(table=False)))
+        forms.append(("node table", dict(table="nodes")))
+        for name, kw in forms:
+            obj = tricubic(rows, "quiet", mode=mode, **kw)
+            mem = (obj._nodes if obj._nodes is not None else obj._packed if obj._packed is not None else obj._planes).numel() * 8 / 1e9
+            line = [f"{k}: {rate(obj, qq):.3e} q/s (x{rate(obj, qq) / base[k]:.2f} of the cell table)"
+                    for k, qq in (("uniform random", q), ("cell-sorted", qs))]
+            print(f"[tablefree] {grid}^3 {mode} {name} ({mem:.3f} GB vs {tgb:.2f} GB of cell table): " + " | ".join(line), flush=True)
+            del obj
+            torch.cuda.empty_cache()
+        print(f"[tablefree] {grid}^3 {mode} cell table: " + " | ".join(f"{k}: {v:.3e} q/s" for k, v in base.items()), flush=True)
+        del rows
