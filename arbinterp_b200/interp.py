@@ -225,6 +225,14 @@ class _CubicInterpolator:
         self._last_cells = None
         self.queryInd = None
 
+    def release(self):
+        """Drop the device tensors now.  The mode-specific entry points bound in the constructor (``self.Query = ...``,
+        as the reference binds them, A.py:27-30) make every interpolator part of a reference cycle, so ``del obj`` frees
+        its 8-50 GB only at the next garbage collection; call this to give the memory back at once."""
+        for rep in getattr(self, "_replicas", [self])[1:]:
+            rep.release()
+        self._table = self._nodes = self._packed = self._planes = self._raw = self._last_cells = None
+
     def _bind_mode(self):
         # bind the mode-specific entry points like the reference does (A.py:27-30, 38-41, ...)
         mode = self._mode

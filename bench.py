@@ -402,6 +402,28 @@ def time_device(torch, lib, obj, mode, d, q, outs, cells, steps, warmup, dist=No
     return ev[0].elapsed_time(ev[steps]) / 1e3, per
 
 
+def time_public_device(torch, obj, q, steps, warmup):
+    """K calls of obj.Query on a device-resident batch (the public call with a CUDA tensor: kernel + output allocation
+    from torch's caching allocator); queries/s from CUDA events around the K calls."""
+    # these legs follow seconds of CPU-side checking with the GPU idle: warm up for >= 100 ms so that the clocks are
+    # back up before the timed calls (a 2 ms kernel timed right after an idle period ran at half its rate)
+    t0 = time.perf_counter()
+    done = 0
+    while done < warmup or time.perf_counter() - t0 < 0.1:
+        obj.Query(q)
+        torch.cuda.synchronize()
+        done += 1
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        res = obj.Query(q)
+    e1.record()
+    torch.cuda.synchronize()
+    res = res if isinstance(res, tuple) else (res,)
+    return q.shape[0] * steps / (e0.elapsed_time(e1) / 1e3), all(bool(torch.isfinite(r).all()) for r in res)
+
+
 def alloc_outputs(torch, mode, d, n, device):
     kw = dict(dtype=torch.float64, device=device)
     comps = torch.empty(n, 3, **kw) if mode in ("vector", "both") else None
@@ -549,6 +571,8 @@ def run_sharded(torch, dist, args, rank, world, device):
                           "what": "outputs, queryInds and the in-place NaN rows of SlabShardedInterp.Query(numpy) are "
                                   "bit-identical to the unsharded quadcubic on the same rank; every component has an "
                                   "x*y*z*t term (A.py:860 rank-16 term excited)"}
+    whole.release()
+    sh.local.release()
     del whole, sh
     torch.cuda.empty_cache()
 
@@ -718,12 +742,15 @@ def run_sharded(torch, dist, args, rank, world, device):
             "max_scaled_diff_vs_slab_sharded": node_err, "tolerance": 1e-12, "cell_indices_equal": not cells_differ,
             "ok": bool(node_err <= 1e-12 and not cells_differ)},
     })
+    obj.local.release()
+    rep.local.release()
     del obj, loc, rep
     torch.cuda.empty_cache()
     return out
 
 
 def run_b200(args):
+    import gc
     import torch
     from arbinterp_b200 import tricubic, _lib
 
@@ -878,6 +905,7 @@ def run_b200(args):
                     "pinned": {"value": v_multi_pin, "api": "the same call with the caller's array page-locked"},
                     "bit_identical_to_one_gpu": bool(same),
                     "api": f"tricubic(field, devices=[0..{world - 1}]).Query(pageable numpy) in ONE process, other ranks idle"}
+                multi.release()
                 del multi
             except Exception as e:                                   # noqa: BLE001 -- report, do not lose the line
                 e2e["single_process_multi_gpu"] = {"error": f"{type(e).__name__}: {e}"}
@@ -887,6 +915,7 @@ def run_b200(args):
     # ---- other modes and the 4-D path (device-resident), each guarded by an oracle sample (N = 1)
     others = {}
     if not args.no_other_modes and rank == 0 and world == 1:
+        obj.release()
         del obj, outs
         torch.cuda.empty_cache()
         ax3, _, raw = analytic_planes(torch, n, device)
@@ -916,8 +945,28 @@ def run_b200(args):
                          "traffic_bytes_per_query_ncu": ncu_traffic(m),
                          "queries_per_step": Q2, "table_gb": o2.table.numel() * 8 / 1e9, "parity": guard}
             assert guard["ok"] and finite, f"parity failure in bench (mode {m}): {guard}"
-            del o2, outs2, vals
+            o2.release()
+            del o2, outs2
+            gc.collect()
             torch.cuda.empty_cache()
+            # the memory-light forms of the same mode: node (Hermite) table and table-free (no table at all)
+            for form, kw in (("node_table", {"table": "nodes"}), ("table_free", {"table": False})):
+                _, rows = analytic_field_rows(torch, n, device)
+                o3 = tricubic(rows, "quiet", mode=m, **kw)
+                del rows
+                torch.cuda.empty_cache()
+                r3, fin3 = time_public_device(torch, o3, q[:Q2 // 2], max(3, args.steps // 2), args.warmup)
+                g3 = oracle_sample_check(o3, [ax_np] * 3, vals, m, 3, 50_000, 13)
+                g3["timed_outputs_finite"] = fin3
+                store = o3._nodes if o3._nodes is not None else o3._packed if o3._packed is not None else o3._planes
+                others[m][form] = {"value": r3, "unit": "queries/s", "of_cell_table": r3 / rate,
+                                   "memory_gb": store.numel() * 8 / 1e9, "parity": g3}
+                assert g3["ok"] and fin3, f"parity failure in bench ({form}, mode {m}): {g3}"
+                o3.release()
+                del o3, store
+                gc.collect()
+                torch.cuda.empty_cache()
+            del vals
         # quadcubic (time-dependent field, 256x256 Lekien-Marsden matrix with the A.py:860 quirk), value + 4-gradient
         from arbinterp_b200 import quadcubic
         shape4 = (48, 48, 48, 32)
@@ -949,8 +998,46 @@ def run_b200(args):
                                                 "uniform random (x,y,z,t) queries" % shape4, "constructor_s": t_ctor4,
                                     "parity": guard}
         assert guard["ok"] and finite, f"parity failure in bench (quadcubic): {guard}"
-        del o4, outs4, q4
+        rate4 = rate
+        o4.release()
+        del o4, outs4
+        gc.collect()
         torch.cuda.empty_cache()
+        o4n = quadcubic(torch.stack([t.reshape(-1) for t in torch.meshgrid(*reversed(axes), indexing="ij")][::-1] +
+                                    [torch.from_numpy(u_np).to(device)], dim=1), "quiet", table="nodes")
+        r4n, fin4n = time_public_device(torch, o4n, q4, max(3, args.steps // 2), args.warmup)
+        g4n = oracle_sample_check(o4n, [a.cpu().numpy() for a in axes], {"n": u_np}, "norm", 4, 50_000, 14, scalar=True)
+        others["quadcubic_norm"]["node_table"] = {"value": r4n, "unit": "queries/s", "of_cell_table": r4n / rate4,
+                                                  "memory_gb": o4n.nodes.numel() * 8 / 1e9, "parity": g4n,
+                                                  "timed_outputs_finite": fin4n}
+        assert g4n["ok"] and fin4n, f"parity failure in bench (quadcubic node table): {g4n}"
+        o4n.release()
+        del o4n, q4
+        gc.collect()
+        torch.cuda.empty_cache()
+        # the headline mode on the node table and table-free
+        vals_main = {}
+        if args.mode in ("vector", "both"):
+            vals_main.update(x=raw_np[0], y=raw_np[1], z=raw_np[2])
+        if args.mode in ("norm", "both"):
+            vals_main["n"] = np.linalg.norm(np.stack(raw_np, axis=1), axis=1)
+        others[args.mode + "_memory_light"] = {}
+        for form, kw in (("node_table", {"table": "nodes"}), ("table_free", {"table": False})):
+            _, rows = analytic_field_rows(torch, n, device)
+            o3 = tricubic(rows, "quiet", mode=args.mode, **kw)
+            del rows
+            torch.cuda.empty_cache()
+            r3, fin3 = time_public_device(torch, o3, q[:Q // 4], max(3, args.steps // 2), args.warmup)
+            g3 = oracle_sample_check(o3, [ax_np] * 3, vals_main, args.mode, 3, 50_000, 15)
+            store = o3._nodes if o3._nodes is not None else o3._packed if o3._packed is not None else o3._planes
+            others[args.mode + "_memory_light"][form] = {"value": r3, "unit": "queries/s", "of_cell_table": r3 / value,
+                                                         "memory_gb": store.numel() * 8 / 1e9, "parity": g3,
+                                                         "timed_outputs_finite": fin3}
+            assert g3["ok"] and fin3, f"parity failure in bench ({form}, mode {args.mode}): {g3}"
+            o3.release()
+            del o3, store
+            gc.collect()
+            torch.cuda.empty_cache()
         _, rows = analytic_field_rows(torch, n, device)
         obj = tricubic(rows, "quiet", mode=args.mode)
         del rows
@@ -961,6 +1048,7 @@ def run_b200(args):
         del outs, cells, q
         table_gb_main = obj.table.numel() * 8 / 1e9
         qbytes = Q * 3 * 8
+        obj.release()
         del obj
         obj = None
         torch.cuda.empty_cache()
