@@ -28,6 +28,7 @@
 #include <cstdlib>
 #include <vector>
 #include <mutex>
+#include <atomic>
 #include "arb_common.cuh"
 #include "arb_build_sep.cuh"
 
@@ -611,7 +612,7 @@ static int get_bfrag(int d, const double** out) {
     return 0;
 }
 
-static int g_build_variant = 0;
+static std::atomic<int> g_build_variant{0};   // measurement knob (arb_set_build_variant)
 
 // Tensor map over the grid [C][nt][nz][ny][nx] (x fastest) with the given box; TMA needs 16-byte global
 // strides, so an odd nx is padded to even in a stream-ordered scratch copy (`padded`, freed by the caller
@@ -815,7 +816,7 @@ int arb_build_coeffs(int d, const double* grid, int ncomp, const int64_t n[4], d
     if (!grid || !table || !n) { arb::set_error("arb_build_coeffs: null pointer"); return 1; }
     if (ncomp < 1 || ncomp > 4) { arb::set_error("arb_build_coeffs: ncomp=%d not in 1..4", ncomp); return 1; }
     cudaStream_t st = (cudaStream_t)stream;
-    const int v = arb::g_build_variant;
+    const int v = arb::g_build_variant.load(std::memory_order_relaxed);
     // 0 (default) and 5..8: separable FP64-pipe kernels (build_sep3_kernel / build_sep4_kernel) in different tile /
     //    march / block-order configurations; 1..3: dense 4^d x 4^d DMMA contraction (1 = its best tile);
     // 9, 4: Kronecker-factored DMMA solve (9 = its best tile).  profiles/r01_build_variants.log
@@ -846,9 +847,7 @@ int arb_build_coeffs(int d, const double* grid, int ncomp, const int64_t n[4], d
 }
 
 int arb_set_build_variant(int variant) {
-    const int old = arb::g_build_variant;
-    arb::g_build_variant = variant;
-    return old;
+    return arb::g_build_variant.exchange(variant);
 }
 
 int arb_build_coeffs_3d(const double* grid, int ncomp, int64_t nx, int64_t ny, int64_t nz, double* table,

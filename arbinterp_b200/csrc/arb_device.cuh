@@ -23,7 +23,15 @@ struct QueryParams {
     int64_t layer_cells;        // prod(nc[0..d-2])
     int64_t nn[4];              // node table (arb_nodes.cuh): nodes per axis = nc + 1
     int64_t node_comp_stride;   // doubles between the components of a node table
+    // routed results (slab-sharded tables, arb_query_routed): row n's outputs go to result row (route[n] & ROUTE_ROW) of
+    // rank (route[n] >> ROUTE_SHIFT)'s buffer -- peer memory reached over NVLink -- laid out [comps | norm | grad | cell]
+    const int64_t* route;
+    double* peer[ARB_MAX_PEERS];
+    int64_t peer_ld;            // doubles per result row
+    int off_norm, off_grad, off_cell;
 };
+constexpr int ROUTE_SHIFT = 40;
+constexpr int64_t ROUTE_ROW = (int64_t(1) << ROUTE_SHIFT) - 1;
 
 // --------------------------------------------------------------------------------------
 // locate: bounds mask, cell index, cell-fraction coordinates (A.py:350-373, 1069-1092).

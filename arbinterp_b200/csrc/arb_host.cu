@@ -548,3 +548,17 @@ extern "C" int arb_query_grid_host(const arb_geom* g, const double* grid, int64_
     return query_host_impl(g, grid, pitch_x, mode, q_host, N, ldq, out_comps_host, out_norm_host, out_grad_host,
                            out_cell_host, chunk_rows);
 }
+
+// Let kernels on the current device store into memory of `peer_device` (the routed form of the query kernel writes
+// results into the home rank's buffer over NVLink).  Already-enabled is not an error.
+extern "C" int arb_enable_peer_access(int peer_device) {
+    int dev = 0;
+    ARB_CUDA(cudaGetDevice(&dev));
+    if (dev == peer_device) return 0;
+    int can = 0;
+    ARB_CUDA(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+    if (!can) { arb::set_error("arb_enable_peer_access: device %d cannot access device %d", dev, peer_device); return 2; }
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
+    return arb::check_cuda(e, "cudaDeviceEnablePeerAccess");
+}

@@ -30,8 +30,9 @@
 
 namespace arb {
 
-static int g_query_variant = 0;
-int current_query_variant() { return g_query_variant; }
+// debugging / measurement knob (arb_set_query_variant); atomic so that concurrent callers at least see a whole value
+static std::atomic<int> g_query_variant{0};
+int current_query_variant() { return g_query_variant.load(std::memory_order_relaxed); }
 
 template <int MODE, int D> struct OutCount { static constexpr int NV = MODE == 0 ? 3 : (MODE == 1 ? 1 + D : 4 + D); };
 constexpr int next_pow2(int v) { return v <= 1 ? 1 : (v <= 2 ? 2 : (v <= 4 ? 4 : (v <= 8 ? 8 : 16))); }
@@ -267,8 +268,9 @@ __global__ void __launch_bounds__(THREADS) query_bulk_kernel(const QueryParams p
 //   GRID_IL : raw grid   [nz][ny][nx][4] (table-free); lane k holds z-plane k of the 4x4x4 neighbourhood (4 segments
 //             of 128 B = the four x-neighbours of all components).
 constexpr int KIND_CELLS = 0, KIND_NODES = 1, KIND_NODES_IL = 2, KIND_GRID_IL = 3;
+// ROUTED: the outputs of row n go to the result row route[n] names in a peer rank's buffer (QueryParams::route / peer).
 template <int D, int MODE, int THREADS, bool DEDUP, bool LOOPC = false, int SLOTS = 32, bool PREFETCH = false,
-          bool FETCH_LDGSTS = false, int KIND = KIND_CELLS, bool QUIRK4 = true>
+          bool FETCH_LDGSTS = false, int KIND = KIND_CELLS, bool QUIRK4 = true, bool ROUTED = false>
 __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams p, const int* __restrict__ gate, int gate_want) {
     static_assert(KIND == KIND_CELLS || FETCH_LDGSTS, "node slots are gathered from several segments");
     constexpr bool QUAD = (KIND == KIND_NODES_IL || KIND == KIND_GRID_IL);
@@ -322,6 +324,20 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
         } else {
             if (n < p.N) L = locate<D>(p, n);
         }
+        // where this row's outputs go
+        double *o_comps = nullptr, *o_norm = nullptr, *o_grad = nullptr;
+        int64_t* o_cell = nullptr;
+        if (n < p.N) {
+            if (ROUTED) {
+                const int64_t rt = p.route[n];
+                double* row = p.peer[rt >> ROUTE_SHIFT] + (rt & ROUTE_ROW) * p.peer_ld;
+                o_comps = row; o_norm = row + p.off_norm; o_grad = row + p.off_grad;
+                o_cell = reinterpret_cast<int64_t*>(row + p.off_cell);
+            } else {
+                o_comps = p.out_comps + n * 3; o_norm = p.out_norm + n; o_grad = p.out_grad + n * D;
+                o_cell = p.out_cell ? p.out_cell + n : nullptr;
+            }
+        }
 #pragma unroll 1
       for (int ci = 0; ci < (LOOPC ? C : 1); ++ci) {
         const int comp = LOOPC ? ci : (int)(item - batch * C);
@@ -344,7 +360,7 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
             if (npass < 1) npass = 1;
         }
         if (comp == 0 && sl == 0 && n < p.N) {
-            if (p.out_cell) p.out_cell[n] = L.cell_global;
+            if (o_cell) *o_cell = L.cell_global;
             if (L.masked) mask_row_in_place(p, n);
         }
         const bool grad_comp = (MODE == 1) || (MODE == 2 && (QUAD || comp == 3));     // warp-uniform
@@ -467,21 +483,21 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
             if (n < p.N && sl == 0) {
                 const double nan = qnan();
 #pragma unroll
-                for (int c = 0; c < 3; ++c) p.out_comps[n * 3 + c] = L.ok ? g[c] : nan;
+                for (int c = 0; c < 3; ++c) o_comps[c] = L.ok ? g[c] : nan;
                 if (MODE == 2) {
-                    p.out_norm[n] = L.ok ? g[3] : nan;
+                    *o_norm = L.ok ? g[3] : nan;
 #pragma unroll
-                    for (int a = 0; a < 3; ++a) p.out_grad[n * 3 + a] = L.ok ? __ddiv_rn(g[4 + a], p.h[a]) : nan;
+                    for (int a = 0; a < 3; ++a) o_grad[a] = L.ok ? __ddiv_rn(g[4 + a], p.h[a]) : nan;
                 }
             }
         } else if (n < p.N && sl == 0) {
             const double nan = qnan();
             if (!grad_comp) {
-                p.out_comps[n * 3 + comp] = L.ok ? g[0] : nan;
+                o_comps[comp] = L.ok ? g[0] : nan;
             } else {
-                p.out_norm[n] = L.ok ? g[0] : nan;
+                *o_norm = L.ok ? g[0] : nan;
 #pragma unroll
-                for (int a = 0; a < D; ++a) p.out_grad[n * D + a] = L.ok ? __ddiv_rn(g[1 + a], p.h[a]) : nan;
+                for (int a = 0; a < D; ++a) o_grad[a] = L.ok ? __ddiv_rn(g[1 + a], p.h[a]) : nan;
             }
         }
       }
@@ -830,13 +846,13 @@ static int launch_bulk(const QueryParams& p, cudaStream_t st) {
 }
 
 template <int D, int MODE, int THREADS, bool DEDUP, bool LOOPC = false, int SLOTS = 32, bool PREFETCH = false,
-          bool FETCH_LDGSTS = false, int KIND = KIND_CELLS, bool QUIRK4 = true>
+          bool FETCH_LDGSTS = false, int KIND = KIND_CELLS, bool QUIRK4 = true, bool ROUTED = false>
 static int launch_block(const QueryParams& p, cudaStream_t st, const int* gate = nullptr, int gate_want = 0) {
     constexpr bool QUAD = (KIND == KIND_NODES_IL || KIND == KIND_GRID_IL);
     constexpr int C = QUAD ? 1 : (MODE == 0 ? 3 : (MODE == 1 ? 1 : 4));
     constexpr int QPW = (D == 4 || QUAD) ? 8 : 32;
     const size_t smem = (size_t)(THREADS / 32) * SLOTS * 528;
-    auto k = query_block_kernel<D, MODE, THREADS, DEDUP, LOOPC, SLOTS, PREFETCH, FETCH_LDGSTS, KIND, QUIRK4>;
+    auto k = query_block_kernel<D, MODE, THREADS, DEDUP, LOOPC, SLOTS, PREFETCH, FETCH_LDGSTS, KIND, QUIRK4, ROUTED>;
     static LaunchCache cache = {};
     const int64_t items = ((p.N + QPW - 1) / QPW) * (LOOPC ? 1 : C);
     const int grid = persistent_grid(k, THREADS, smem, (items + THREADS / 32 - 1) / (THREADS / 32), cache);
@@ -1018,7 +1034,7 @@ int query_gridil_device(const arb_geom* g, const double* packed, int mode, doubl
     if (g->d != 3 || mode == ARB_MODE_NORM) { set_error("arb_query_gridil: 3-D 'vector' / 'both' only"); return 1; }
     if (g->slab_lo != 0 || g->slab_hi != g->ncell[2]) { set_error("arb_query_gridil: slabs are not supported"); return 1; }
     if (reinterpret_cast<uintptr_t>(packed) & 31) { set_error("arb_query_gridil: grid must be 32-byte aligned"); return 1; }
-    const int v = g_query_variant;
+    const int v = current_query_variant();
     if (mode == ARB_MODE_VECTOR) {
         if (v == 73) return launch_block<3, 0, 128, false, true, 32, true, true, KIND_GRID_IL>(p, st);
         return launch_block<3, 0, 128, true, true, 32, true, true, KIND_GRID_IL>(p, st);
@@ -1037,7 +1053,7 @@ int query_nodes_device(const arb_geom* g, const double* nodes, int mode, double*
     if (g->slab_lo != 0 || g->slab_hi != g->ncell[g->d - 1]) { set_error("arb_query_nodes: slabs are not supported (a node table is small enough to replicate)"); return 1; }
     if (reinterpret_cast<uintptr_t>(nodes) & 127) { set_error("arb_query_nodes: node table must be 128-byte aligned"); return 1; }
     const bool quirk = !(g->flags & ARB_GEOM_FIXED_D4);
-    const int v = g_query_variant;
+    const int v = current_query_variant();
     if (g->d == 3) {
         if (mode == ARB_MODE_VECTOR) return dispatch_nodes<3, 0>(p, st, v, quirk);
         if (mode == ARB_MODE_NORM) return dispatch_nodes<3, 1>(p, st, v, quirk);
@@ -1046,6 +1062,38 @@ int query_nodes_device(const arb_geom* g, const double* nodes, int mode, double*
     if (mode == ARB_MODE_VECTOR) return dispatch_nodes<4, 0>(p, st, v, quirk);
     if (mode == ARB_MODE_NORM) return dispatch_nodes<4, 1>(p, st, v, quirk);
     return dispatch_nodes<4, 2>(p, st, v, quirk);
+}
+
+// Slab-sharded tables: evaluate the rows this rank received and store every row's outputs into its home rank's result
+// buffer (peer memory over NVLink) at its home row -- the return all-to-all and the re-ordering pass are gone.
+int query_routed_device(const arb_geom* g, const double* table, int mode, double* q, int64_t N, int64_t ldq,
+                        const int64_t* route, double* const* peers, int npeers, int64_t ld, cudaStream_t st) {
+    QueryParams p;
+    const int rc = fill_params("arb_query_routed", g, true, table, mode, q, N, ldq, nullptr, nullptr, nullptr, nullptr,
+                               nullptr, nullptr, p, false);
+    if (rc) return rc < 0 ? 0 : rc;
+    const int d = g->d;
+    const int ncomp_out = (mode == ARB_MODE_NORM) ? 0 : 3, ngrad = (mode == ARB_MODE_VECTOR) ? 0 : 1 + d;
+    if (!route || !peers || npeers < 1 || npeers > ARB_MAX_PEERS || ld < ncomp_out + ngrad + 1) {
+        set_error("arb_query_routed: need route, 1..%d peers and ld >= %d (npeers=%d ld=%lld)", ARB_MAX_PEERS,
+                  ncomp_out + ngrad + 1, npeers, (long long)ld);
+        return 1;
+    }
+    p.route = route;
+    for (int r = 0; r < npeers; ++r) {
+        if (!peers[r]) { set_error("arb_query_routed: peers[%d] is null", r); return 1; }
+        p.peer[r] = peers[r];
+    }
+    p.peer_ld = ld;
+    p.off_norm = ncomp_out; p.off_grad = ncomp_out + 1; p.off_cell = ncomp_out + ngrad;
+    if (d == 3) {
+        if (mode == ARB_MODE_VECTOR) return launch_block<3, 0, 128, true, false, 32, false, false, KIND_CELLS, true, true>(p, st);
+        if (mode == ARB_MODE_NORM) return launch_block<3, 1, 128, true, false, 32, false, false, KIND_CELLS, true, true>(p, st);
+        return launch_block<3, 2, 128, true, false, 32, false, false, KIND_CELLS, true, true>(p, st);
+    }
+    if (mode == ARB_MODE_VECTOR) return launch_block<4, 0, 128, true, true, 32, false, false, KIND_CELLS, true, true>(p, st);
+    if (mode == ARB_MODE_NORM) return launch_block<4, 1, 128, true, true, 32, false, false, KIND_CELLS, true, true>(p, st);
+    return launch_block<4, 2, 128, true, true, 32, false, false, KIND_CELLS, true, true>(p, st);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1117,7 +1165,7 @@ int query_grid_device(const arb_geom* g, const double* grid, int64_t pitch_x, in
                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { set_error("arb_query_grid: cuTensorMapEncodeTiled failed with CUresult %d", (int)cr); return 2; }
-    const bool dedup = g_query_variant != 20;      // variant 20: no warp de-duplication (here as in the table kernel)
+    const bool dedup = current_query_variant() != 20;      // variant 20: no warp de-duplication (here as in the table kernel)
     if (d == 3) {
         if (!dedup) {
             if (mode == ARB_MODE_VECTOR) return launch_grid<0, false>(tm, p, st);
@@ -1148,9 +1196,7 @@ int query_grid_device(const arb_geom* g, const double* grid, int64_t pitch_x, in
 extern "C" {
 
 int arb_set_query_variant(int variant) {
-    const int old = arb::g_query_variant;
-    arb::g_query_variant = variant;
-    return old;
+    return arb::g_query_variant.exchange(variant);
 }
 
 int arb_query_grid(const arb_geom* g, const double* grid, int64_t pitch_x, int mode, double* q, int64_t N, int64_t ldq,
@@ -1158,6 +1204,11 @@ int arb_query_grid(const arb_geom* g, const double* grid, int64_t pitch_x, int m
                    unsigned long long* masked_count, void* stream) {
     return arb::query_grid_device(g, grid, pitch_x, mode, q, N, ldq, out_comps, out_norm, out_grad, out_cell,
                                   masked_rows, masked_count, (cudaStream_t)stream);
+}
+
+int arb_query_routed(const arb_geom* g, const double* table, int mode, double* q, int64_t N, int64_t ldq,
+                     const int64_t* route, double* const* peers, int npeers, int64_t ld, void* stream) {
+    return arb::query_routed_device(g, table, mode, q, N, ldq, route, peers, npeers, ld, (cudaStream_t)stream);
 }
 
 int arb_query_gridil(const arb_geom* g, const double* packed, int mode, double* q, int64_t N, int64_t ldq,
@@ -1178,6 +1229,6 @@ int arb_query(const arb_geom* g, const double* table, int mode, double* q, int64
               double* out_norm, double* out_grad, int64_t* out_cell, int64_t* masked_rows,
               unsigned long long* masked_count, void* stream) {
     return arb::query_device(g, table, mode, q, N, ldq, out_comps, out_norm, out_grad, out_cell, masked_rows,
-                             masked_count, (cudaStream_t)stream, arb::g_query_variant);
+                             masked_count, (cudaStream_t)stream, arb::current_query_variant());
 }
 }

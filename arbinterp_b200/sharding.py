@@ -59,10 +59,13 @@ def _no_mark(name: str) -> None:
     pass
 
 
-def route_rows(rows: torch.Tensor, owner: torch.Tensor, group=None, mark: Callable[[str], None] = _no_mark):
+def route_rows(rows: torch.Tensor, owner: torch.Tensor, group=None, mark: Callable[[str], None] = _no_mark,
+               with_home_rows: bool = False):
     """Send every row of ``rows`` to rank ``owner[row]`` (one all-to-all of the counts, one of the rows).
     Returns ``(received, order, send_split, recv_split)``: ``order`` sorts the caller's rows by owner (what was
     sent is ``rows[order]``), the splits are what :func:`return_rows` needs to send answers back.
+    ``with_home_rows``: a fifth value, the row number every received row has in its sender's batch (``order`` sent
+    along in a second, 8-byte-per-row all-to-all) -- what the fused return leg addresses its peer stores with.
     ``mark(name)`` is called at the end of each phase (sort / counts / permute / alltoall) for profiling."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
@@ -83,6 +86,11 @@ def route_rows(rows: torch.Tensor, owner: torch.Tensor, group=None, mark: Callab
     mark("permute")
     recvbuf = rows.new_empty((sum(recv_split), rows.shape[1]))
     dist.all_to_all_single(recvbuf, sendbuf, recv_split, send_split, group=group)
+    if with_home_rows:
+        home_rows = order.new_empty(sum(recv_split))
+        dist.all_to_all_single(home_rows, order.contiguous(), recv_split, send_split, group=group)
+        mark("alltoall")
+        return recvbuf, order, send_split, recv_split, home_rows
     mark("alltoall")
     return recvbuf, order, send_split, recv_split
 
@@ -212,6 +220,63 @@ def broadcast_ingested(field, d: int, src: int = 0, device=None, group=None):
     return out
 
 
+class PeerResults:
+    """One result buffer per rank, ``(rows, ld)`` float64, mapped into every rank of the group, so that the routed form
+    of the query kernel (``arb_query_routed``) can store a row's outputs straight into its home rank's buffer over
+    NVLink / NVSwitch.  Mapping: ``torch.distributed._symmetric_memory`` when it is available and works for the group,
+    else CUDA IPC handles exchanged with ``all_gather_object`` (``torch.multiprocessing.reductions``) plus
+    ``cudaDeviceEnablePeerAccess``.  Raises when neither works (the caller falls back to the all-to-all return)."""
+
+    def __init__(self, lib, device, group, rows: int, ld: int):
+        import torch.distributed as dist
+        self.rows, self.ld = int(rows), int(ld)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.how = None
+        self._keep = []
+        errors = []
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            buf = symm_mem.empty((self.rows, self.ld), dtype=torch.float64, device=device)
+            name = (group if group is not None else dist.group.WORLD).group_name
+            hdl = symm_mem.rendezvous(buf, name)
+            self.buf, self.ptrs, self.how = buf, [int(x) for x in hdl.buffer_ptrs], "symmetric_memory"
+            self._keep.append(hdl)
+        except Exception as e:                                   # noqa: BLE001 -- try the IPC route
+            errors.append(f"symmetric_memory: {type(e).__name__}: {e}")
+        # every rank must take the same route
+        ok = torch.tensor([int(self.how is not None)], dtype=torch.int64, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if not bool(ok.item()):
+            self.how = None
+            try:
+                from torch.multiprocessing.reductions import reduce_tensor
+                self.buf = torch.empty((self.rows, self.ld), dtype=torch.float64, device=device)
+                fn, args = reduce_tensor(self.buf)
+                gathered = [None] * self.world
+                dist.all_gather_object(gathered, args, group=group)
+                self.ptrs = []
+                with torch.cuda.device(device):
+                    for r in range(self.world):
+                        if r == self.rank:
+                            self.ptrs.append(self.buf.data_ptr())
+                            continue
+                        t = fn(*gathered[r])
+                        self._keep.append(t)
+                        if t.device != self.buf.device:
+                            from . import _lib
+                            _lib.check(lib.arb_enable_peer_access(t.device.index), "arb_enable_peer_access")
+                        self.ptrs.append(t.data_ptr())
+                self.how = "cuda_ipc"
+            except Exception as e:                               # noqa: BLE001
+                errors.append(f"cuda_ipc: {type(e).__name__}: {e}")
+            ok = torch.tensor([int(self.how is not None)], dtype=torch.int64, device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if not bool(ok.item()):
+                raise RuntimeError("no peer mapping of the result buffers: " + "; ".join(errors))
+        import ctypes
+        self.cptrs = (ctypes.c_void_p * self.world)(*self.ptrs)
+
+
 class ReplicatedInterp:
     """One process per GPU, the coefficient table replicated: rank ``src`` holds the field, it is ingested once, the
     dense planes are broadcast (NCCL over NVLink) and every rank builds its own table (cheaper than moving 8-33 GB of
@@ -248,6 +313,7 @@ class SlabShardedInterp:
         import torch.distributed as dist
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        kwargs_fused = kwargs.pop("fused", False)
         device = kwargs.get("device") or torch.device("cuda", torch.cuda.current_device())
         d = cls._d
         full = broadcast_ingested(field, d, src=src, device=device, group=group)
@@ -263,6 +329,11 @@ class SlabShardedInterp:
         self.d = d
         g = self.local._geo
         self._slow = (g.int_min[d - 1], g.int_max[d - 1], g.h[d - 1])
+        # return leg fused into the query kernel (results stored into the home rank's buffer over NVLink); "auto" tries
+        # it on CUDA + NCCL and falls back to the all-to-all return when the peer mapping is not available
+        self.fused = kwargs_fused
+        self._peer = None
+        self._peer_error = None
 
     def Query(self, q, timing: Optional[dict] = None):
         """Drop-in range query over the sharded table (rQuery1/2/3, A.py:1064-1258 / 344-521): ``q`` holds THIS rank's
@@ -307,7 +378,11 @@ class SlabShardedInterp:
             cells = self.local._last_cells.view(torch.float64).unsqueeze(1)     # int64 bits ride along exactly
             return torch.cat(list(res) + [cells], dim=1)
 
-        flat = exchange_and_query(coords, owner, evaluate, sum(widths) + 1, self.group, mark)
+        flat = None
+        if self.fused and self.world <= 16:
+            flat = self._query_fused(coords, owner, sum(widths) + 1, mark)
+        if flat is None:
+            flat = exchange_and_query(coords, owner, evaluate, sum(widths) + 1, self.group, mark)
         outs, col = [], 0
         for w in widths:
             outs.append(flat[:, col:col + w].contiguous())
@@ -327,6 +402,47 @@ class SlabShardedInterp:
                 timing[name + "_ms"] = timing.get(name + "_ms", 0.0) + e0.elapsed_time(e1)
             timing["total_ms"] = timing.get("total_ms", 0.0) + ev[0][1].elapsed_time(ev[-1][1])
         return outs[0] if len(outs) == 1 else tuple(outs)
+
+    def _query_fused(self, coords, owner, ld, mark):
+        """Rows travel to their owner with their home row number; the owner's kernel (``arb_query_routed``) stores every
+        row's outputs into the home rank's result buffer at that row -- peer memory over NVLink -- so the results arrive
+        in the caller's order with no return all-to-all and no re-ordering pass.  Returns the (n, ld) result rows of
+        this rank, or None when the peer mapping is unavailable (the caller then takes the all-to-all return)."""
+        import ctypes
+        import torch.distributed as dist
+        from . import _lib
+        loc = self.local
+        dev = loc._device
+        if self._peer_error is not None or dev.type != "cuda" or dist.get_backend(self.group) != "nccl":
+            return None
+        d, n = self.d, coords.shape[0]
+        # every rank's buffer must hold its own batch; (re)map collectively when any rank's batch outgrows it
+        need = torch.tensor([n], dtype=torch.int64, device=dev)
+        dist.all_reduce(need, op=dist.ReduceOp.MAX, group=self.group)
+        need = int(need.item())
+        if self._peer is None or self._peer.rows < need or self._peer.ld != ld:
+            try:
+                self._peer = PeerResults(loc._lib, dev, self.group, max(need, 1) * 5 // 4 + 1024, ld)
+            except Exception as e:                               # noqa: BLE001 -- remembered: the group falls back together
+                self._peer, self._peer_error = None, f"{type(e).__name__}: {e}"
+                if self.fused is True:
+                    raise
+                return None
+        peer = self._peer
+        recv, _, _, recv_split, home_rows = route_rows(coords, owner, self.group, mark, with_home_rows=True)
+        m = recv.shape[0]
+        home = torch.repeat_interleave(torch.arange(self.world, dtype=torch.int64, device=dev),
+                                       torch.tensor(recv_split, dtype=torch.int64, device=dev), output_size=m)
+        route = (home << 40) | home_rows
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(loc._lib.arb_query_routed(ctypes.byref(loc._cgeom), loc.table.data_ptr(), loc._mode_code,
+                                                 recv.data_ptr(), m, d, route.data_ptr(), peer.cptrs, self.world, ld,
+                                                 stream), "arb_query_routed")
+        mark("kernel")
+        dist.barrier(group=self.group)          # every rank's kernel has finished: all rows of this batch have landed
+        mark("alltoall_back")
+        return peer.buf[:n]
 
     @property
     def queryInds(self):

@@ -670,10 +670,10 @@ def run_sharded(torch, dist, args, rank, world, device):
     vel[:, 3] = (hi_t[3] - lo_t[3]) * 0.01
     only_space = torch.tensor([1, 1, 1, 0], dtype=torch.float64, device=device)
     span = (hi_t - lo_t) * (1 - 1e-9)
-    timing = {}
-    step_ms = []
+    timing, timing_plain = {}, {}
+    step_ms, plain_ms = [], []
     node_ms = []
-    finite = True
+    finite, same_fused = True, True
     for step in range(args.warmup + args.steps):
         pos = pos + vel + 0.002 * (hi_t - lo_t) * torch.randn(n, 4, generator=gen, dtype=torch.float64, device=device) * only_space
         rel = torch.remainder(pos - lo_t, 2 * span)
@@ -685,9 +685,24 @@ def run_sharded(torch, dist, args, rank, world, device):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        obj.fused = "auto"        # return leg fused into the kernel (peer stores over NVLink) when the buffers can be mapped
         res = obj.Query(q, timing=timing if timed else None)
         e1.record()
         torch.cuda.synchronize()
+        cells_fused = obj._last_cells
+        # the same rows with the all-to-all return (the library default)
+        was, obj.fused = obj.fused, False
+        dist.barrier()
+        e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e4.record()
+        res_plain = obj.Query(q, timing=timing_plain if timed else None)
+        e5.record()
+        torch.cuda.synchronize()
+        obj.fused = was
+        same_fused &= all(bool(torch.equal(a.view(torch.int64), b.view(torch.int64))) for a, b in zip(res, res_plain)) and \
+            bool(torch.equal(cells_fused, obj._last_cells))
+        if timed:
+            plain_ms.append(e4.elapsed_time(e5))
         dist.barrier()
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e2.record()
@@ -703,9 +718,17 @@ def run_sharded(torch, dist, args, rank, world, device):
     node_err = scaled_error(tuple(r[:m].cpu().numpy() for r in res_n), tuple(r[:m].cpu().numpy() for r in res), 4,
                             g.h, float(torch.stack([r.abs().max() for r in res[:2]]).max()))
     same_cells = bool(torch.equal(rep.local._last_cells, obj._last_cells))
-    tn = torch.tensor([sum(node_ms), node_err, float(not same_cells)], dtype=torch.float64, device=device)
+    tn = torch.tensor([sum(node_ms), node_err, float(not same_cells), sum(plain_ms), float(not same_fused)],
+                      dtype=torch.float64, device=device)
     dist.all_reduce(tn, op=dist.ReduceOp.MAX)
     node_s, node_err, cells_differ = float(tn[0]) / 1e3, float(tn[1]), bool(tn[2] > 0)
+    plain_s, fused_differs = float(tn[3]) / 1e3, bool(tn[4] > 0)
+    php = torch.tensor([timing_plain.get(k + "_ms", 0.0) for k in
+                        ("owner", "sort", "counts", "permute", "alltoall", "kernel", "alltoall_back", "scatter", "unpack")],
+                       dtype=torch.float64, device=device)
+    dist.all_reduce(php, op=dist.ReduceOp.MAX)
+    php = (php / args.steps).tolist()
+    peer_how = obj._peer.how if getattr(obj, "_peer", None) is not None else None
     node_gb = rep.local.nodes.numel() * 8 / 1e9
     t = torch.tensor([sum(step_ms)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -732,6 +755,15 @@ def run_sharded(torch, dist, args, rank, world, device):
             "sort + permute + scatter": ph[1] + ph[3] + ph[7], "owner + unpack": ph[0] + ph[8],
             "each": dict(zip(("owner", "sort", "counts", "permute", "alltoall", "kernel", "alltoall_back", "scatter", "unpack"), ph))},
         "kernel_frac_of_measured_hbm": (ALG_BYTES[(4, "both")] * n / (ph[5] * 1e-3) / 1e9 / measured_peak()[0]) if ph[5] > 0 else None,
+        "return_leg": ("fused into the query kernel: every row's outputs are stored into its home rank's result buffer "
+                       f"over NVLink (arb_query_routed, peer mapping: {peer_how})") if peer_how else
+                      "all-to-all (peer mapping of the result buffers unavailable: " + str(getattr(obj, "_peer_error", None)) + ")",
+        "all_to_all_return": {
+            "what": "the same rows with the return leg as an NCCL all-to-all of the result rows + a re-ordering pass",
+            "value": world * n * args.steps / plain_s, "unit": "queries/s", "ms_per_step": 1e3 * plain_s / args.steps,
+            "fused_speedup": plain_s / total_s, "bit_identical_to_fused": not fused_differs,
+            "phase_ms_per_step_max_over_ranks": dict(zip(("owner", "sort", "counts", "permute", "alltoall", "kernel",
+                                                          "alltoall_back", "scatter", "unpack"), php))},
         "replicated_node_table": {
             "what": "the same field as a node (Hermite) table replicated on every rank (quadcubic(table='nodes') via "
                     "sharding.ReplicatedInterp): each rank answers its own rows, no exchange; same queries as above",

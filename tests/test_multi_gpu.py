@@ -119,3 +119,56 @@ def test_sharded_push_equals_unsharded_world2(tmp_path):
         assert int(z["lost"]) == int(np.isnan(z["pr"][:, 0]).sum())
         lost += int(z["lost"])
     assert lost == int(z["lost_ref"]) and lost > 0
+
+
+def _fused_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from arbinterp_b200 import quadcubic, tricubic
+    from arbinterp_b200.sharding import SlabShardedInterp
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    rng = np.random.default_rng(100 + rank)
+    ok, how = True, ""
+    for cls, gname, d in ((quadcubic, "quad_8x7x7x6", 4), (tricubic, "tri_12x10x9", 3)):
+        field = load_golden(gname)["field"]
+        for mode in ("vector", "norm", "both"):
+            whole = cls(field.copy(), "quiet", mode=mode)
+            fused = SlabShardedInterp(cls, field if rank == 0 else None, "quiet", mode=mode, fused=True)
+            plain = SlabShardedInterp(cls, field if rank == 0 else None, "quiet", mode=mode, fused=False)
+            lo = np.array(whole._geo.int_min); hi = np.array(whole._geo.int_max)
+            for n in (5000 + 37 * rank, 11, 0, 20000):            # growing, shrinking and empty batches re-use / re-map the buffers
+                q = lo + rng.uniform(-0.05, 1.05, (n, d + 1))[:, :d] * (hi - lo)
+                if n > 100:
+                    q[::97, 1] = np.nan
+                qa, qb, qc = q.copy(), q.copy(), q.copy()
+                ra, rb, rc = whole.Query(qa) if n else None, fused.Query(qb), plain.Query(qc)
+                rb = rb if isinstance(rb, tuple) else (rb,)
+                rc = rc if isinstance(rc, tuple) else (rc,)
+                if n:
+                    ra = ra if isinstance(ra, tuple) else (ra,)
+                    ok &= all(np.array_equal(x, y, equal_nan=True) for x, y in zip(rb, ra))
+                    ok &= bool(np.array_equal(fused.queryInds, whole.queryInds)) and bool(np.array_equal(qb, qa, equal_nan=True))
+                ok &= all(np.array_equal(x, y, equal_nan=True) for x, y in zip(rb, rc))
+                ok &= bool(np.array_equal(fused.queryInds, plain.queryInds))
+            how = fused._peer.how if fused._peer is not None else "none"
+    np.save(os.path.join(out_dir, f"fused{rank}.npy"), np.array([ok]))
+    with open(os.path.join(out_dir, f"how{rank}.txt"), "w") as f:
+        f.write(how)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_fused_peer_store_return_world2(tmp_path):
+    """SlabShardedInterp.Query with the return leg fused into the kernel (arb_query_routed: results stored into the home
+    rank's buffer over NVLink) is bit-identical to the all-to-all return and to the unsharded table -- outputs, global
+    queryInds and in-place NaN rows; 3-D and 4-D, every mode, batches that grow, shrink and are empty."""
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_fused_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for rank in range(world):
+        assert bool(np.load(tmp_path / f"fused{rank}.npy")[0])
+        assert open(tmp_path / f"how{rank}.txt").read() in ("symmetric_memory", "cuda_ipc")
