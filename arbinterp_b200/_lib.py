@@ -92,7 +92,7 @@ def load():
     lib.arb_query_gridil_host.restype = i32
     lib.arb_query_gridil_host.argtypes = lib.arb_query_host.argtypes
     lib.arb_query_routed.restype = i32
-    lib.arb_query_routed.argtypes = [ctypes.POINTER(ArbGeom), vp, i32, vp, i64, i64, vp, ctypes.POINTER(vp), i32, i64, vp]
+    lib.arb_query_routed.argtypes = [ctypes.POINTER(ArbGeom), vp, i32, vp, i64, i64, vp, vp, ctypes.POINTER(vp), i32, i64, vp]
     lib.arb_enable_peer_access.restype = i32
     lib.arb_enable_peer_access.argtypes = [i32]
     lib.arb_push.restype = i32

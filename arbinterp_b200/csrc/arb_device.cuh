@@ -23,15 +23,15 @@ struct QueryParams {
     int64_t layer_cells;        // prod(nc[0..d-2])
     int64_t nn[4];              // node table (arb_nodes.cuh): nodes per axis = nc + 1
     int64_t node_comp_stride;   // doubles between the components of a node table
-    // routed results (slab-sharded tables, arb_query_routed): row n's outputs go to result row (route[n] & ROUTE_ROW) of
-    // rank (route[n] >> ROUTE_SHIFT)'s buffer -- peer memory reached over NVLink -- laid out [comps | norm | grad | cell]
-    const int64_t* route;
+    // routed results (slab-sharded tables, arb_query_routed): rows [seg_start[h], seg_start[h+1]) came from rank h; row n's
+    // outputs go to result row home_row[n] of rank h's buffer -- peer memory reached over NVLink -- laid out
+    // [comps | norm | grad | cell (| pad)], peer_ld doubles per row
+    int npeers;
+    int64_t seg_start[ARB_MAX_PEERS + 1];
+    const int64_t* home_row;
     double* peer[ARB_MAX_PEERS];
-    int64_t peer_ld;            // doubles per result row
-    int off_norm, off_grad, off_cell;
+    int64_t peer_ld;
 };
-constexpr int ROUTE_SHIFT = 40;
-constexpr int64_t ROUTE_ROW = (int64_t(1) << ROUTE_SHIFT) - 1;
 
 // --------------------------------------------------------------------------------------
 // locate: bounds mask, cell index, cell-fraction coordinates (A.py:350-373, 1069-1092).

@@ -268,7 +268,11 @@ __global__ void __launch_bounds__(THREADS) query_bulk_kernel(const QueryParams p
 //   GRID_IL : raw grid   [nz][ny][nx][4] (table-free); lane k holds z-plane k of the 4x4x4 neighbourhood (4 segments
 //             of 128 B = the four x-neighbours of all components).
 constexpr int KIND_CELLS = 0, KIND_NODES = 1, KIND_NODES_IL = 2, KIND_GRID_IL = 3;
-// ROUTED: the outputs of row n go to the result row route[n] names in a peer rank's buffer (QueryParams::route / peer).
+// ROUTED (slab-sharded tables): the rows are the ones other ranks sent here, in segments by sender; a row's outputs are
+// stored into the SENDER's result buffer -- peer memory over NVLink -- at the row it has in the sender's batch
+// (home_row[n]).  The outputs of a warp item are assembled in shared memory (the slot ring is free by then) and every
+// result row leaves as 16-byte pieces stored by adjacent lanes, because small scattered remote stores are what NVLink
+// is worst at (one 8-byte store per output: the kernel took twice as long at 8 ranks).
 template <int D, int MODE, int THREADS, bool DEDUP, bool LOOPC = false, int SLOTS = 32, bool PREFETCH = false,
           bool FETCH_LDGSTS = false, int KIND = KIND_CELLS, bool QUIRK4 = true, bool ROUTED = false>
 __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams p, const int* __restrict__ gate, int gate_want) {
@@ -327,16 +331,17 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
         // where this row's outputs go
         double *o_comps = nullptr, *o_norm = nullptr, *o_grad = nullptr;
         int64_t* o_cell = nullptr;
-        if (n < p.N) {
-            if (ROUTED) {
-                const int64_t rt = p.route[n];
-                double* row = p.peer[rt >> ROUTE_SHIFT] + (rt & ROUTE_ROW) * p.peer_ld;
-                o_comps = row; o_norm = row + p.off_norm; o_grad = row + p.off_grad;
-                o_cell = reinterpret_cast<int64_t*>(row + p.off_cell);
-            } else {
-                o_comps = p.out_comps + n * 3; o_norm = p.out_norm + n; o_grad = p.out_grad + n * D;
-                o_cell = p.out_cell ? p.out_cell + n : nullptr;
-            }
+        constexpr int OFFN = (MODE == 1) ? 0 : 3;                           // routed result row: [comps | norm grad | cell | pad]
+        constexpr int OFFC = (MODE == 0) ? 3 : OFFN + 1 + D;
+        constexpr int LDS = (OFFC + 2) / 2 * 2;
+        double rowv[ROUTED ? LDS : 1];
+        if (ROUTED) {
+            static_assert(!ROUTED || (LOOPC && !QUAD), "routed rows are assembled per query: components looped in the item");
+#pragma unroll
+            for (int i = 0; i < (ROUTED ? LDS : 1); ++i) rowv[i] = 0.0;
+        } else if (n < p.N) {
+            o_comps = p.out_comps + n * 3; o_norm = p.out_norm + n; o_grad = p.out_grad + n * D;
+            o_cell = p.out_cell ? p.out_cell + n : nullptr;
         }
 #pragma unroll 1
       for (int ci = 0; ci < (LOOPC ? C : 1); ++ci) {
@@ -360,7 +365,8 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
             if (npass < 1) npass = 1;
         }
         if (comp == 0 && sl == 0 && n < p.N) {
-            if (o_cell) *o_cell = L.cell_global;
+            if (ROUTED) rowv[ROUTED ? OFFC : 0] = __longlong_as_double(L.cell_global);
+            else if (o_cell) *o_cell = L.cell_global;
             if (L.masked) mask_row_in_place(p, n);
         }
         const bool grad_comp = (MODE == 1) || (MODE == 2 && (QUAD || comp == 3));     // warp-uniform
@@ -490,6 +496,18 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
                     for (int a = 0; a < 3; ++a) o_grad[a] = L.ok ? __ddiv_rn(g[4 + a], p.h[a]) : nan;
                 }
             }
+        } else if (ROUTED) {
+            const double nan = qnan();
+            if (!grad_comp) {
+                const double v = L.ok ? g[0] : nan;
+                if (comp == 0) rowv[0] = v;
+                else if (comp == 1) rowv[ROUTED ? 1 : 0] = v;
+                else rowv[ROUTED ? 2 : 0] = v;
+            } else {
+                rowv[ROUTED ? OFFN : 0] = L.ok ? g[0] : nan;
+#pragma unroll
+                for (int a = 0; a < D; ++a) rowv[ROUTED ? OFFN + 1 + a : 0] = L.ok ? __ddiv_rn(g[1 + a], p.h[a]) : nan;
+            }
         } else if (n < p.N && sl == 0) {
             const double nan = qnan();
             if (!grad_comp) {
@@ -500,6 +518,35 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
                 for (int a = 0; a < D; ++a) o_grad[a] = L.ok ? __ddiv_rn(g[1 + a], p.h[a]) : nan;
             }
         }
+      }
+      if constexpr (ROUTED) {
+        // assemble the item's result rows in shared memory, then store them with 16-byte pieces contiguous across lanes
+        double* stage = reinterpret_cast<double*>(ring);
+        if (sl == 0 && n < p.N) {
+#pragma unroll
+            for (int i = 0; i < LDS; ++i) stage[qi * LDS + i] = rowv[i];
+        }
+        unsigned long long dst = 0;
+        if (n < p.N) {
+            int h = 0;
+            for (int r = 1; r < p.npeers; ++r) h = (n >= p.seg_start[r]) ? r : h;
+            dst = reinterpret_cast<unsigned long long>(p.peer[h] + p.home_row[n] * LDS);
+        }
+        __syncwarp();
+        constexpr int CPR = LDS / 2, NCH = QPW * CPR;
+#pragma unroll
+        for (int c0 = 0; c0 < NCH; c0 += 32) {
+            const int c = c0 + lane;
+            const bool valid = c < NCH;
+            const int r = valid ? c / CPR : 0, part = c - r * CPR;
+            const unsigned long long d0 = __shfl_sync(0xffffffffu, dst, r * SL);
+            if (valid && d0) {
+                const double2 v = *reinterpret_cast<const double2*>(stage + r * LDS + part * 2);
+                stg_stream_d2(reinterpret_cast<double*>(d0) + part * 2, v.x, v.y);
+            }
+        }
+        fence_proxy_async();   // generic-proxy writes to the ring above, async-proxy (TMA) writes to it next
+        __syncwarp();          // the staging area is the slot ring: the next item's copies must not land before it is read
       }
     }
 }
@@ -1067,29 +1114,35 @@ int query_nodes_device(const arb_geom* g, const double* nodes, int mode, double*
 // Slab-sharded tables: evaluate the rows this rank received and store every row's outputs into its home rank's result
 // buffer (peer memory over NVLink) at its home row -- the return all-to-all and the re-ordering pass are gone.
 int query_routed_device(const arb_geom* g, const double* table, int mode, double* q, int64_t N, int64_t ldq,
-                        const int64_t* route, double* const* peers, int npeers, int64_t ld, cudaStream_t st) {
+                        const int64_t* seg_start, const int64_t* home_row, double* const* peers, int npeers, int64_t ld,
+                        cudaStream_t st) {
     QueryParams p;
     const int rc = fill_params("arb_query_routed", g, true, table, mode, q, N, ldq, nullptr, nullptr, nullptr, nullptr,
                                nullptr, nullptr, p, false);
     if (rc) return rc < 0 ? 0 : rc;
     const int d = g->d;
     const int ncomp_out = (mode == ARB_MODE_NORM) ? 0 : 3, ngrad = (mode == ARB_MODE_VECTOR) ? 0 : 1 + d;
-    if (!route || !peers || npeers < 1 || npeers > ARB_MAX_PEERS || ld < ncomp_out + ngrad + 1) {
-        set_error("arb_query_routed: need route, 1..%d peers and ld >= %d (npeers=%d ld=%lld)", ARB_MAX_PEERS,
-                  ncomp_out + ngrad + 1, npeers, (long long)ld);
+    const int64_t want_ld = (ncomp_out + ngrad + 2) / 2 * 2;
+    if (!seg_start || !home_row || !peers || npeers < 1 || npeers > ARB_MAX_PEERS || ld != want_ld) {
+        set_error("arb_query_routed: need segments, 1..%d peers and ld == %lld (npeers=%d ld=%lld)", ARB_MAX_PEERS,
+                  (long long)want_ld, npeers, (long long)ld);
         return 1;
     }
-    p.route = route;
+    p.npeers = npeers;
     for (int r = 0; r < npeers; ++r) {
-        if (!peers[r]) { set_error("arb_query_routed: peers[%d] is null", r); return 1; }
+        if (!peers[r] || (reinterpret_cast<uintptr_t>(peers[r]) & 15)) { set_error("arb_query_routed: peers[%d] is null or not 16-byte aligned", r); return 1; }
+        if (seg_start[r] > seg_start[r + 1]) { set_error("arb_query_routed: bad segment %d", r); return 1; }
         p.peer[r] = peers[r];
+        p.seg_start[r] = seg_start[r];
     }
+    p.home_row = home_row;
+    p.seg_start[npeers] = seg_start[npeers];
+    if (seg_start[0] != 0 || seg_start[npeers] != N) { set_error("arb_query_routed: segments must cover the N rows"); return 1; }
     p.peer_ld = ld;
-    p.off_norm = ncomp_out; p.off_grad = ncomp_out + 1; p.off_cell = ncomp_out + ngrad;
     if (d == 3) {
-        if (mode == ARB_MODE_VECTOR) return launch_block<3, 0, 128, true, false, 32, false, false, KIND_CELLS, true, true>(p, st);
-        if (mode == ARB_MODE_NORM) return launch_block<3, 1, 128, true, false, 32, false, false, KIND_CELLS, true, true>(p, st);
-        return launch_block<3, 2, 128, true, false, 32, false, false, KIND_CELLS, true, true>(p, st);
+        if (mode == ARB_MODE_VECTOR) return launch_block<3, 0, 128, true, true, 32, false, false, KIND_CELLS, true, true>(p, st);
+        if (mode == ARB_MODE_NORM) return launch_block<3, 1, 128, true, true, 32, false, false, KIND_CELLS, true, true>(p, st);
+        return launch_block<3, 2, 128, true, true, 32, false, false, KIND_CELLS, true, true>(p, st);
     }
     if (mode == ARB_MODE_VECTOR) return launch_block<4, 0, 128, true, true, 32, false, false, KIND_CELLS, true, true>(p, st);
     if (mode == ARB_MODE_NORM) return launch_block<4, 1, 128, true, true, 32, false, false, KIND_CELLS, true, true>(p, st);
@@ -1207,8 +1260,10 @@ int arb_query_grid(const arb_geom* g, const double* grid, int64_t pitch_x, int m
 }
 
 int arb_query_routed(const arb_geom* g, const double* table, int mode, double* q, int64_t N, int64_t ldq,
-                     const int64_t* route, double* const* peers, int npeers, int64_t ld, void* stream) {
-    return arb::query_routed_device(g, table, mode, q, N, ldq, route, peers, npeers, ld, (cudaStream_t)stream);
+                     const int64_t* seg_start, const int64_t* home_row, double* const* peers, int npeers, int64_t ld,
+                     void* stream) {
+    return arb::query_routed_device(g, table, mode, q, N, ldq, seg_start, home_row, peers, npeers, ld,
+                                    (cudaStream_t)stream);
 }
 
 int arb_query_gridil(const arb_geom* g, const double* packed, int mode, double* q, int64_t N, int64_t ldq,

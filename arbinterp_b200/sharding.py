@@ -313,7 +313,7 @@ class SlabShardedInterp:
         import torch.distributed as dist
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        kwargs_fused = kwargs.pop("fused", False)
+        kwargs_fused = kwargs.pop("fused", "auto")
         device = kwargs.get("device") or torch.device("cuda", torch.cuda.current_device())
         d = cls._d
         full = broadcast_ingested(field, d, src=src, device=device, group=group)
@@ -405,8 +405,9 @@ class SlabShardedInterp:
 
     def _query_fused(self, coords, owner, ld, mark):
         """Rows travel to their owner with their home row number; the owner's kernel (``arb_query_routed``) stores every
-        row's outputs into the home rank's result buffer at that row -- peer memory over NVLink -- so the results arrive
-        in the caller's order with no return all-to-all and no re-ordering pass.  Returns the (n, ld) result rows of
+        row's outputs into the home rank's result buffer at that row -- peer memory over NVLink, each result row as
+        16-byte pieces from adjacent lanes -- so the results arrive in the caller's order with no return all-to-all and no
+        re-ordering pass.  Returns the (n, ld) result rows of
         this rank, or None when the peer mapping is unavailable (the caller then takes the all-to-all return)."""
         import ctypes
         import torch.distributed as dist
@@ -420,6 +421,7 @@ class SlabShardedInterp:
         need = torch.tensor([n], dtype=torch.int64, device=dev)
         dist.all_reduce(need, op=dist.ReduceOp.MAX, group=self.group)
         need = int(need.item())
+        ld = (ld + 1) // 2 * 2                  # result rows leave the kernel as 16-byte pieces
         if self._peer is None or self._peer.rows < need or self._peer.ld != ld:
             try:
                 self._peer = PeerResults(loc._lib, dev, self.group, max(need, 1) * 5 // 4 + 1024, ld)
@@ -431,14 +433,15 @@ class SlabShardedInterp:
         peer = self._peer
         recv, _, _, recv_split, home_rows = route_rows(coords, owner, self.group, mark, with_home_rows=True)
         m = recv.shape[0]
-        home = torch.repeat_interleave(torch.arange(self.world, dtype=torch.int64, device=dev),
-                                       torch.tensor(recv_split, dtype=torch.int64, device=dev), output_size=m)
-        route = (home << 40) | home_rows
+        world = self.world
+        seg_start = (ctypes.c_int64 * (world + 1))()
+        for h in range(world):
+            seg_start[h + 1] = seg_start[h] + recv_split[h]
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             _lib.check(loc._lib.arb_query_routed(ctypes.byref(loc._cgeom), loc.table.data_ptr(), loc._mode_code,
-                                                 recv.data_ptr(), m, d, route.data_ptr(), peer.cptrs, self.world, ld,
-                                                 stream), "arb_query_routed")
+                                                 recv.data_ptr(), m, d, seg_start, home_rows.data_ptr(), peer.cptrs, world,
+                                                 peer.ld, stream), "arb_query_routed")
         mark("kernel")
         dist.barrier(group=self.group)          # every rank's kernel has finished: all rows of this batch have landed
         mark("alltoall_back")

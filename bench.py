@@ -685,12 +685,11 @@ def run_sharded(torch, dist, args, rank, world, device):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        obj.fused = "auto"        # return leg fused into the kernel (peer stores over NVLink) when the buffers can be mapped
         res = obj.Query(q, timing=timing if timed else None)
         e1.record()
         torch.cuda.synchronize()
-        cells_fused = obj._last_cells
-        # the same rows with the all-to-all return (the library default)
+        cells_plain = obj._last_cells
+        # the same rows with the return leg as an NCCL all-to-all + re-ordering pass (fused peer-store return switched off)
         was, obj.fused = obj.fused, False
         dist.barrier()
         e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -700,7 +699,7 @@ def run_sharded(torch, dist, args, rank, world, device):
         torch.cuda.synchronize()
         obj.fused = was
         same_fused &= all(bool(torch.equal(a.view(torch.int64), b.view(torch.int64))) for a, b in zip(res, res_plain)) and \
-            bool(torch.equal(cells_fused, obj._last_cells))
+            bool(torch.equal(cells_plain, obj._last_cells))
         if timed:
             plain_ms.append(e4.elapsed_time(e5))
         dist.barrier()
@@ -755,11 +754,12 @@ def run_sharded(torch, dist, args, rank, world, device):
             "sort + permute + scatter": ph[1] + ph[3] + ph[7], "owner + unpack": ph[0] + ph[8],
             "each": dict(zip(("owner", "sort", "counts", "permute", "alltoall", "kernel", "alltoall_back", "scatter", "unpack"), ph))},
         "kernel_frac_of_measured_hbm": (ALG_BYTES[(4, "both")] * n / (ph[5] * 1e-3) / 1e9 / measured_peak()[0]) if ph[5] > 0 else None,
-        "return_leg": ("fused into the query kernel: every row's outputs are stored into its home rank's result buffer "
-                       f"over NVLink (arb_query_routed, peer mapping: {peer_how})") if peer_how else
-                      "all-to-all (peer mapping of the result buffers unavailable: " + str(getattr(obj, "_peer_error", None)) + ")",
+        "return_leg": ("fused into the query kernel (the library default): every row's outputs are stored into its home "
+                       f"rank's result buffer over NVLink (arb_query_routed, peer mapping: {peer_how})") if peer_how else
+                      ("NCCL all-to-all of the result rows + a re-ordering pass (peer mapping of the result buffers "
+                       "unavailable: " + str(getattr(obj, "_peer_error", None)) + ")"),
         "all_to_all_return": {
-            "what": "the same rows with the return leg as an NCCL all-to-all of the result rows + a re-ordering pass",
+            "what": "the same rows with the return leg as an NCCL all-to-all of the result rows + a re-ordering pass (fused=False)",
             "value": world * n * args.steps / plain_s, "unit": "queries/s", "ms_per_step": 1e3 * plain_s / args.steps,
             "fused_speedup": plain_s / total_s, "bit_identical_to_fused": not fused_differs,
             "phase_ms_per_step_max_over_ranks": dict(zip(("owner", "sort", "counts", "permute", "alltoall", "kernel",

@@ -156,19 +156,21 @@ int arb_query_gridil_host(const arb_geom* g, const double* packed, int mode, dou
                           double* out_comps_host, double* out_norm_host, double* out_grad_host, int64_t* out_cell_host,
                           int64_t chunk_rows);
 
-/* Slab-sharded tables, the return leg fused into the query kernel: row n is evaluated on this rank's slab and its
- * outputs are stored straight into the HOME rank's result buffer -- peer memory reached over NVLink / NVSwitch -- at
- * the row it has in the caller's batch there, so no result all-to-all and no re-ordering pass follow (rQuery1/2/3 over
- * a table sharded by slabs, A.py:1064-1258 / 344-521; global cell index A.py:1088).
- *   route   : device int64 [N]: (home rank << 40) | home row
- *   peers   : host array of npeers device pointers (npeers <= ARB_MAX_PEERS), peers[r] = rank r's result buffer mapped
- *             into this process (CUDA IPC / symmetric memory); result row = ld doubles:
- *             [comps(3, modes VECTOR/BOTH) | norm(1) grad(d) (modes NORM/BOTH) | cell index (int64 bits)]
+/* Slab-sharded tables, the return leg fused into the query kernel: the N rows are the ones the other ranks sent to
+ * this rank (the owner of their slab), in segments by sender -- rows [seg_start[h], seg_start[h+1]) came from rank h --
+ * and row n's outputs are stored straight into rank h's result buffer, peer memory reached over NVLink / NVSwitch, at
+ * result row home_row[n] (the row it has in the sender's batch).  No result all-to-all and no re-ordering pass follow
+ * (rQuery1/2/3 over a table sharded by slabs, A.py:1064-1258 / 344-521; global cell index A.py:1088).
+ *   seg_start : host int64 [npeers + 1], seg_start[0] = 0, seg_start[npeers] = N;  home_row : device int64 [N]
+ *   peers     : host array of npeers device pointers (npeers <= ARB_MAX_PEERS), peers[h] = rank h's result buffer mapped
+ *               into this process (symmetric memory / CUDA IPC), 16-byte aligned; result row = ld doubles:
+ *               [comps(3, modes VECTOR/BOTH) | norm(1) grad(d) (modes NORM/BOTH) | cell index (int64 bits) | pad to even]
  * Rows outside this rank's slab or outside the volume store NaN outputs and the sentinel index like arb_query.  The
- * caller orders the kernel against the readers (stream sync + a barrier across the ranks). */
+ * caller orders the kernel against the readers (a barrier across the ranks after the kernel). */
 #define ARB_MAX_PEERS 16
 int arb_query_routed(const arb_geom* g, const double* table, int mode, double* q, int64_t N, int64_t ldq,
-                     const int64_t* route, double* const* peers, int npeers, int64_t ld, void* stream);
+                     const int64_t* seg_start, const int64_t* home_row, double* const* peers, int npeers, int64_t ld,
+                     void* stream);
 /* cudaDeviceEnablePeerAccess(peer_device) for the current device; "already enabled" is success. */
 int arb_enable_peer_access(int peer_device);
 
