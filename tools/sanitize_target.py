@@ -35,6 +35,27 @@ for mode in ("vector", "norm", "both"):
     lib.arb_set_query_variant(0)
     for fixed in (False, True):
         quadcubic(f4, "quiet", mode=mode, table=False, fixed_d4=fixed).Query(q4.copy())
+# round 2: compact slot rings / prefetch / probe / LDGSTS variants of the cell kernel, node tables (3-D paired and
+# interleaved, 4-D with the A.py:860 term), interleaved table-free grid
+for mode in ("vector", "norm", "both"):
+    o = tricubic(f3, "quiet", mode=mode)
+    o4 = quadcubic(f4, "quiet", mode=mode)
+    qs = np.sort(q, axis=0)                        # clustered rows: the compact rings take one pass
+    for v in (24, 25, 40, 42, 43, 50, 60, 62):
+        lib.arb_set_query_variant(v)
+        o.Query(q.copy()); o.Query(qs.copy()); o4.Query(q4.copy())
+    lib.arb_set_query_variant(0)
+    import torch as _t
+    big = _t.from_numpy(np.tile(qs, (100, 1))).cuda()          # >= 2^16 rows: the probed launch
+    o.Query(big)
+    n3 = tricubic(f3, "quiet", mode=mode, table="nodes")
+    n4 = quadcubic(f4, "quiet", mode=mode, table="nodes")
+    n4f = quadcubic(f4, "quiet", mode=mode, table="nodes", fixed_d4=True)
+    for v in (0, 71, 72, 73):
+        lib.arb_set_query_variant(v)
+        n3.Query(q.copy()); n4.Query(q4.copy()); n4f.Query(q4.copy())
+    lib.arb_set_query_variant(0)
+    n3.Query(q[:40].copy()); n3.update_values(f3[:, 3:] * 0.5)
 # zero-copy path (<= 256 rows), single point, resumable push on slab tables, update_values
 import torch
 o = tricubic(f3, "quiet", mode="both")

@@ -25,15 +25,23 @@ for case in range(a.cases):
     vals = [np.sin(arg + phase[0])] if scalar else [np.sin(arg + phase[0]), np.cos(1.7 * arg + phase[1]) + 0.1 * arg, np.sin(0.6 * arg + phase[2]) * arg]
     field = np.stack(coords + vals, axis=1)[rng.permutation(len(coords[0]))]
     mode = "scalar" if scalar else str(rng.choice(["vector", "norm", "both"]))
-    table_free = bool(rng.integers(0, 3) == 0)
-    bv = int(rng.integers(0, 10)); qv = int(rng.choice([0, 1, 2, 10, 11, 20, 21, 22, 23, 30]))
+    form = int(rng.integers(0, 6))                 # 0-2 cell table, 3 table-free, 4 table-free planes (round-1 kernels), 5 node table
+    table_free = form in (3, 4)
+    bv = int(rng.integers(0, 10))
+    qv = int(rng.choice([0, 1, 2, 10, 11, 20, 21, 22, 23, 30, 24, 25, 40, 41, 42, 43, 44, 45, 50, 51, 60, 61, 62, 63, 71, 72, 73]))
     kw = {} if scalar else {"mode": mode}
     if table_free:
         kw["table"] = False
+        if form == 4:
+            kw["interleave"] = False
+    if form == 5:
+        kw["table"] = "nodes"
+        if d == 4 and rng.integers(0, 4) == 0:
+            kw["fixed_d4"] = True
     lib.arb_set_build_variant(bv); lib.arb_set_query_variant(qv)
     try:
         obj = (tricubic if d == 3 else quadcubic)(field.copy(), "quiet", **kw)
-        ora = OracleInterp(field, d, mode="vector" if scalar else mode)
+        ora = OracleInterp(field, d, mode="vector" if scalar else mode, reference_quirk=not kw.get("fixed_d4", False))
         n = int(rng.integers(1, 20000))
         lo = np.array(ora.geo.int_min); hi = np.array(ora.geo.int_max)
         q = lo + rng.uniform(-0.05, 1.05, (n, d + int(rng.integers(0, 3)))) [:, :d + 2][:, :] * 1.0 if False else None
@@ -61,7 +69,7 @@ for case in range(a.cases):
         worst = max(worst, err)
         if not ok or err > 1e-12:
             fails += 1
-            print(f"[stress] FAIL case {case}: d={d} shape={shape} mode={mode} table_free={table_free} bv={bv} qv={qv} n={n} ok={ok} err={err:.3e}", flush=True)
+            print(f"[stress] FAIL case {case}: d={d} shape={shape} mode={mode} form={form} kw={kw} bv={bv} qv={qv} n={n} ok={ok} err={err:.3e}", flush=True)
     finally:
         lib.arb_set_build_variant(0); lib.arb_set_query_variant(0)
 print(f"[stress] {a.cases} random cases, {fails} failures, worst scaled error {worst:.3e}")
