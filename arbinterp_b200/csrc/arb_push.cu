@@ -224,3 +224,66 @@ extern "C" int arb_permute_rows(double* dst, const double* src, const int64_t* o
     else permute_rows_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dst, src, order, n, width);
     return check_cuda(cudaGetLastError(), "permute_rows_kernel launch");
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Owner keys for the slab-sharded routing path: for every row the rank whose slab holds its slowest-axis cell layer
+// (the reference's cell location, floor((t - tIntMin) / ht), A.py:1081-1086 -- same IEEE subtract / divide / floor as
+// the query kernel's locate) and whether the row lies outside the volume (A.py:1069-1076).  One kernel instead of the
+// dozen elementwise torch launches it replaces (0.48 -> 0.03 ms for 4 M rows).
+// ---------------------------------------------------------------------------------------------------
+namespace arb {
+struct OwnerParams {
+    const double* q;
+    int64_t n, ld;
+    int d, nslab;
+    double mn[4], mx[4], h_slow;
+    int64_t hi[ARB_MAX_PEERS];
+    int16_t* owner;
+    unsigned char* outside;
+};
+__global__ void owner_keys_kernel(const OwnerParams p) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double* row = p.q + i * p.ld;
+        bool out = false;
+        double slow = 0.0;
+        for (int a = 0; a < p.d; ++a) {
+            const double c = row[a];
+            out |= (c < p.mn[a]) | (c > p.mx[a]);
+            if (a == p.d - 1) slow = c;
+        }
+        const bool valid = (slow >= p.mn[p.d - 1]) & (slow <= p.mx[p.d - 1]);
+        int owner = 0;
+        if (valid) {
+            const double fl = floor(__ddiv_rn(__dsub_rn(slow, p.mn[p.d - 1]), p.h_slow));
+            int64_t layer = (int64_t)fl;
+            const int64_t last = p.hi[p.nslab - 1] - 1;
+            layer = layer < 0 ? 0 : (layer > last ? last : layer);
+            while (owner < p.nslab - 1 && layer >= p.hi[owner]) ++owner;
+        }
+        p.owner[i] = (int16_t)owner;
+        p.outside[i] = out ? 1 : 0;
+    }
+}
+}  // namespace arb
+
+extern "C" int arb_owner_keys(const arb_geom* g, const double* q, int64_t n, int64_t ldq, const int64_t* slab_hi,
+                              int nslab, int16_t* owner, unsigned char* outside, void* stream) {
+    using namespace arb;
+    if (!g || (g->d != 3 && g->d != 4) || n < 0 || ldq < g->d || !slab_hi || nslab < 1 || nslab > ARB_MAX_PEERS) {
+        set_error("arb_owner_keys: bad arguments");
+        return 1;
+    }
+    if (n == 0) return 0;
+    if (!q || !owner || !outside) { set_error("arb_owner_keys: null pointer"); return 1; }
+    OwnerParams p;
+    memset(&p, 0, sizeof(p));
+    p.q = q; p.n = n; p.ld = ldq; p.d = g->d; p.nslab = nslab; p.owner = owner; p.outside = outside;
+    for (int a = 0; a < g->d; ++a) { p.mn[a] = g->int_min[a]; p.mx[a] = g->int_max[a]; }
+    p.h_slow = g->h[g->d - 1];
+    for (int r = 0; r < nslab; ++r) p.hi[r] = slab_hi[r];
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    owner_keys_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    return check_cuda(cudaGetLastError(), "owner_keys_kernel launch");
+}

@@ -365,10 +365,23 @@ class SlabShardedInterp:
 
         mark("start")
         g = self.local._geo
-        lo = torch.tensor(g.int_min, dtype=torch.float64, device=dev)
-        hi = torch.tensor(g.int_max, dtype=torch.float64, device=dev)
-        outside = ((coords < lo) | (coords > hi)).any(dim=1)                    # A.py:1069-1076
-        owner = owner_ranks(coords[:, d - 1], *self._slow, self.slabs)
+        if coords.is_cuda and self.world <= 16:
+            # one kernel for both (arb_owner_keys): owner rank of every row and the out-of-volume mask
+            import ctypes
+            from . import _lib
+            owner = torch.empty(coords.shape[0], dtype=torch.int16, device=dev)
+            outside = torch.empty(coords.shape[0], dtype=torch.bool, device=dev)
+            his = (ctypes.c_int64 * self.world)(*[s_[1] for s_ in self.slabs])
+            with torch.cuda.device(dev):
+                _lib.check(self.local._lib.arb_owner_keys(ctypes.byref(self.local._cgeom), coords.data_ptr(), coords.shape[0],
+                                                          coords.shape[1], his, self.world, owner.data_ptr(),
+                                                          outside.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
+                           "arb_owner_keys")
+        else:
+            lo = torch.tensor(g.int_min, dtype=torch.float64, device=dev)
+            hi = torch.tensor(g.int_max, dtype=torch.float64, device=dev)
+            outside = ((coords < lo) | (coords > hi)).any(dim=1)                # A.py:1069-1076
+            owner = owner_ranks(coords[:, d - 1], *self._slow, self.slabs)
         mark("owner")
         widths = {"vector": (3,), "norm": (1, d), "both": (3, 1, d)}[mode]
 

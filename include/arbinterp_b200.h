@@ -171,6 +171,11 @@ int arb_query_gridil_host(const arb_geom* g, const double* packed, int mode, dou
 int arb_query_routed(const arb_geom* g, const double* table, int mode, double* q, int64_t N, int64_t ldq,
                      const int64_t* seg_start, const int64_t* home_row, double* const* peers, int npeers, int64_t ld,
                      void* stream);
+/* Routing keys of a slab-sharded table: owner[n] = the rank whose slab [slab_hi[r-1], slab_hi[r]) holds row n's
+ * slowest-axis cell layer floor((t - tIntMin) / ht) (A.py:1081-1086; rows without a layer go to rank 0), outside[n] = 1
+ * when a coordinate lies outside the interpolation volume (A.py:1069-1076).  q: device [n][ldq]; g->slab_* are ignored. */
+int arb_owner_keys(const arb_geom* g, const double* q, int64_t n, int64_t ldq, const int64_t* slab_hi, int nslab,
+                   int16_t* owner, unsigned char* outside, void* stream);
 /* cudaDeviceEnablePeerAccess(peer_device) for the current device; "already enabled" is success. */
 int arb_enable_peer_access(int peer_device);
 

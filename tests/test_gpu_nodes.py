@@ -250,3 +250,36 @@ def test_round2_variants_bit_identical_on_large_batches(variant, cuda_lib):
         assert torch.equal(obj._last_cells, base_cells), name
         for a, b in zip(got, base):
             assert torch.equal(a.view(torch.int64), b.view(torch.int64)), (name, variant)
+
+
+@pytest.mark.parametrize("d", [3, 4])
+def test_owner_keys_kernel_matches_torch(d, cuda_lib):
+    """arb_owner_keys (owner rank + out-of-volume mask in one kernel) against sharding.owner_ranks and the torch mask,
+    on rows inside, outside, exactly on the bounds and NaN / inf."""
+    import ctypes
+    from arbinterp_b200 import _lib
+    from arbinterp_b200.sharding import owner_ranks, plan_slabs
+    rng = np.random.default_rng(d)
+    field = _analytic_field3(9, 8, 21, rng=rng) if d == 3 else _analytic_field4(7, 6, 5, 23, rng=rng)
+    obj = _cls(d)(field, "quiet")
+    g = obj._geo
+    lo, hi = np.array(g.int_min), np.array(g.int_max)
+    q = lo + rng.uniform(-0.1, 1.1, (50_000, d + 1))[:, :d] * (hi - lo)
+    q[0], q[1] = lo, hi
+    q[2, d - 1] = hi[d - 1] + 1e-300
+    q[3:40:3, d - 1] = lo[d - 1] + np.arange(13) * g.h[d - 1]          # exactly on layer boundaries
+    q[100, 0] = np.nan; q[101, d - 1] = np.nan; q[102, d - 1] = np.inf; q[103, 1] = -np.inf
+    qt = torch.from_numpy(q).cuda()
+    for world in (1, 2, 5, 8):
+        slabs = plan_slabs(g.ncell[d - 1], world)
+        want_owner = owner_ranks(qt[:, d - 1], g.int_min[d - 1], g.int_max[d - 1], g.h[d - 1], slabs)
+        tl = torch.tensor(g.int_min, dtype=torch.float64, device="cuda")
+        th = torch.tensor(g.int_max, dtype=torch.float64, device="cuda")
+        want_out = ((qt < tl) | (qt > th)).any(dim=1)
+        owner = torch.empty(len(q), dtype=torch.int16, device="cuda")
+        outside = torch.empty(len(q), dtype=torch.bool, device="cuda")
+        his = (ctypes.c_int64 * world)(*[s[1] for s in slabs])
+        _lib.check(cuda_lib.arb_owner_keys(ctypes.byref(obj._cgeom), qt.data_ptr(), len(q), d, his, world, owner.data_ptr(),
+                                           outside.data_ptr(), torch.cuda.current_stream().cuda_stream), "arb_owner_keys")
+        assert torch.equal(owner.to(torch.int64), want_owner.to(torch.int64)), world
+        assert torch.equal(outside, want_out), world
