@@ -46,7 +46,9 @@ def owner_ranks(coord_slow: torch.Tensor, int_min: float, int_max: float, h: flo
     """Owning rank of every query from its slowest-axis coordinate.  Rows that are outside the
     volume or NaN have no owner and are sent to rank 0, whose kernel NaN-masks them like any other
     out-of-volume row.  Same expression as the kernel's locate (subtract, divide, floor)."""
-    layer = torch.floor((coord_slow - int_min) / h)
+    # a true IEEE division like the kernel's locate: torch turns `tensor / python_scalar` into a multiplication by the
+    # reciprocal on CUDA, which is one ulp off for rows exactly on a layer boundary and would send them to the wrong rank
+    layer = torch.floor((coord_slow - int_min) / torch.full((1,), h, dtype=coord_slow.dtype, device=coord_slow.device))
     valid = (coord_slow >= int_min) & (coord_slow <= int_max)
     n_layers = slabs[-1][1]
     layer = torch.where(valid, layer, torch.zeros_like(layer)).clamp_(0, n_layers - 1).to(torch.int64)

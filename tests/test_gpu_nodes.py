@@ -272,7 +272,15 @@ def test_owner_keys_kernel_matches_torch(d, cuda_lib):
     qt = torch.from_numpy(q).cuda()
     for world in (1, 2, 5, 8):
         slabs = plan_slabs(g.ncell[d - 1], world)
-        want_owner = owner_ranks(qt[:, d - 1], g.int_min[d - 1], g.int_max[d - 1], g.h[d - 1], slabs)
+        # expected: the reference's cell location with a true division (A.py:1081-1086), as the query kernel computes it
+        slow = q[:, d - 1]
+        with np.errstate(invalid="ignore"):
+            valid = (slow >= lo[d - 1]) & (slow <= hi[d - 1])
+            layer = np.clip(np.where(valid, np.floor((slow - lo[d - 1]) / g.h[d - 1]), 0), 0, g.ncell[d - 1] - 1)
+        want = np.where(valid, np.searchsorted([s[1] for s in slabs], layer, side="right"), 0)
+        want_owner = torch.from_numpy(want).cuda()
+        assert torch.equal(owner_ranks(qt[:, d - 1], g.int_min[d - 1], g.int_max[d - 1], g.h[d - 1], slabs).to(torch.int64),
+                           want_owner.to(torch.int64)), world
         tl = torch.tensor(g.int_min, dtype=torch.float64, device="cuda")
         th = torch.tensor(g.int_max, dtype=torch.float64, device="cuda")
         want_out = ((qt < tl) | (qt > th)).any(dim=1)

@@ -143,6 +143,8 @@ def _fused_worker(rank, world, port, out_dir):
                 q = lo + rng.uniform(-0.05, 1.05, (n, d + 1))[:, :d] * (hi - lo)
                 if n > 100:
                     q[::97, 1] = np.nan
+                    k = np.arange(len(q[5::50]))                     # rows exactly on cell-layer (and slab) boundaries
+                    q[5::50, d - 1] = lo[d - 1] + (k % whole._geo.ncell[d - 1]) * whole._geo.h[d - 1]
                 qa, qb, qc = q.copy(), q.copy(), q.copy()
                 ra, rb, rc = whole.Query(qa) if n else None, fused.Query(qb), plain.Query(qc)
                 rb = rb if isinstance(rb, tuple) else (rb,)
