@@ -109,10 +109,11 @@ class CopyPool {
         cpu_set_t set;
         if (sched_getaffinity(0, sizeof(set), &set) == 0) allowed = CPU_COUNT(&set);
         if (allowed <= 0) allowed = (int)std::thread::hardware_concurrency();
-        // half of the allowed cores, at most 8: the staging needs ~35 GB/s (4 threads), and a pool as large as the
-        // core count starves the caller thread that feeds the GPU (16 cores: 8 helpers 1.18e9 q/s, 15 helpers 0.55e9)
+        // half of the allowed cores, at most 16: one GPU's staging needs ~35 GB/s (4 threads; a process that drives
+        // several GPUs needs that per GPU), and a pool as large as the core count starves the caller thread that feeds
+        // the GPU (16 cores: 8 helpers 1.18e9 q/s, 15 helpers 0.55e9)
         int n = allowed / 2;
-        if (n > 8) n = 8;
+        if (n > 16) n = 16;
         if (n < 1) n = 1;
         if (const char* e = getenv("ARB_COPY_THREADS")) { const int v = atoi(e); if (v >= 0 && v <= 64) n = v; }
         std::lock_guard<std::mutex> grow_lock(grow_m_);

@@ -258,7 +258,7 @@ class _CubicInterpolator:
     def _make_cgeom(self):
         d, geo = self._d, self._geo
         g = _lib.ArbGeom()
-        g.d, g.ncomp = d, (self._planes.shape[0] if self._table is None else self._table.shape[1])
+        g.d, g.ncomp = d, {"vector": 3, "norm": 1, "both": 4}[self._mode]
         for a in range(4):
             g.ncell[a] = geo.ncell[a] if a < d else 1
             g.int_min[a] = geo.int_min[a] if a < d else 0.0
@@ -272,20 +272,22 @@ class _CubicInterpolator:
     _MAGIC = b"ARBTAB01"
 
     def save(self, path, chunk_bytes=256 << 20):
-        """Write the coefficient table and everything needed to query it (geometry, mode, slab) to
+        """Write the coefficient table (or, for ``table='nodes'``, the node table) and everything needed to query it (geometry, mode, slab) to
         ``path``: 8-byte magic, uint64 header length, JSON header, zero padding to 4096, then the
         raw little-endian float64 table ``[ncell_local+1][C][4^d]``.  The field itself is not stored."""
         import json
-        if self._table is None:
+        store = self._nodes if self._nodes is not None else self._table
+        if store is None:
             raise ValueError("a table=False interpolator has no coefficient table to save")
         geo = self._geo
-        header = {"format": 1, "d": self._d, "mode": self._mode, "scalar_input": self._scalar_input,
+        header = {"format": 1, "kind": "nodes" if self._nodes is not None else "cells",
+                  "d": self._d, "mode": self._mode, "scalar_input": self._scalar_input,
                   "explicit_vector": self._explicit_vector, "reference_quirk": self._reference_quirk,
                   "npts": list(geo.npts), "h": [float(v).hex() for v in geo.h],
                   "int_min": [float(v).hex() for v in geo.int_min], "int_max": [float(v).hex() for v in geo.int_max],
-                  "slab": list(self._slab), "table_shape": list(self._table.shape), "dtype": "<f8"}
+                  "slab": list(self._slab), "table_shape": list(store.shape), "dtype": "<f8"}
         blob = json.dumps(header).encode("utf-8")
-        flat = self._table.reshape(-1)
+        flat = store.reshape(-1)
         step = max(1, chunk_bytes // 8)
         with open(path, "wb") as f:
             f.write(self._MAGIC)
@@ -328,7 +330,6 @@ class _CubicInterpolator:
             self._raw = None
             self._replicas = [self]
             self._table_free = False
-            self._nodes = None
             self._packed = None
             shape = tuple(int(v) for v in header["table_shape"])
             # the header is untrusted input: the table shape must be the one this geometry, slab and mode imply,
@@ -340,14 +341,29 @@ class _CubicInterpolator:
             layer = 1
             for a in range(d - 1):
                 layer *= npts[a] - 3
-            want = (layer * (hi - lo) + 1, {"vector": 3, "norm": 1, "both": 4}[self._mode], 4 ** d)
+            ncomp = {"vector": 3, "norm": 1, "both": 4}[self._mode]
+            kind = header.get("kind", "cells")
+            if kind == "nodes":                                  # layouts of _build_nodes
+                if (lo, hi) != (0, npts[d - 1] - 3):
+                    raise ValueError(f"{path}: node tables are not slab-sharded")
+                if d == 3 and ncomp >= 3:
+                    want = (npts[2] - 2, npts[1] - 2, npts[0] - 2, 4, 8)
+                elif d == 3:
+                    want = (ncomp, npts[2] - 2, npts[1] - 2, npts[0] - 3, 2, 8)
+                else:
+                    want = (ncomp,) + tuple(npts[a] - 2 for a in reversed(range(d))) + (16,)
+            elif kind == "cells":
+                want = (layer * (hi - lo) + 1, ncomp, 4 ** d)
+            else:
+                raise ValueError(f"{path}: unknown table kind {kind!r}")
             if shape != want:
                 raise ValueError(f"{path}: table shape {shape} does not match geometry/mode (expected {want})")
             left = os.fstat(f.fileno()).st_size - f.tell()
-            if left < 8 * want[0] * want[1] * want[2]:
+            if left < 8 * int(np.prod(want)):
                 raise ValueError(f"{path}: truncated table")
-            self._table = torch.empty(shape, dtype=torch.float64, device=self._device)
-            flat = self._table.reshape(-1)
+            store = torch.empty(shape, dtype=torch.float64, device=self._device)
+            self._table, self._nodes = (None, store) if kind == "nodes" else (store, None)
+            flat = store.reshape(-1)
             step = max(1, chunk_bytes // 8)
             for lo in range(0, flat.numel(), step):
                 n = min(step, flat.numel() - lo)

@@ -168,6 +168,32 @@ def test_table_free_interleaved_grid(mode):
         assert np.array_equal(x, y, equal_nan=True)
 
 
+@pytest.mark.parametrize("name,d,mode", [("tri_12x10x9", 3, "both"), ("tri_12x10x9", 3, "norm"), ("quad_8x7x7x6", 4, "both")])
+def test_node_table_save_and_load(name, d, mode, tmp_path):
+    """save() / load() of a node table: the loaded interpolator answers bit-identically with no field, ingest or build;
+    a file whose header does not match its node layout is refused."""
+    g = load_golden(name)
+    obj = _cls(d)(g["field"].copy(), "quiet", mode=mode, table="nodes")
+    q = g[mode + "_q_in"].copy()
+    ref = obj.Query(q.copy())
+    path = tmp_path / "nodes.arb"
+    obj.save(str(path), chunk_bytes=1 << 14)
+    back = _cls(d).load(str(path), chunk_bytes=1 << 13)
+    got = back.Query(q.copy())
+    for a, b in zip(ref if isinstance(ref, tuple) else (ref,), got if isinstance(got, tuple) else (got,)):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert np.array_equal(back.queryInds, obj.queryInds) and torch.equal(back.nodes, obj.nodes)
+    with pytest.raises(AttributeError):
+        back.table
+    blob = bytearray(path.read_bytes())
+    i = blob.find(b'"kind": "nodes"')
+    blob[i:i + 15] = b'"kind": "cells"'
+    bad = tmp_path / "bad.arb"
+    bad.write_bytes(bytes(blob))
+    with pytest.raises(ValueError):
+        _cls(d).load(str(bad))
+
+
 def test_node_table_quirk_is_visible():
     from arbinterp_b200 import quadcubic
     field = _analytic_field4(9, 8, 8, 7)[:, [0, 1, 2, 3, 5]]          # the column with the x*y*z*t monomial
