@@ -295,6 +295,20 @@ def _routing_worker(rank, world, port, field, q_all, out_dir):
     owner = owner_ranks(mine[:, d - 1], geo.int_min[d - 1], geo.int_max[d - 1], geo.h[d - 1], slabs)
     out = exchange_and_query(mine, owner, evaluate, 3 + 1 + d)
     np.save(os.path.join(out_dir, f"out{rank}.npy"), out.numpy())
+    # the addressing of the fused return leg (arb_query_routed): rows arrive in segments by sender together with the row
+    # number they have in the sender's batch; "storing" every result at (sender, that row) -- emulated here with an
+    # all-gather -- must reproduce the caller's order without any re-ordering pass
+    from arbinterp_b200.sharding import route_rows
+    recv, _, _, recv_split, home_rows = route_rows(mine, owner, with_home_rows=True)
+    res = evaluate(recv)
+    home = torch.repeat_interleave(torch.arange(world), torch.tensor(recv_split))
+    boxes = [None] * world
+    dist.all_gather_object(boxes, (home.numpy(), home_rows.numpy(), res.numpy()))
+    landed = np.full(out.shape, np.inf)
+    for h, rows, vals in boxes:
+        sel = h == rank
+        landed[rows[sel]] = vals[sel]
+    seen.append(bool(np.array_equal(landed, out.numpy(), equal_nan=True)))
     np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array(seen))
     dist.barrier()
     dist.destroy_process_group()
