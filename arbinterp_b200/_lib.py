@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = (
     "arb_build_coeffs", "arb_build_coeffs_3d", "arb_build_coeffs_4d",
     "arb_query", "arb_query_host", "arb_query_grid", "arb_query_grid_host",
     "arb_build_nodes", "arb_query_nodes", "arb_query_nodes_host", "arb_query_gridil", "arb_query_gridil_host", "arb_query_routed", "arb_enable_peer_access", "arb_owner_keys",
-    "arb_push", "arb_push_steps", "arb_permute_rows", "arb_set_query_variant", "arb_set_build_variant",
+    "arb_push", "arb_push_steps", "arb_push_nodes", "arb_permute_rows", "arb_set_query_variant", "arb_set_build_variant",
 )
 
 
@@ -100,6 +100,8 @@ def load():
     lib.arb_push.restype = i32
     lib.arb_push.argtypes = [ctypes.POINTER(ArbGeom), vp, i32, vp, vp, i64, ctypes.c_double, i64, ctypes.c_double,
                              ctypes.POINTER(ctypes.c_double * 3), vp, vp]
+    lib.arb_push_nodes.restype = i32
+    lib.arb_push_nodes.argtypes = lib.arb_push.argtypes
     lib.arb_push_steps.restype = i32
     lib.arb_push_steps.argtypes = [ctypes.POINTER(ArbGeom), vp, i32, vp, vp, vp, i64, ctypes.c_double, i64,
                                    ctypes.c_double, ctypes.POINTER(ctypes.c_double * 3), vp, vp]

@@ -18,6 +18,7 @@
 // owning the neighbouring slab resumes it with exactly the arithmetic of an unsharded run
 // (sharding.SlabShardedInterp.push moves the rows).
 #include "arb_device.cuh"
+#include "arb_nodes.cuh"
 
 namespace arb {
 
@@ -37,7 +38,10 @@ struct PushParams {
 // (u, v, w) and the spatial gradient is the s^l-weighted sum over the four lanes (as in
 // query_block_kernel); all four lanes carry the particle state redundantly and update it identically.
 // pos is [N][D] (the 4th coordinate is the particle's own time and advances by dt per step), vel [N][3].
-template <int D, int THREADS>
+// NODES: `table` is a node (Hermite) table (arb_nodes.cuh; one component, or the |B| block of the interleaved 3-D
+// layout): the lane's slot is gathered from its 4 (3-D) / 2 (4-D) x-pair segments by one warp-wide LDGSTS per slot and
+// evaluated with the Hermite basis; in 4-D the four lanes own (cz, ct) and the A.py:860 term is added unless QUIRK4 is off.
+template <int D, int THREADS, bool NODES = false, bool QUIRK4 = true>
 __global__ void __launch_bounds__(THREADS) push_kernel(const PushParams P) {
     constexpr int SL = (D == 4) ? 4 : 1;
     constexpr int PPW = 32 / SL;                 // particles per warp pass
@@ -58,6 +62,15 @@ __global__ void __launch_bounds__(THREADS) push_kernel(const PushParams P) {
     const int64_t nwarps = ((int64_t)gridDim.x * THREADS) >> 5;
     uint32_t phase = 0;
     const double hdt = 0.5 * P.dt;
+    // node tables: bytes between a slot's first byte and this lane's 16 bytes of it in global memory, and the layout's
+    // strides -- one component [..][nx-3 pairs][2][8] / [..][nx-2][16], or the 4th block of the interleaved [..][nx-2][4][8]
+    const bool il = NODES && D == 3 && P.ncomp >= 3;
+    int64_t lane_src = 0;
+    if (NODES) {
+        if (D == 4) lane_src = (lane >> 4) * p.nn[0] * 128 + (lane & 15) * 16;
+        else if (il) lane_src = ((lane >> 4) * p.nn[1] + ((lane >> 3) & 1)) * p.nn[0] * 256 + ((lane >> 2) & 1) * 256 + 192 + (lane & 3) * 16;
+        else lane_src = ((lane >> 4) * p.nn[1] + ((lane >> 3) & 1)) * p.nc[0] * 128 + (lane & 7) * 16;
+    }
     for (int64_t base = warp_global * PPW; base < p.N; base += nwarps * PPW) {
         const int64_t n = base + pi;
         const bool active = n < p.N;
@@ -92,18 +105,64 @@ __global__ void __launch_bounds__(THREADS) push_kernel(const PushParams P) {
             const bool fetch = alive && (blk != cur_blk);
             const unsigned fmask = __ballot_sync(0xffffffffu, fetch);
             if (fmask) {                         // warp-uniform
-                if (lane == 0) mbar_expect_tx(bar, (uint32_t)__popc(fmask) * BYTES);
-                __syncwarp();
-                if (fetch) {
-                    bulk_g2s(slot, p.table + blk * 64, BYTES, bar);
-                    cur_blk = blk;
+                if (NODES) {
+                    const double* src;
+                    if (D == 4)
+                        src = p.table + (P.ncomp - 1) * p.node_comp_stride +
+                              ((((L.idx[3] + (sl >> 1)) * p.nn[2] + L.idx[2] + (sl & 1)) * p.nn[1] + L.idx[1]) * p.nn[0] + L.idx[0]) * 16;
+                    else if (il)
+                        src = p.table + ((L.idx[2] * p.nn[1] + L.idx[1]) * p.nn[0] + L.idx[0]) * 32;
+                    else
+                        src = p.table + ((L.idx[2] * p.nn[1] + L.idx[1]) * p.nc[0] + L.idx[0]) * 16;
+                    const uint32_t src16 = (uint32_t)((reinterpret_cast<const char*>(src) - reinterpret_cast<const char*>(p.table)) >> 4);
+                    const char* const lane_base = reinterpret_cast<const char*>(p.table) + lane_src;
+                    const uint32_t ring0 = smem_u32(smem + (size_t)(threadIdx.x - lane) * SLOT) + lane * 16;
+#pragma unroll 8
+                    for (int o = 0; o < 32; ++o) {
+                        if ((fmask >> o) & 1u) {
+                            const uint32_t s16 = __shfl_sync(0xffffffffu, src16, o);
+                            cp_async_16(ring0 + o * SLOT, lane_base + ((size_t)s16 << 4));
+                        }
+                    }
+                    if (fetch) cur_blk = blk;
+                    cp_async_wait_all();
+                    __syncwarp();
+                } else {
+                    if (lane == 0) mbar_expect_tx(bar, (uint32_t)__popc(fmask) * BYTES);
+                    __syncwarp();
+                    if (fetch) {
+                        bulk_g2s(slot, p.table + blk * 64, BYTES, bar);
+                        cur_blk = blk;
+                    }
+                    mbar_wait(bar, phase);
+                    phase ^= 1;
                 }
-                mbar_wait(bar, phase);
-                phase ^= 1;
             }
             double g[5] = {0, 0, 0, 0, 0};
-            if (alive) eval_value_grad<3, true>(reinterpret_cast<const double*>(slot), L.frac, g);
-            if (D == 4) {
+            if (NODES) {
+                const double* cb = reinterpret_cast<const double*>(slot);
+                if (D == 3) {
+                    if (alive) nodes::eval3<true>(cb, L.frac, g);
+                } else {
+                    double f15[4] = {0.0, 0.0, 0.0, 0.0};
+                    if (alive) {
+                        nodes::eval4_lane<true, false>(cb, sl & 1, sl >> 1, L.frac, 0.0, g);
+                        if (QUIRK4) { f15[0] = cb[15]; f15[1] = cb[31]; f15[2] = cb[47]; f15[3] = cb[63]; }
+                    }
+                    if (QUIRK4) {
+                        const double up = __shfl_up_sync(0xffffffffu, f15[3], 1);
+                        if (alive) nodes::quirk4_lane<true>(f15, sl ? up : 0.0, sl & 1, sl >> 1, L.frac, g);
+                    }
+#pragma unroll
+                    for (int c = 1; c <= 3; ++c) {
+                        g[c] += __shfl_xor_sync(0xffffffffu, g[c], 1);
+                        g[c] += __shfl_xor_sync(0xffffffffu, g[c], 2);
+                    }
+                }
+            } else if (alive) {
+                eval_value_grad<3, true>(reinterpret_cast<const double*>(slot), L.frac, g);
+            }
+            if (D == 4 && !NODES) {
                 const double w = alive ? pow_sel(L.frac[D - 1], sl) : 0.0;
 #pragma unroll
                 for (int c = 1; c <= 3; ++c) {
@@ -145,12 +204,12 @@ __global__ void __launch_bounds__(THREADS) push_kernel(const PushParams P) {
     }
 }
 
-template <int D>
+template <int D, bool NODES = false, bool QUIRK4 = true>
 static int launch_push(const PushParams& P, int64_t N, cudaStream_t st) {
     constexpr int THREADS = 128;
     constexpr int PPW = (D == 4) ? 8 : 32;
     const size_t smem = (size_t)THREADS * 528;
-    auto k = push_kernel<D, THREADS>;
+    auto k = push_kernel<D, THREADS, NODES, QUIRK4>;
     ARB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, THREADS, smem) != cudaSuccess || occ < 1) occ = 1;
@@ -183,6 +242,32 @@ extern "C" int arb_push_steps(const arb_geom* g, const double* table, int mode, 
     for (int a = 0; a < 3; ++a) P.g[a] = gravity ? gravity[a] : 0.0;
     if (g->d == 3) return launch_push<3>(P, N, (cudaStream_t)stream);
     return launch_push<4>(P, N, (cudaStream_t)stream);
+}
+
+// The same integrator on a node (Hermite) table (arb_build_nodes): 4-16x less memory, so a field whose cell table must be
+// slab-sharded (config 5: 402 GB) is pushed on every GPU from its own 26 GB replica, with no particle migration.
+extern "C" int arb_push_nodes(const arb_geom* g, const double* nodes, int mode, double* pos, double* vel, int64_t N,
+                              double dt, int64_t nsteps, double kappa, const double* gravity,
+                              unsigned long long* lost_count, void* stream) {
+    using namespace arb;
+    if (mode != ARB_MODE_NORM && mode != ARB_MODE_BOTH) {
+        set_error("arb_push_nodes: needs a table with a norm component (mode norm or both), got mode %d", mode);
+        return 1;
+    }
+    if (!pos || !vel || nsteps < 0) { set_error("arb_push_nodes: null pos/vel or negative nsteps"); return 1; }
+    PushParams P;
+    memset(&P, 0, sizeof(P));
+    const int rc = fill_params("arb_push_nodes", g, true, nodes, mode, pos, N, g ? g->d : 3, nullptr, nullptr, nullptr,
+                               nullptr, nullptr, nullptr, P.q, false);
+    if (rc) return rc < 0 ? 0 : rc;
+    if (g->slab_lo != 0 || g->slab_hi != g->ncell[g->d - 1]) { set_error("arb_push_nodes: slabs are not supported"); return 1; }
+    if (reinterpret_cast<uintptr_t>(nodes) & 127) { set_error("arb_push_nodes: node table must be 128-byte aligned"); return 1; }
+    P.pos = pos; P.vel = vel; P.dt = dt; P.kappa = kappa; P.nsteps = nsteps; P.lost = lost_count; P.ncomp = g->ncomp;
+    P.step_io = nullptr;
+    for (int a = 0; a < 3; ++a) P.g[a] = gravity ? gravity[a] : 0.0;
+    if (g->d == 3) return launch_push<3, true>(P, N, (cudaStream_t)stream);
+    if (g->flags & ARB_GEOM_FIXED_D4) return launch_push<4, true, false>(P, N, (cudaStream_t)stream);
+    return launch_push<4, true, true>(P, N, (cudaStream_t)stream);
 }
 
 extern "C" int arb_push(const arb_geom* g, const double* table, int mode, double* pos, double* vel, int64_t N,

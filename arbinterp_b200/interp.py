@@ -764,8 +764,10 @@ class _CubicInterpolator:
         """One launch of the push kernel on this table.  ``steps``: optional int64 CUDA tensor (N,) with every
         particle's next step index (arb_push_steps; a particle inside the volume but outside this table's slab
         is parked unchanged); None = plain arb_push.  Returns the number of particles lost in this launch."""
-        if self._mode == "vector" or self._table is None:
-            raise ValueError("push() needs a coefficient table in 'norm', 'both' or scalar mode")
+        if self._mode == "vector" or (self._table is None and self._nodes is None):
+            raise ValueError("push() needs a coefficient or node table in 'norm', 'both' or scalar mode")
+        if self._nodes is not None and steps is not None:
+            raise ValueError("the resumable push (slab-sharded tables) needs a cell table; a node table is replicated")
         for t, w in ((p, self._d), (v, 3)):
             if t.dtype != torch.float64 or not t.is_contiguous() or t.dim() != 2 or t.shape[1] != w or t.device != self._device:
                 raise ValueError(f"pos must be (N,{self._d}) and vel (N,3): contiguous float64 on the interpolator's device")
@@ -778,10 +780,16 @@ class _CubicInterpolator:
         grav = (ctypes.c_double * 3)(*([0.0, 0.0, 0.0] if gravity is None else [float(x) for x in gravity]))
         with torch.cuda.device(self._device):
             stream = torch.cuda.current_stream(self._device).cuda_stream
-            _lib.check(self._lib.arb_push_steps(ctypes.byref(self._cgeom), self._table.data_ptr(), self._mode_code,
-                                                p.data_ptr(), v.data_ptr(), None if steps is None else steps.data_ptr(),
-                                                p.shape[0], float(dt), int(nsteps), float(kappa), ctypes.byref(grav),
-                                                lost.data_ptr(), stream), "arb_push")
+            if self._nodes is not None:
+                _lib.check(self._lib.arb_push_nodes(ctypes.byref(self._cgeom), self._nodes.data_ptr(), self._mode_code,
+                                                    p.data_ptr(), v.data_ptr(), p.shape[0], float(dt), int(nsteps),
+                                                    float(kappa), ctypes.byref(grav), lost.data_ptr(), stream),
+                           "arb_push_nodes")
+            else:
+                _lib.check(self._lib.arb_push_steps(ctypes.byref(self._cgeom), self._table.data_ptr(), self._mode_code,
+                                                    p.data_ptr(), v.data_ptr(), None if steps is None else steps.data_ptr(),
+                                                    p.shape[0], float(dt), int(nsteps), float(kappa), ctypes.byref(grav),
+                                                    lost.data_ptr(), stream), "arb_push")
         return int(lost.item())
 
     # ------------------------------------------------------------------ single-point queries

@@ -196,6 +196,9 @@ int arb_push(const arb_geom* g, const double* table, int mode, double* pos, doub
 int arb_push_steps(const arb_geom* g, const double* table, int mode, double* pos, double* vel, int64_t* step_io,
                    int64_t N, double dt, int64_t nsteps, double kappa, const double* gravity,
                    unsigned long long* lost_count, void* stream);
+/* arb_push on a node table (arb_build_nodes) instead of the cell table; no slabs (a node table is replicated). */
+int arb_push_nodes(const arb_geom* g, const double* nodes, int mode, double* pos, double* vel, int64_t N, double dt,
+                   int64_t nsteps, double kappa, const double* gravity, unsigned long long* lost_count, void* stream);
 
 /* Row permutation used by the slab-sharded routing path (no counterpart in the single-process reference):
  * gather  (scatter == 0): dst[i][:] = src[order[i]][:];  scatter (scatter != 0): dst[order[i]][:] = src[i][:].

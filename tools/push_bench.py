@@ -8,6 +8,7 @@ from arbinterp_b200 import tricubic
 from tools.perf_sweep import field_rows
 dev = torch.device("cuda", 0)
 obj = tricubic(field_rows((256,) * 3, dev), "quiet", mode="norm")
+nod = tricubic(field_rows((256,) * 3, dev), "quiet", mode="norm", table="nodes")      # the same push on the node table
 n = 1 << 24
 g = torch.Generator(device=dev); g.manual_seed(3)
 lo = torch.tensor(obj._geo.int_min, dtype=torch.float64, device=dev); hi = torch.tensor(obj._geo.int_max, dtype=torch.float64, device=dev)
@@ -34,5 +35,13 @@ for label, speed in (("0.01 cell/step", 0.01), ("0.3 cell/step", 0.3), ("3 cells
     torch.cuda.synchronize(); t_loop = time.perf_counter() - t0
     ok = ~torch.isnan(p2[:, 0])
     err = float((p[ok] - p2[ok]).abs().max())
+    pn, vn = pos0.clone(), vel0.clone()
+    nod.push(pn, vn, 1.0, 2, 1e-6)
+    pn, vn = pos0.clone(), vel0.clone()
+    torch.cuda.synchronize(); e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(); nod.push(pn, vn, 1.0, nsteps, 1e-6); e3.record(); torch.cuda.synchronize()
+    t_nodes = e2.elapsed_time(e3) / 1e3
+    print(f"[push] {label}: node table {n * nsteps / t_nodes:.3e} particle-steps/s (x{t_fused / t_nodes:.2f} of the cell table), "
+          f"max |dx| vs cell table {float((p[ok] - pn[ok]).abs().max()):.2e}", flush=True)
     print(f"[push] {label}: fused {n * nsteps / t_fused:.3e} particle-steps/s ({t_fused * 1e3:.1f} ms for {nsteps} steps of {n}), "
           f"Query loop {n * nsteps / t_loop:.3e} -> x{t_loop / t_fused:.1f}; lost {lost}; max |dx| fused vs loop {err:.2e}", flush=True)
