@@ -114,14 +114,14 @@ __global__ void __launch_bounds__(THREADS) push_kernel(const PushParams P) {
                         src = p.table + ((L.idx[2] * p.nn[1] + L.idx[1]) * p.nn[0] + L.idx[0]) * 32;
                     else
                         src = p.table + ((L.idx[2] * p.nn[1] + L.idx[1]) * p.nc[0] + L.idx[0]) * 16;
-                    const uint32_t src16 = (uint32_t)((reinterpret_cast<const char*>(src) - reinterpret_cast<const char*>(p.table)) >> 4);
+                    const uint32_t src16 = (uint32_t)((reinterpret_cast<const char*>(src) - reinterpret_cast<const char*>(p.table)) >> 7);   // 128-byte units: 512 GB
                     const char* const lane_base = reinterpret_cast<const char*>(p.table) + lane_src;
                     const uint32_t ring0 = smem_u32(smem + (size_t)(threadIdx.x - lane) * SLOT) + lane * 16;
 #pragma unroll 8
                     for (int o = 0; o < 32; ++o) {
                         if ((fmask >> o) & 1u) {
                             const uint32_t s16 = __shfl_sync(0xffffffffu, src16, o);
-                            cp_async_16(ring0 + o * SLOT, lane_base + ((size_t)s16 << 4));
+                            cp_async_16(ring0 + o * SLOT, lane_base + ((size_t)s16 << 7));
                         }
                     }
                     if (fetch) cur_blk = blk;

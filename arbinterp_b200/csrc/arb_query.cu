@@ -395,10 +395,12 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
             const bool fetch = leader && active;
             const unsigned fmask = __ballot_sync(0xffffffffu, fetch);
             if (FETCH_LDGSTS) {
-                // one shuffle per slot: the owner's source as a 32-bit count of 16-byte units from the table base
-                // (tables < 64 GB), the destination packed beside it when the ring is compact; the 32 trips are
-                // unrolled and independent of each other (warp-uniform predicate from the ballot)
-                const uint32_t src16 = (uint32_t)((reinterpret_cast<const char*>(src) - reinterpret_cast<const char*>(p.table)) >> 4);
+                // one shuffle per slot: the owner's source as a 32-bit count of 2^USH-byte units from the table base (every
+                // slot starts on such a unit: cell blocks 512 B, node pairs 128 / 256 B, interleaved grid points 32 B --
+                // good for 2 TB / 512 GB / 128 GB of table), the destination packed beside it when the ring is compact;
+                // the 32 trips are unrolled and independent of each other (warp-uniform predicate from the ballot)
+                constexpr int USH = (KIND == KIND_CELLS) ? 9 : (KIND == KIND_GRID_IL ? 5 : 7);
+                const uint32_t src16 = (uint32_t)((reinterpret_cast<const char*>(src) - reinterpret_cast<const char*>(p.table)) >> USH);
                 const char* const lane_base = reinterpret_cast<const char*>(p.table) + lane_src;
                 const uint32_t ring0 = smem_u32(ring) + lane * 16;
 #pragma unroll 8
@@ -406,7 +408,7 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
                     if ((fmask >> o) & 1u) {
                         const uint32_t s16 = __shfl_sync(0xffffffffu, src16, o);
                         const uint32_t slot_o = (SLOTS == 32) ? (uint32_t)o : (uint32_t)__shfl_sync(0xffffffffu, myslot, o);
-                        cp_async_16(ring0 + slot_o * SLOT, lane_base + ((size_t)s16 << 4));
+                        cp_async_16(ring0 + slot_o * SLOT, lane_base + ((size_t)s16 << USH));
                     }
                 }
             } else {
@@ -1081,6 +1083,10 @@ int query_gridil_device(const arb_geom* g, const double* packed, int mode, doubl
     if (g->d != 3 || mode == ARB_MODE_NORM) { set_error("arb_query_gridil: 3-D 'vector' / 'both' only"); return 1; }
     if (g->slab_lo != 0 || g->slab_hi != g->ncell[2]) { set_error("arb_query_gridil: slabs are not supported"); return 1; }
     if (reinterpret_cast<uintptr_t>(packed) & 31) { set_error("arb_query_gridil: grid must be 32-byte aligned"); return 1; }
+    if ((double)(g->ncell[0] + 3) * (double)(g->ncell[1] + 3) * (double)(g->ncell[2] + 3) * 32.0 >= 137438953472.0) {
+        set_error("arb_query_gridil: interleaved grids of 128 GB and more are not addressable by the gather");
+        return 1;
+    }
     const int v = current_query_variant();
     if (mode == ARB_MODE_VECTOR) {
         if (v == 73) return launch_block<3, 0, 128, false, true, 32, true, true, KIND_GRID_IL>(p, st);

@@ -283,3 +283,35 @@ def test_single_process_devices_list():
     one.update_values(vals); many.update_values(vals)
     ra, rb = one.Query(q.copy()), many.Query(q.copy())
     assert all(np.array_equal(x, y, equal_nan=True) for x, y in zip(ra, rb))
+
+
+def test_pageable_rows_staged_piecewise(monkeypatch):
+    """arb_query_host stages ordinary (pageable) numpy rows into its pinned ring in pieces and issues each piece's H2D
+    copy as soon as it is staged (csrc/arb_host.cu, StageBuf).  A batch of several chunks with a ragged tail, extra
+    query columns (README: ignored) and out-of-volume rows in the first / a middle / the last piece must come back
+    bit-identical to the device-tensor path, with the NaN rows written into the caller's array (A.py:350-355)."""
+    from arbinterp_b200 import tricubic
+    rng = np.random.default_rng(11)
+    ax = [np.linspace(-1, 1, 23), np.linspace(0, 1, 19), np.linspace(-2, 0, 21)]
+    Z, Y, X = [a.ravel() for a in np.meshgrid(ax[2], ax[1], ax[0], indexing="ij")]
+    field = np.stack([X, Y, Z, np.sin(2 * X) * np.cos(3 * Y) * np.exp(Z) + 2.0], axis=1)
+    obj = tricubic(field, "quiet")
+    n, ld = 2 * (1 << 20) + 777_777, 5
+    lo = np.array([obj.xIntMin, obj.yIntMin, obj.zIntMin]); hi = np.array([obj.xIntMax, obj.yIntMax, obj.zIntMax])
+    q = np.empty((n, ld))
+    q[:, :3] = lo + rng.uniform(0, 1, (n, 3)) * (hi - lo) * (1 - 1e-9)
+    q[:, 3:] = rng.normal(size=(n, 2))
+    bad = [0, 5, 131_071, 131_072, (1 << 20) - 1, 1 << 20, (1 << 20) + 600_000, n - 2, n - 1]
+    q[bad, 0] = 7.0
+    dev_q = torch.from_numpy(q).cuda()
+    ref = obj.Query(dev_q)
+    ref_inds = obj.queryInds.copy()
+    for chunk in ("0", "300000", "1048576"):
+        monkeypatch.setenv("ARB_HOST_CHUNK_ROWS", chunk)
+        qh = q.copy()
+        got = obj.Query(qh)
+        for a, b in zip(ref, got):
+            assert np.array_equal(a.cpu().numpy(), b, equal_nan=True), f"chunk {chunk}"
+        assert np.array_equal(obj.queryInds, ref_inds)
+        assert np.isnan(qh[bad]).all() and np.array_equal(np.delete(qh, bad, axis=0), np.delete(q, bad, axis=0))
+    assert torch.isnan(dev_q[bad]).all()
