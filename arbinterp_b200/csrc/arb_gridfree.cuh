@@ -172,6 +172,55 @@ ARB_HD void plane_il(const double* slot, int k, const double* f, double* out) {
     }
 }
 
+// 4-D table-free, interleaved components (grid [nt][nz][ny][nx][4]): one lane = z-plane k of the 4^4 neighbourhood, one
+// pass = t-plane l, slot [j][i][c] as in plane_il.  out[0..6] = this (k, l) plane's share of the (u, v, w) contraction
+// with the z weight applied (the caller applies the t weight): components 0..2 and (BOTH) |B|, its d/du, d/dv, d/dw.
+// QUIRK: Pq[cx + 2 cy][c] = the plane's signed xy parity sums  sum_{i, j} (+-) f[j][i][c]  over i in {cx, cx + 2},
+// j in {cy, cy + 2} (sign + when i and j are both the upper or both the lower point) -- the xy part of the 1/16 (+-)
+// central difference fxyzt at the cell's corners (A.py:860 term, see the header of this file).
+template <bool BOTH, bool QUIRK>
+ARB_HD void plane_il4(const double* slot, double wzk, double dwzk, const double (&wx)[4], const double (&dwx)[4],
+                      const double (&wy)[4], const double (&dwy)[4], double (&out)[7], double (&Pq)[4][4]) {
+    constexpr int NC = BOTH ? 4 : 3;
+    double P[4] = {0.0, 0.0, 0.0, 0.0}, Px = 0.0, Py = 0.0;
+    if (QUIRK) {
+        ARB_UNROLL
+        for (int q = 0; q < 4; ++q)
+            ARB_UNROLL
+            for (int c = 0; c < 4; ++c) Pq[q][c] = 0.0;
+    }
+    ARB_UNROLL
+    for (int j = 0; j < 4; ++j) {
+        double pp[4] = {0.0, 0.0, 0.0, 0.0}, dp = 0.0;
+        ARB_UNROLL
+        for (int i = 0; i < 4; ++i) {
+            const Pair2 a = *reinterpret_cast<const Pair2*>(slot + (j * 4 + i) * 4);
+            const Pair2 b = *reinterpret_cast<const Pair2*>(slot + (j * 4 + i) * 4 + 2);
+            const double v[4] = {a.x, a.y, b.x, b.y};
+            ARB_UNROLL
+            for (int c = 0; c < NC; ++c) {
+                pp[c] = fma_(v[c], wx[i], pp[c]);
+                if (QUIRK) Pq[(j & 1) * 2 + (i & 1)][c] = ((i >> 1) == (j >> 1)) ? Pq[(j & 1) * 2 + (i & 1)][c] + v[c]
+                                                                                 : Pq[(j & 1) * 2 + (i & 1)][c] - v[c];
+            }
+            if (BOTH) dp = fma_(v[3], dwx[i], dp);
+        }
+        ARB_UNROLL
+        for (int c = 0; c < NC; ++c) P[c] = fma_(wy[j], pp[c], P[c]);
+        if (BOTH) {
+            Px = fma_(wy[j], dp, Px);
+            Py = fma_(dwy[j], pp[3], Py);
+        }
+    }
+    out[0] = wzk * P[0]; out[1] = wzk * P[1]; out[2] = wzk * P[2];
+    if (BOTH) {
+        out[3] = wzk * P[3];
+        out[4] = wzk * Px;
+        out[5] = wzk * Py;
+        out[6] = dwzk * P[3];
+    }
+}
+
 // Quirk term of one ct before the t factor: c[0] = sum_c3 hx hy hz e[c3], c[1..3] = its partials in u, v, w.
 // g = fxyzt at the 8 corners of this ct, g7prev = fxyzt(corner 7 of ct-1) for ct = 1, 0 for ct = 0.
 template <bool GRAD>

@@ -1072,7 +1072,10 @@ static int dispatch_nodes(const QueryParams& p, cudaStream_t st, int variant, bo
     }
 }
 
-// Table-free 3-D 'vector' / 'both' on the component-interleaved grid [nz][ny][nx][4] (Bx, By, Bz, |B| or 0).
+// Table-free 'vector' / 'both' on the component-interleaved grid [nt][nz][ny][nx][4] (Bx, By, Bz, |B| or 0); the 4-D
+// kernel lives in arb_gridil4.cu.
+int query_gridil4_launch(const QueryParams& p, int mode, bool quirk, bool dedup, cudaStream_t st);
+
 int query_gridil_device(const arb_geom* g, const double* packed, int mode, double* q, int64_t N, int64_t ldq,
                         double* out_comps, double* out_norm, double* out_grad, int64_t* out_cell, int64_t* masked_rows,
                         unsigned long long* masked_count, cudaStream_t st) {
@@ -1080,14 +1083,17 @@ int query_gridil_device(const arb_geom* g, const double* packed, int mode, doubl
     const int rc = fill_params("arb_query_gridil", g, true, packed, mode, q, N, ldq, out_comps, out_norm, out_grad,
                                out_cell, masked_rows, masked_count, p);
     if (rc) return rc < 0 ? 0 : rc;
-    if (g->d != 3 || mode == ARB_MODE_NORM) { set_error("arb_query_gridil: 3-D 'vector' / 'both' only"); return 1; }
-    if (g->slab_lo != 0 || g->slab_hi != g->ncell[2]) { set_error("arb_query_gridil: slabs are not supported"); return 1; }
+    if (mode == ARB_MODE_NORM) { set_error("arb_query_gridil: 'vector' / 'both' only (one component has nothing to interleave)"); return 1; }
+    if (g->slab_lo != 0 || g->slab_hi != g->ncell[g->d - 1]) { set_error("arb_query_gridil: slabs are not supported"); return 1; }
     if (reinterpret_cast<uintptr_t>(packed) & 31) { set_error("arb_query_gridil: grid must be 32-byte aligned"); return 1; }
-    if ((double)(g->ncell[0] + 3) * (double)(g->ncell[1] + 3) * (double)(g->ncell[2] + 3) * 32.0 >= 137438953472.0) {
+    double bytes = 32.0;
+    for (int a = 0; a < g->d; ++a) bytes *= (double)(g->ncell[a] + 3);
+    if (bytes >= 137438953472.0) {
         set_error("arb_query_gridil: interleaved grids of 128 GB and more are not addressable by the gather");
         return 1;
     }
     const int v = current_query_variant();
+    if (g->d == 4) return query_gridil4_launch(p, mode, !(g->flags & ARB_GEOM_FIXED_D4), v != 73 && v != 20, st);
     if (mode == ARB_MODE_VECTOR) {
         if (v == 73) return launch_block<3, 0, 128, false, true, 32, true, true, KIND_GRID_IL>(p, st);
         return launch_block<3, 0, 128, true, true, 32, true, true, KIND_GRID_IL>(p, st);

@@ -142,7 +142,11 @@ class _CubicInterpolator:
             self._pitch = nx + (nx & 1)                           # TMA needs 16-byte row strides
             if self._pitch != nx:
                 self._planes = torch.nn.functional.pad(self._planes, (0, 1)).contiguous()
-            self._use_packed = d == 3 and mode in ("vector", "both") and kwargs.get("interleave", True)
+            # component-interleaved grid (one 128-byte piece per neighbourhood row serves every component): the default
+            # for 3-D 'vector' / 'both' and 4-D 'both'; 4-D 'vector' would gather the unused |B| slot too (8 KB per
+            # query instead of 6), so it keeps the per-component TMA boxes unless asked (interleave=True)
+            self._use_packed = (not scalar) and mode in ("vector", "both") and bool(
+                kwargs.get("interleave", d == 3 or mode == "both"))
             self._pack_planes()
             self._make_cgeom()
             # the planes were written by torch ops on the current stream; numpy queries run on the library's own
@@ -379,7 +383,7 @@ class _CubicInterpolator:
         return self
 
     def _pack_planes(self):
-        """Table-free 3-D 'vector' / 'both': the component-interleaved grid ``[nz][ny][nx][4]`` (Bx, By, Bz, |B| or 0)
+        """Table-free 'vector' / 'both': the component-interleaved grid ``[nt][nz][ny][nx][4]`` (Bx, By, Bz, |B| or 0)
         the query kernel gathers from -- one 128-byte piece per neighbourhood row serves every component."""
         if not getattr(self, "_use_packed", False):
             self._packed = None

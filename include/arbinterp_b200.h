@@ -145,10 +145,12 @@ int arb_query_nodes_host(const arb_geom* g, const double* nodes, int mode, doubl
                          double* out_comps_host, double* out_norm_host, double* out_grad_host, int64_t* out_cell_host,
                          int64_t chunk_rows);
 
-/* Table-free 3-D 'vector' / 'both' queries on a component-interleaved grid: packed = device [nz][ny][nx][4]
- * (Bx, By, Bz, |B| -- the 4th value is not read in mode VECTOR), 32-byte aligned; g->ncomp = 3 or 4 as for arb_query_grid.
- * One 128-byte piece per grid row of the neighbourhood serves every component (arb_query_grid: one 48-byte piece per
- * row and component).  Same outputs and conventions as arb_query_grid. */
+/* Table-free 'vector' / 'both' queries on a component-interleaved grid: packed = device [nz][ny][nx][4] (3-D) or
+ * [nt][nz][ny][nx][4] (4-D; rQuery1 / rQuery3 of quadcubic, A.py:1064-1127, 1190-1258, incl. the A.py:860 term unless
+ * ARB_GEOM_FIXED_D4) with the point's values (Bx, By, Bz, |B|) together -- the 4th value is not read in mode VECTOR --
+ * 32-byte aligned, smaller than 128 GB; g->ncomp = 3 or 4 as for arb_query_grid.  One 128-byte piece per grid row of
+ * the neighbourhood serves every component (arb_query_grid: one 48-byte piece per row and component).  Same outputs
+ * and conventions as arb_query_grid. */
 int arb_query_gridil(const arb_geom* g, const double* packed, int mode, double* q, int64_t N, int64_t ldq,
                      double* out_comps, double* out_norm, double* out_grad, int64_t* out_cell, int64_t* masked_rows,
                      unsigned long long* masked_count, void* stream);

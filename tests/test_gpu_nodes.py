@@ -168,6 +168,59 @@ def test_table_free_interleaved_grid(mode):
         assert np.array_equal(x, y, equal_nan=True)
 
 
+@pytest.mark.parametrize("fixed", [False, True])
+@pytest.mark.parametrize("mode", ["vector", "both"])
+def test_table_free_interleaved_grid_4d(mode, fixed):
+    """Table-free 4-D 'vector' / 'both' on the component-interleaved grid [nt][nz][ny][nx][4] (query_gridil4_kernel:
+    four lanes = the z-planes of a query, four passes = its t-planes, A.py:860 term from parity sums exchanged between
+    the lanes) against the cell table, the per-component TMA-box kernel and -- with the quirk -- the oracle; the field
+    has an xyzt monomial, so the quirk and fixed answers differ by ~1e-6.  Odd nx, clustered rows (shared slots),
+    NaN / out-of-volume rows, device tensors, update_values."""
+    from arbinterp_b200 import quadcubic
+    rng = np.random.default_rng(4242)
+    field = _analytic_field4(13, 9, 8, 7, rng=rng)
+    cells = quadcubic(field.copy(), "quiet", mode=mode, fixed_d4=fixed)
+    il = quadcubic(field.copy(), "quiet", mode=mode, fixed_d4=fixed, table=False, interleave=True)
+    pl = quadcubic(field.copy(), "quiet", mode=mode, fixed_d4=fixed, table=False, interleave=False)
+    assert il._packed is not None and pl._packed is None and tuple(il._packed.shape) == (7, 8, 9, 13, 4)
+    if mode == "both":          # the default form of 4-D 'both'
+        assert quadcubic(field.copy(), "quiet", mode=mode, table=False)._packed is not None
+    q = _uniform_queries(cells, 4, 120_000, rng, extra=1)
+    q[40_000:80_000] = q[40_000:40_400].repeat(100, axis=0)      # bunches of rows in the same cells: shared slots
+    q[40_000:80_000, :4] += rng.uniform(0, 1e-4, (40_000, 4)) * np.array([cells.hx, cells.hy, cells.hz, cells.ht])
+    q[::101, 0] = -9.0
+    q[::977, 3] = np.nan
+    q[::53, 3] = -1.0
+    h = [cells.hx, cells.hy, cells.hz, cells.ht]
+    outs = {}
+    for name, obj in (("cells", cells), ("il", il), ("pl", pl)):
+        qq = q.copy()
+        r = obj.Query(qq)
+        outs[name] = (r if isinstance(r, tuple) else (r,), qq, obj.queryInds)
+    for name in ("il", "pl"):
+        _check_outputs(outs[name][0], outs["cells"][0], mode, field, 4, h, f"4-D table-free {name} vs cells {mode} fixed={fixed}")
+        assert np.array_equal(outs[name][1], outs["cells"][1], equal_nan=True)
+        assert np.array_equal(outs[name][2], outs["cells"][2])
+    if not fixed:
+        from oracle.arb_oracle import OracleInterp
+        ora = OracleInterp(field, 4, mode=mode)
+        ref = ora.query(q[:10_000].copy())
+        ref = ref if isinstance(ref, tuple) else (ref,)
+        _check_outputs(il.Query(q[:10_000].copy()), ref, mode, field, 4, ora.geo.h, f"4-D interleaved vs oracle {mode}")
+        assert np.array_equal(il.queryInds, ora.query_inds)
+    dev = il.Query(torch.from_numpy(q.copy()).cuda())
+    dev = dev if isinstance(dev, tuple) else (dev,)
+    for x, y in zip(outs["il"][0], dev):
+        assert np.array_equal(x, y.cpu().numpy(), equal_nan=True)
+    new_vals = field[:, 4:] * 0.5 - 0.125
+    il.update_values(new_vals)
+    fresh = quadcubic(np.concatenate([field[:, :4], new_vals], axis=1), "quiet", mode=mode, fixed_d4=fixed, table=False,
+                      interleave=True)
+    a, b = il.Query(q.copy()), fresh.Query(q.copy())
+    for x, y in zip(a if isinstance(a, tuple) else (a,), b if isinstance(b, tuple) else (b,)):
+        assert np.array_equal(x, y, equal_nan=True)
+
+
 @pytest.mark.parametrize("name,d,mode", [("tri_12x10x9", 3, "both"), ("tri_12x10x9", 3, "norm"), ("quad_8x7x7x6", 4, "both")])
 def test_node_table_save_and_load(name, d, mode, tmp_path):
     """save() / load() of a node table: the loaded interpolator answers bit-identically with no field, ingest or build;
@@ -354,3 +407,68 @@ def test_push_on_node_table_matches_cell_table(d, mode, fixed):
     p_np, v_np = pos.copy(), vel.copy()
     assert nodes.push(p_np, v_np, dt, 40, -0.3, gravity=(0.0, 0.0, -0.05)) == lb
     assert np.array_equal(p_np, pb, equal_nan=True)
+
+
+def test_node_table_beyond_64_gb(cuda_lib):
+    """The LDGSTS gather passes a slot's source between lanes as a 32-bit count of 128-byte units, so node tables may
+    be larger than the 64 GB a count of 16-byte units could address (they fit a 180 GB GPU long before a cell table
+    does).  C-ABI level, no field rows: an 824^3 one-component grid made on the device, its 71 GB node table, and
+    queries concentrated in the last z-layers (table offsets above 64 GB) checked against the table-free path on the
+    same grid and against the analytic field, which both forms reproduce to round-off (per-axis quadratics)."""
+    import ctypes
+    from arbinterp_b200 import _lib
+    torch.cuda.empty_cache()
+    free, total = torch.cuda.mem_get_info(0)
+    if free < 100 * (1 << 30):
+        pytest.skip(f"needs ~80 GB of free device memory, {free >> 30} GB free")
+    dev = torch.device("cuda", 0)
+    n = 824
+    ax = torch.linspace(-1.0, 1.0, n, dtype=torch.float64, device=dev)
+    X, Y, Z = ax.view(1, 1, n), ax.view(1, n, 1), ax.view(n, 1, 1)
+    f = lambda x, y, z: 1.0 + x * x - 0.5 * y * y + 0.25 * z * z + 0.3 * x * y * z + 0.2 * y * z * z
+    planes = f(X, Y, Z).contiguous().view(1, n, n, n)
+    nodes = torch.empty((1, n - 2, n - 2, n - 3, 2, 8), dtype=torch.float64, device=dev)
+    assert nodes.numel() * 8 > 68 * (1 << 30)
+    npts = (ctypes.c_int64 * 4)(n, n, n, 1)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    _lib.check(cuda_lib.arb_build_nodes(3, planes.data_ptr(), 1, ctypes.byref(npts), n, nodes.data_ptr(), st), "arb_build_nodes")
+    g = _lib.ArbGeom()
+    g.d, g.ncomp = 3, 1
+    h = float(ax[1] - ax[0])
+    for a in range(4):
+        g.ncell[a] = n - 3 if a < 3 else 1
+        g.int_min[a] = float(ax[1]) if a < 3 else 0.0
+        g.int_max[a] = float(ax[n - 2]) if a < 3 else 0.0
+        g.h[a] = h if a < 3 else 1.0
+    g.slab_lo, g.slab_hi, g.flags = 0, n - 3, 0
+    gen = torch.Generator(device=dev).manual_seed(5)
+    N = 400_000
+    lo, hi = float(ax[1]), float(ax[n - 2])
+    q = lo + torch.rand((N, 3), generator=gen, dtype=torch.float64, device=dev) * (hi - lo) * (1 - 1e-9)
+    q[N // 2:, 2] = hi - torch.rand(N - N // 2, generator=gen, dtype=torch.float64, device=dev) * 40 * h   # last z-layers
+    outs = {}
+    for name in ("nodes", "grid"):
+        norm = torch.empty(N, dtype=torch.float64, device=dev)
+        grad = torch.empty((N, 3), dtype=torch.float64, device=dev)
+        cell = torch.empty(N, dtype=torch.int64, device=dev)
+        qq = q.clone()
+        if name == "nodes":
+            rc = cuda_lib.arb_query_nodes(ctypes.byref(g), nodes.data_ptr(), _lib.MODE_NORM, qq.data_ptr(), N, 3, None,
+                                          norm.data_ptr(), grad.data_ptr(), cell.data_ptr(), None, None, st)
+        else:
+            rc = cuda_lib.arb_query_grid(ctypes.byref(g), planes.data_ptr(), n, _lib.MODE_NORM, qq.data_ptr(), N, 3, None,
+                                         norm.data_ptr(), grad.data_ptr(), cell.data_ptr(), None, None, st)
+        _lib.check(rc, name)
+        outs[name] = (norm, grad, cell)
+    torch.cuda.synchronize()
+    assert torch.equal(outs["nodes"][2], outs["grid"][2])
+    top = outs["nodes"][2].max().item() // ((n - 3) * (n - 3))
+    assert (top * (n - 2) * (n - 3)) * 128 > 64 * (1 << 30), "no query reached table offsets beyond 64 GB"
+    want = f(q[:, 0], q[:, 1], q[:, 2])
+    S = float(planes.abs().max())
+    for name in ("nodes", "grid"):
+        assert float((outs[name][0] - want).abs().max()) < 1e-12 * S, name
+    assert float((outs["nodes"][0] - outs["grid"][0]).abs().max()) < 1e-12 * S
+    assert float((outs["nodes"][1] - outs["grid"][1]).abs().max()) < 1e-12 * S / h
+    del nodes, planes
+    torch.cuda.empty_cache()

@@ -153,6 +153,25 @@ def test_table_free_quadcubic_math_on_host(tmp_path):
     assert len(errs) >= 4 and max(errs) <= 1e-12
 
 
+def test_interleaved_grid_4d_math_on_host(tmp_path):
+    """The __host__ __device__ pieces of the 4-D interleaved table-free kernel (arb_gridil4.cuh: one lane per z-plane,
+    one pass per t-plane, parity sums for the A.py:860 term and the two lane exchanges) equal the monomial evaluation of
+    alpha = A f for every component, 'vector' and 'both', with and without the quirk."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "gridil4_host_emul")
+    subprocess.run([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "--expt-relaxed-constexpr", "-o", exe,
+                    os.path.join(ROOT, "tests", "host_emul", "gridil4_host_emul.cu"),
+                    os.path.join(ROOT, "arbinterp_b200", "csrc", "arb_core.cu")], check=True, timeout=600)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    errs = [float(x) for x in re.findall(r"max scaled error ([0-9.eE+-]+)", out.stdout)]
+    assert out.returncode == 0, out.stdout
+    assert len(errs) >= 5 and max(errs) <= 1e-12
+
+
 def test_node_table_math_on_host(tmp_path):
     """The __host__ __device__ pieces of the node (Hermite) table (arb_nodes.cuh: the central-difference stencil of the
     build, the 3-D evaluation, the four-lane 4-D evaluation with the A.py:860 term) equal the monomial evaluation of
