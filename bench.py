@@ -20,6 +20,7 @@ import subprocess
 import sys
 import threading
 import time
+_T_PROCESS_START = time.perf_counter()
 import warnings
 
 import numpy as np
@@ -1187,6 +1188,7 @@ def run_b200(args):
         line["other_modes"] = others
     if sharded:
         line["sharded"] = sharded
+    line["wall_s"] = time.perf_counter() - _T_PROCESS_START      # the whole run, imports and every extra leg included
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
