@@ -403,12 +403,15 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
                 const uint32_t src16 = (uint32_t)((reinterpret_cast<const char*>(src) - reinterpret_cast<const char*>(p.table)) >> USH);
                 const char* const lane_base = reinterpret_cast<const char*>(p.table) + lane_src;
                 const uint32_t ring0 = smem_u32(ring) + lane * 16;
+                // interleaved nodes in mode 'vector': the |B| block of each node (bytes 192..255 of its 256) is never
+                // read, so the four lanes that would copy it stay idle -- a quarter of the bytes is not moved at all
+                const bool lane_copies = !(KIND == KIND_NODES_IL && MODE == 0 && (lane & 12) == 12);
 #pragma unroll 8
                 for (int o = 0; o < 32; ++o) {
                     if ((fmask >> o) & 1u) {
                         const uint32_t s16 = __shfl_sync(0xffffffffu, src16, o);
                         const uint32_t slot_o = (SLOTS == 32) ? (uint32_t)o : (uint32_t)__shfl_sync(0xffffffffu, myslot, o);
-                        cp_async_16(ring0 + slot_o * SLOT, lane_base + ((size_t)s16 << USH));
+                        if (lane_copies) cp_async_16(ring0 + slot_o * SLOT, lane_base + ((size_t)s16 << USH));
                     }
                 }
             } else {
