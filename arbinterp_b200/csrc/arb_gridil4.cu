@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(THREADS) query_gridil4_kernel(const QueryParam
     unsigned char* const ring = smem + (size_t)wid * 32 * SLOT;
     const int64_t nx = p.nc[0] + 3, ny = p.nc[1] + 3, nz = p.nc[2] + 3;
     // this lane's 16 bytes of a slot: row j = lane / 8 of the plane (nx grid points of 32 B apart), piece lane % 8
-    const char* const lane_base = reinterpret_cast<const char*>(p.table) + (lane >> 3) * nx * 32 + (lane & 7) * 16;
+    const char* const lane_base = reinterpret_cast<const char*>(p.table) + gridil4::lane_piece_bytes(lane, nx);
     const uint32_t ring0 = smem_u32(ring) + lane * 16;
     const int64_t warp_global = ((int64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * THREADS) >> 5;
@@ -54,8 +54,6 @@ __global__ void __launch_bounds__(THREADS) query_gridil4_kernel(const QueryParam
         gridil4::Acc acc;
         gridil4::clear<QUIRK>(acc);
         // first row of this lane's plane in pass 0, as a count of grid points (32 B each) from the grid's first byte
-        const int64_t pt0 = (((int64_t)L.idx[3] * nz + L.idx[2] + sl) * ny + L.idx[1]) * nx + L.idx[0];
-        const int64_t pt_step = nz * ny * nx;                              // one t-plane further
         // lanes of different queries that want the same z-plane of the same cell share one slot in every pass
         int src_lane = lane;
         bool leader = L.ok;
@@ -67,7 +65,8 @@ __global__ void __launch_bounds__(THREADS) query_gridil4_kernel(const QueryParam
         const unsigned fmask = __ballot_sync(0xffffffffu, leader);
 #pragma unroll 1
         for (int l = 0; l < 4; ++l) {
-            const uint32_t src32 = (uint32_t)(pt0 + l * pt_step);         // grids < 128 GB (checked by the launcher)
+            // grids < 128 GB (checked by the launcher): the count of 32-byte points fits 32 bits
+            const uint32_t src32 = (uint32_t)gridil4::plane_first_point(L.idx, sl, l, nx, ny, nz);
 #pragma unroll 8
             for (int o = 0; o < 32; ++o) {
                 if ((fmask >> o) & 1u) {

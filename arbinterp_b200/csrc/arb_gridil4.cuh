@@ -20,6 +20,15 @@ namespace gridil4 {
 using gridfree::fma_;
 using gridfree::sel4;
 
+// Gather addressing (shared with the host emulation).  A slot is the 4 x 4 (y, x) points of one (z, t) plane with their
+// four components: 4 rows of 128 contiguous bytes, nx grid points (32 B each) apart.  One warp-wide 16-byte copy fills
+// it: lane i brings bytes [16 i, 16 i + 16) of the slot, i.e. row i / 8, piece i % 8 of that row.
+ARB_HD int64_t lane_piece_bytes(int lane, int64_t nx) { return (int64_t)(lane >> 3) * nx * 32 + (lane & 7) * 16; }
+// first grid point (count of 32-byte points from the grid's first byte) of the plane lane k (z-plane) needs in pass l
+ARB_HD int64_t plane_first_point(const int* idx, int k, int l, int64_t nx, int64_t ny, int64_t nz) {
+    return ((((int64_t)idx[3] + l) * nz + idx[2] + k) * ny + idx[1]) * nx + idx[0];
+}
+
 struct Weights {          // Catmull-Rom weights of the query's cell fractions, computed once per query
     double wx[4], dwx[4], wy[4], dwy[4], wz[4], dwz[4], wt[4], dwt[4];
 };

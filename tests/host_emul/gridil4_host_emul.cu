@@ -62,9 +62,16 @@ static double run(int64_t nx, int64_t ny, int64_t nz, int64_t nt, int nq, uint64
             clear<QUIRK>(acc[k]);
             if (!QUIRK) memset(acc[k].T, 0, sizeof(acc[k].T));
             for (int l = 0; l < 4; ++l) {
+                // the kernel's gather: 32 "lanes" bring 16 bytes each, addressed by the kernel's own helpers
                 alignas(16) double slot[64];
+                const int idx[4] = {(int)ix, (int)iy, (int)iz, (int)it};
+                const uint32_t src32 = (uint32_t)plane_first_point(idx, k, l, nx, ny, nz);
+                for (int lane = 0; lane < 32; ++lane)
+                    memcpy(reinterpret_cast<char*>(slot) + lane * 16,
+                           reinterpret_cast<const char*>(grid.data()) + lane_piece_bytes(lane, nx) + ((size_t)src32 << 5), 16);
                 for (int j = 0; j < 4; ++j)
-                    for (int i = 0; i < 4; ++i) memcpy(slot + (j * 4 + i) * 4, at(ix + i, iy + j, iz + k, it + l), 4 * sizeof(double));
+                    for (int i = 0; i < 4; ++i)
+                        if (memcmp(slot + (j * 4 + i) * 4, at(ix + i, iy + j, iz + k, it + l), 4 * sizeof(double)) != 0) return 1.0;
                 pass<BOTH, QUIRK>(acc[k], slot, k, l, W);
             }
         }

@@ -8,7 +8,7 @@ OUT=gpurun_out
 mkdir -p $OUT
 cap() {  # name units_per_launch args...   (SKIP = query-kernel launches before the captured one)
   name=$1; units=$2; shift 2
-  timeout 600 ncu --set full --clock-control none --import-source on -k "regex:query_block_kernel" -s ${SKIP:-2} -c 1 -f \
+  timeout 600 ncu --set full --clock-control none --import-source on -k "regex:${KREGEX:-query_block_kernel}" -s ${SKIP:-2} -c 1 -f \
       -o $OUT/r02_$name python tools/profile_target.py --launches 3 "$@" > $OUT/r02_ncu_$name.log 2>&1
   tail -1 $OUT/r02_ncu_$name.log
   python tools/ncu_summary.py $OUT/r02_$name.ncu-rep $units > $OUT/r02_${name}_ncu.txt 2>&1
@@ -28,6 +28,8 @@ for c in "$@"; do
     nodes)        cap nodes3d_norm $Q --mode norm --table nodes ;;
     nodes_sorted) SKIP=3 cap nodes3d_norm_sorted $Q --mode norm --table nodes --order sorted ;;
     nodes4)       cap nodes4d_both 4194304 --d 4 --mode both --queries 4194304 --table nodes ;;
+    gridil4)      KREGEX=query_gridil4_kernel SKIP=1 cap gridil4_both 4194304 --d 4 --mode both --queries 4194304 --table free ;;
+    nodes_vec)    cap nodes3d_vector $Q --mode vector --table nodes ;;
     *) echo "unknown capture $c" ;;
   esac
 done
