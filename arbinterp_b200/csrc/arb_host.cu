@@ -165,33 +165,15 @@ struct Slot {
     int64_t off = 0, rows = 0;
 };
 
-// pinned staging ring for pageable query rows.  A buffer holds one chunk and is filled in up to NPIECE pieces, one
-// copy-pool task and one ticket each, NSTAGE - 1 chunks ahead of the chunk being issued; the H2D copy of a piece is
-// issued as soon as that piece is staged.  Staging granularity (pieces of 1-3 MB: the first copy starts ~0.2 ms into
-// the call) is thereby independent of the chunk the GPU works on (1 Mi rows: a quarter of the launches and copies
-// per row of the 256 Ki-row chunks staging needed while it was chunk-granular).  A buffer is refilled once its own
-// H2D copies have finished.
-constexpr int NSTAGE = 4;
-constexpr int NPIECE = 16;       // capacity; stage_pieces() of them are used (default 8, ARB_STAGE_PIECES)
+// pinned staging ring for pageable query rows: deeper than the stream ring, so the helper threads run
+// NSTAGE - 1 chunks ahead of the chunk being issued; a buffer is refilled once its own H2D copy has finished
+constexpr int NSTAGE = 6;
 struct StageBuf {
     double* h = nullptr;
     cudaEvent_t h2d_done = nullptr;
     bool used = false;
-    int npiece = 0;
-    int64_t piece_rows = 0;
-    CopyPool::Ticket ticket[NPIECE];
+    CopyPool::Ticket ticket;
 };
-
-int stage_pieces() {
-    static int v = 0;
-    if (!v) {
-        const char* e = getenv("ARB_STAGE_PIECES");
-        v = e ? atoi(e) : 8;
-        if (v < 1) v = 1;
-        if (v > NPIECE) v = NPIECE;
-    }
-    return v;
-}
 
 struct HostCtx {
     Slot slot[NSLOT];
@@ -414,7 +396,7 @@ namespace {
 // error exit of the pipelined path: nothing may stay in flight that still points at this call's buffers
 int abandon(HostCtx& ctx, int rc) {
     for (int i = 0; i < NSTAGE; ++i) {             // helper threads still read the caller's rows
-        for (int k = 0; k < NPIECE; ++k) g_pool.wait(&ctx.stage[i].ticket[k]);
+        g_pool.wait(&ctx.stage[i].ticket);
         ctx.stage[i].used = false;
     }
     for (int i = 0; i < NSLOT; ++i) {
@@ -449,12 +431,12 @@ static int query_host_impl(const arb_geom* g, const double* table, int64_t grid_
     c.grad_pinned = is_pinned(c.grad); c.cell_pinned = is_pinned(c.cell);
     c.cell_on_device = is_device(c.cell);
     if (chunk_rows <= 0) {
-        // measured optima (profiles/r01_e2e_chunk_sweep.log, r01_midsize_chunks.log): 1 Mi rows when the results land
-        // in page-locked memory (pageable QUERY rows are staged piecewise, see StageBuf, so they do not need small
-        // chunks), 256 Ki when results are staged out through the ring (that memcpy runs in line with the issue
-        // loop), and never fewer than ~6 chunks so that mid-size batches pipeline at all
-        const bool out_pinned = c.comps_pinned && c.norm_pinned && c.grad_pinned && (c.cell_pinned || c.cell_on_device);
-        const int64_t base = out_pinned ? (1 << 20) : (1 << 18);
+        // measured optima (profiles/r01_e2e_chunk_sweep.log, r01_midsize_chunks.log): 1 Mi rows when every
+        // buffer is page-locked, 256 Ki when something is staged through the ring (the staging memcpy then
+        // overlaps the copies), and never fewer than ~6 chunks so that mid-size batches pipeline at all
+        const bool all_pinned = c.q_pinned && c.comps_pinned && c.norm_pinned && c.grad_pinned &&
+                                (c.cell_pinned || c.cell_on_device);
+        const int64_t base = all_pinned ? (1 << 20) : (1 << 18);
         int64_t sixth = (N + 5) / 6;
         if (sixth < 65536) sixth = 65536;
         chunk_rows = sixth < base ? sixth : base;
@@ -478,19 +460,12 @@ static int query_host_impl(const arb_geom* g, const double* table, int64_t grid_
         if (_rc) return abandon(ctx, _rc);                          \
     } while (0)
     const int64_t nchunks = (N + chunk_rows - 1) / chunk_rows;
-    // pageable rows: chunk j is staged into ring buffer j % NSTAGE by the helper threads, piece by piece
+    // pageable rows: chunk j is staged into ring buffer j % NSTAGE by the helper threads, NSTAGE - 1 chunks ahead
     auto stage_chunk = [&](int64_t j) -> int {
         StageBuf& b = ctx.stage[j % NSTAGE];
         if (b.used) ARB_CUDA(cudaEventSynchronize(b.h2d_done));
         const int64_t o = j * chunk_rows, n = (N - o < chunk_rows) ? (N - o) : chunk_rows;
-        int np = (int)((sizeof(double) * n * ldq) >> 20);            // pieces of >= 1 MiB
-        np = np < 1 ? 1 : (np > stage_pieces() ? stage_pieces() : np);
-        b.piece_rows = (((n + np - 1) / np) + 511) & ~(int64_t)511;   // whole 4 KiB pages for any ldq
-        b.npiece = (int)((n + b.piece_rows - 1) / b.piece_rows);
-        for (int k = 0; k < b.npiece; ++k) {
-            const int64_t r0 = k * b.piece_rows, rn = (n - r0 < b.piece_rows) ? (n - r0) : b.piece_rows;
-            g_pool.submit(b.h + r0 * ldq, q_host + (o + r0) * ldq, sizeof(double) * rn * ldq, &b.ticket[k], 1);
-        }
+        g_pool.submit(b.h, q_host + o * ldq, sizeof(double) * n * ldq, &b.ticket, 2);
         b.used = true;
         return 0;
     };
@@ -505,18 +480,19 @@ static int query_host_impl(const arb_geom* g, const double* table, int64_t grid_
         rc = retire(s, c);
         if (rc) return abandon(ctx, rc);
         const int64_t n = (N - off < chunk_rows) ? (N - off) : chunk_rows;
-        if (c.q_pinned) {
-            ARB_CUDA_OR_ABANDON(cudaMemcpyAsync(s.d_q, q_host + off * ldq, sizeof(double) * n * ldq, cudaMemcpyHostToDevice, s.stream));
-        } else {
-            StageBuf& sb = ctx.stage[chunk % NSTAGE];
-            for (int k = 0; k < sb.npiece; ++k) {                    // each piece leaves as soon as it is staged
-                const int64_t r0 = k * sb.piece_rows, rn = (n - r0 < sb.piece_rows) ? (n - r0) : sb.piece_rows;
-                g_pool.wait(&sb.ticket[k]);
-                ARB_CUDA_OR_ABANDON(cudaMemcpyAsync(s.d_q + r0 * ldq, sb.h + r0 * ldq, sizeof(double) * rn * ldq,
-                                                    cudaMemcpyHostToDevice, s.stream));
+        const double* src = q_host + off * ldq;
+        StageBuf* sb = nullptr;
+        if (!c.q_pinned) {
+            if (chunk + NSTAGE - 1 < nchunks) {
+                rc = stage_chunk(chunk + NSTAGE - 1);
+                if (rc) return abandon(ctx, rc);
             }
-            ARB_CUDA_OR_ABANDON(cudaEventRecord(sb.h2d_done, s.stream));
+            sb = &ctx.stage[chunk % NSTAGE];
+            g_pool.wait(&sb->ticket);
+            src = sb->h;
         }
+        ARB_CUDA_OR_ABANDON(cudaMemcpyAsync(s.d_q, src, sizeof(double) * n * ldq, cudaMemcpyHostToDevice, s.stream));
+        if (sb) ARB_CUDA_OR_ABANDON(cudaEventRecord(sb->h2d_done, s.stream));
         ARB_CUDA_OR_ABANDON(cudaMemsetAsync(s.d_count, 0, sizeof(unsigned long long), s.stream));
         int64_t* cell_dst = c.cell ? (c.cell_on_device ? c.cell + off : s.d_cell) : nullptr;
         rc = query_any_device(g, table, grid_pitch, mode, s.d_q, n, ldq, s.d_comps, s.d_norm, s.d_grad, cell_dst,
@@ -537,12 +513,6 @@ static int query_host_impl(const arb_geom* g, const double* table, int64_t grid_
         ARB_CUDA_OR_ABANDON(cudaMemcpyAsync(s.h_count, s.d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
         ARB_CUDA_OR_ABANDON(cudaEventRecord(s.done, s.stream));
         s.busy = true; s.off = off; s.rows = n;
-        // the buffer of the chunk issued before this one is free once its H2D copies are done -- by now they have had
-        // this iteration's time, and the GPU has this chunk queued while the host waits for them
-        if (!c.q_pinned && chunk + NSTAGE - 1 < nchunks) {
-            rc = stage_chunk(chunk + NSTAGE - 1);
-            if (rc) return abandon(ctx, rc);
-        }
     }
     for (int i = 0; i < NSLOT; ++i) {
         rc = retire(ctx.slot[i], c);

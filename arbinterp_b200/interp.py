@@ -143,10 +143,10 @@ class _CubicInterpolator:
             if self._pitch != nx:
                 self._planes = torch.nn.functional.pad(self._planes, (0, 1)).contiguous()
             # component-interleaved grid (one 128-byte piece per neighbourhood row serves every component): the default
-            # for 3-D 'vector' / 'both' and 4-D 'both'; 4-D 'vector' would gather the unused |B| slot too (8 KB per
-            # query instead of 6), so it keeps the per-component TMA boxes unless asked (interleave=True)
-            self._use_packed = (not scalar) and mode in ("vector", "both") and bool(
-                kwargs.get("interleave", d == 3 or mode == "both"))
+            # for 'vector' / 'both' in 3-D and 4-D (4-D 'vector' gathers the unused |B| slot too and is still faster
+            # than the per-component TMA boxes: 0.71 against 0.63 of the cell table on 48^3x32, 0.54 against 0.29 on
+            # 64^3x48, profiles/r02_tablefree_bench_4d.log); interleave=False keeps the per-component planes
+            self._use_packed = (not scalar) and mode in ("vector", "both") and bool(kwargs.get("interleave", True))
             self._pack_planes()
             self._make_cgeom()
             # the planes were written by torch ops on the current stream; numpy queries run on the library's own

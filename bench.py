@@ -408,10 +408,14 @@ def time_public_device(torch, obj, q, steps, warmup):
     from torch's caching allocator); queries/s from CUDA events around the K calls."""
     # these legs follow seconds of CPU-side checking with the GPU idle: warm up for >= 100 ms so that the clocks are
     # back up before the timed calls (a 2 ms kernel timed right after an idle period ran at half its rate)
+    # (the warm-up keeps the previous call's outputs alive while the next call allocates, exactly like the timed loop:
+    # otherwise the first timed call needs a second set of output blocks that the caching allocator does not hold yet,
+    # and one cudaMalloc of ~0.5 GB inside ten 2 ms kernels read as "0.3-0.5 of the usual rate" in earlier sessions)
     t0 = time.perf_counter()
     done = 0
-    while done < warmup or time.perf_counter() - t0 < 0.1:
-        obj.Query(q)
+    res = None
+    while done < max(warmup, 2) or time.perf_counter() - t0 < 0.1:
+        res = obj.Query(q)
         torch.cuda.synchronize()
         done += 1
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -285,9 +285,9 @@ def test_single_process_devices_list():
     assert all(np.array_equal(x, y, equal_nan=True) for x, y in zip(ra, rb))
 
 
-def test_pageable_rows_staged_piecewise(monkeypatch):
-    """arb_query_host stages ordinary (pageable) numpy rows into its pinned ring in pieces and issues each piece's H2D
-    copy as soon as it is staged (csrc/arb_host.cu, StageBuf).  A batch of several chunks with a ragged tail, extra
+def test_pageable_rows_staged_ahead(monkeypatch):
+    """arb_query_host stages ordinary (pageable) numpy rows into its pinned ring on helper threads, chunks ahead of the
+    one being issued (csrc/arb_host.cu, StageBuf / CopyPool).  A batch of several chunks with a ragged tail, extra
     query columns (README: ignored) and out-of-volume rows in the first / a middle / the last piece must come back
     bit-identical to the device-tensor path, with the NaN rows written into the caller's array (A.py:350-355)."""
     from arbinterp_b200 import tricubic

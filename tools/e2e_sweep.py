@@ -14,7 +14,7 @@ qh.copy_(torch.from_numpy(lo + np.random.default_rng(0).uniform(0, 1, (n, 3)) * 
 qnp = qh.numpy()
 qpage = qnp.copy()
 chunks = [int(c) for c in os.environ.get("ARB_E2E_CHUNKS", "0,262144,524288,1048576,2097152,4194304").split(",")]
-print(f"[e2e] ARB_COPY_THREADS={os.environ.get('ARB_COPY_THREADS', 'default')} ARB_STAGE_PIECES={os.environ.get('ARB_STAGE_PIECES', 'default')} cores={len(os.sched_getaffinity(0))} (chunk 0 = the library's own choice)", flush=True)
+print(f"[e2e] ARB_COPY_THREADS={os.environ.get('ARB_COPY_THREADS', 'default')} cores={len(os.sched_getaffinity(0))} (chunk 0 = the library's own choice)", flush=True)
 for chunk in chunks:
     os.environ["ARB_HOST_CHUNK_ROWS"] = str(chunk)
     for name, arr in (("pinned", qnp), ("pageable", qpage)):

@@ -35,8 +35,8 @@ for mode in ("vector", "norm", "both"):
     lib.arb_set_query_variant(0)
     for fixed in (False, True):
         quadcubic(f4, "quiet", mode=mode, table=False, fixed_d4=fixed).Query(q4.copy())
-        if mode == "vector":                      # the interleaved 4-D grid is the default for 'both' only
-            quadcubic(f4, "quiet", mode=mode, table=False, fixed_d4=fixed, interleave=True).Query(q4.copy())
+        if mode != "norm":                        # the interleaved 4-D grid is the default; the per-component boxes too
+            quadcubic(f4, "quiet", mode=mode, table=False, fixed_d4=fixed, interleave=False).Query(q4.copy())
 # round 2: compact slot rings / prefetch / probe / LDGSTS variants of the cell kernel, node tables (3-D paired and
 # interleaved, 4-D with the A.py:860 term), interleaved table-free grid
 for mode in ("vector", "norm", "both"):

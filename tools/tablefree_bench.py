@@ -51,6 +51,7 @@ for shape, nq in cases:
         qs = q[torch.argsort(cells._last_cells)].contiguous()
         base = {"uniform random": rate(cells, q), "cell-sorted": rate(cells, qs)}
         tgb = cells.table.numel() * 8 / 1e9
+        cells.release()                        # `del` alone waits for the garbage collector (reference cycle)
         del cells
         torch.cuda.empty_cache()
         forms = [("planes + TMA boxes", dict(table=False, interleave=False))]
@@ -63,6 +64,7 @@ for shape, nq in cases:
             line = [f"{k}: {rate(obj, qq):.3e} q/s (x{rate(obj, qq) / base[k]:.2f} of the cell table)"
                     for k, qq in (("uniform random", q), ("cell-sorted", qs))]
             print(f"[tablefree] {grid} {mode} {name} ({mem:.3f} GB vs {tgb:.2f} GB of cell table): " + " | ".join(line), flush=True)
+            obj.release()
             del obj
             torch.cuda.empty_cache()
         print(f"[tablefree] {grid} {mode} cell table: " + " | ".join(f"{k}: {v:.3e} q/s" for k, v in base.items()), flush=True)
