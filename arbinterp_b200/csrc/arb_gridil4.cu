@@ -8,18 +8,20 @@
 // Four lanes own a query (lane k = z-plane k), the four t-planes are passes; in a pass every lane's 512-byte slot
 // (4 rows of 128 B) is filled by ONE warp-wide cp.async (SASS LDGSTS, 32 lanes x 16 B) whose source comes from the owning
 // lane over a shuffle, exactly like the node-table and 3-D interleaved forms of query_block_kernel.  Lanes of different
-// queries that want the same plane of the same cell share one slot (DEDUP).  The math and the two lane exchanges of the
-// A.py:860 term are in arb_gridil4.cuh.
+// queries that want the same plane of the same cell share one slot (DEDUP).  The math, including the A.py:860 term as a
+// second set of point weights, is in arb_gridil4.cuh.
 #include "arb_device.cuh"
 #include "arb_gridil4.cuh"
 
 namespace arb {
 
-template <int MODE, bool QUIRK, bool DEDUP, int THREADS>
-__global__ void __launch_bounds__(THREADS) query_gridil4_kernel(const QueryParams p) {
+// MINB = 3: the compiler keeps to 168 registers so that three CTAs are resident per SM (the 'both' + quirk form spills
+// ~190 bytes for it); MINB = 2 (query variant 81) lets it take ~250 and two CTAs -- measured in tools/tablefree_bench.py
+template <int MODE, bool QUIRK, bool DEDUP, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) query_gridil4_kernel(const QueryParams p) {
     static_assert(MODE == 0 || MODE == 2, "interleaved grid: 'vector' / 'both'");
     constexpr bool BOTH = (MODE == 2);
-    constexpr int D = 4, SL = 4, QPW = 8, NC = BOTH ? 4 : 3, NV = BOTH ? 8 : 3;
+    constexpr int D = 4, SL = 4, QPW = 8, NV = BOTH ? 8 : 3;
     constexpr uint32_t SLOT = 528;                 // 512 + 16: LDS.128 of neighbouring lanes on distinct bank groups
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -51,9 +53,7 @@ __global__ void __launch_bounds__(THREADS) query_gridil4_kernel(const QueryParam
         }
         gridil4::Weights W;
         gridil4::make_weights(L.frac, W);
-        gridil4::Acc acc;
-        gridil4::clear<QUIRK>(acc);
-        // first row of this lane's plane in pass 0, as a count of grid points (32 B each) from the grid's first byte
+        double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         // lanes of different queries that want the same z-plane of the same cell share one slot in every pass
         int src_lane = lane;
         bool leader = L.ok;
@@ -84,55 +84,32 @@ __global__ void __launch_bounds__(THREADS) query_gridil4_kernel(const QueryParam
             cp_async_wait_all();
             __syncwarp();
             if (L.ok)
-                gridil4::pass<BOTH, QUIRK>(acc, reinterpret_cast<const double*>(ring + (size_t)src_lane * SLOT), sl, l, W);
+                gridil4::pass<BOTH, QUIRK>(acc, reinterpret_cast<const double*>(ring + (size_t)src_lane * SLOT), sl, l, L.frac, W);
             __syncwarp();                         // every lane is done with the slots before the next copies land
-        }
-        if (QUIRK) {
-            // corner layer cz = sl & 1: the two z-planes are held by lanes sl and sl ^ 2
-            double F[2][4][4];
-#pragma unroll
-            for (int ct = 0; ct < 2; ++ct)
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        if (c < NC) {
-                            const double other = __shfl_xor_sync(0xffffffffu, acc.T[ct][q][c], 2);
-                            F[ct][q][c] = gridil4::corner(acc.T[ct][q][c], other, sl);
-                        } else {
-                            F[ct][q][c] = 0.0;
-                        }
-                    }
-            double F11p[2][4];
-#pragma unroll
-            for (int ct = 0; ct < 2; ++ct)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) F11p[ct][c] = (c < NC) ? __shfl_xor_sync(0xffffffffu, F[ct][3][c], 1) : 0.0;
-            if (sl < 2 && L.ok) gridil4::quirk<BOTH>(acc, F, F11p, sl, L.frac);   // lanes 2, 3 hold copies of the same corners
         }
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
-            acc.v[i] += __shfl_xor_sync(0xffffffffu, acc.v[i], 1);
-            acc.v[i] += __shfl_xor_sync(0xffffffffu, acc.v[i], 2);
+            acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 1);
+            acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 2);
         }
         if (n < p.N && sl == 0) {
             const double nan = qnan();
 #pragma unroll
-            for (int c = 0; c < 3; ++c) p.out_comps[n * 3 + c] = L.ok ? acc.v[c] : nan;
+            for (int c = 0; c < 3; ++c) p.out_comps[n * 3 + c] = L.ok ? acc[c] : nan;
             if (BOTH) {
-                p.out_norm[n] = L.ok ? acc.v[3] : nan;
+                p.out_norm[n] = L.ok ? acc[3] : nan;
 #pragma unroll
-                for (int a = 0; a < D; ++a) p.out_grad[n * D + a] = L.ok ? __ddiv_rn(acc.v[4 + a], p.h[a]) : nan;
+                for (int a = 0; a < D; ++a) p.out_grad[n * D + a] = L.ok ? __ddiv_rn(acc[4 + a], p.h[a]) : nan;
             }
         }
     }
 }
 
-template <int MODE, bool QUIRK, bool DEDUP>
+template <int MODE, bool QUIRK, bool DEDUP, int MINB>
 static int launch_gridil4(const QueryParams& p, cudaStream_t st) {
     constexpr int THREADS = 128;
     const size_t smem = (size_t)(THREADS / 32) * 32 * 528;
-    auto k = query_gridil4_kernel<MODE, QUIRK, DEDUP, THREADS>;
+    auto k = query_gridil4_kernel<MODE, QUIRK, DEDUP, THREADS, MINB>;
     static int occ_cache[16] = {};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
@@ -151,13 +128,15 @@ static int launch_gridil4(const QueryParams& p, cudaStream_t st) {
 }
 
 // called by query_gridil_device (arb_query.cu) for d == 4; p is filled and checked there
-int query_gridil4_launch(const QueryParams& p, int mode, bool quirk, bool dedup, cudaStream_t st) {
-    if (mode == ARB_MODE_VECTOR) {
-        if (quirk) return dedup ? launch_gridil4<0, true, true>(p, st) : launch_gridil4<0, true, false>(p, st);
-        return dedup ? launch_gridil4<0, false, true>(p, st) : launch_gridil4<0, false, false>(p, st);
-    }
-    if (quirk) return dedup ? launch_gridil4<2, true, true>(p, st) : launch_gridil4<2, true, false>(p, st);
-    return dedup ? launch_gridil4<2, false, true>(p, st) : launch_gridil4<2, false, false>(p, st);
+template <int MODE, bool QUIRK>
+static int pick(const QueryParams& p, bool dedup, bool wide, cudaStream_t st) {
+    if (wide) return dedup ? launch_gridil4<MODE, QUIRK, true, 2>(p, st) : launch_gridil4<MODE, QUIRK, false, 2>(p, st);
+    return dedup ? launch_gridil4<MODE, QUIRK, true, 3>(p, st) : launch_gridil4<MODE, QUIRK, false, 3>(p, st);
+}
+
+int query_gridil4_launch(const QueryParams& p, int mode, bool quirk, bool dedup, bool wide, cudaStream_t st) {
+    if (mode == ARB_MODE_VECTOR) return quirk ? pick<0, true>(p, dedup, wide, st) : pick<0, false>(p, dedup, wide, st);
+    return quirk ? pick<2, true>(p, dedup, wide, st) : pick<2, false>(p, dedup, wide, st);
 }
 
 }  // namespace arb

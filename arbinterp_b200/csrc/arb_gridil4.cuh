@@ -5,14 +5,11 @@
 // Four lanes own a query, lane k = z-plane k of the 4^4 neighbourhood, and the four t-planes l = 0..3 are passes:
 // in pass l a lane holds the 4 x 4 (y, x) points of plane (k, l) with all components together (one 512-byte slot,
 // four 128-byte rows of the grid) and contracts them with the Catmull-Rom weights (A = M^(x)4 apart from the
-// A.py:860 term).  The quirk term needs fxyzt at the cell's 16 corners: every pass adds the plane's
-// signed xy parity sums into T[ct] with the t sign of that plane (l = ct: -, l = ct + 2: +); after the last pass
-// lane k and lane k ^ 2 hold the two z-planes of corner layer cz = k & 1, so one exchange gives
-// fxyzt(cx, cy, cz, ct) = (T_{z = cz + 2} - T_{z = cz}) / 16, and e[c] = fxyzt(c - 1) - fxyzt(c) in the reference's corner
-// order c = cx + 2 cy + 4 cz + 8 ct takes one more value from lane k ^ 1 (nodes::quirk4_lane does the rest).
+// A.py:860 term).  The A.py:860 term is folded into a second, rank-one-per-corner set of weights on
+// the same points (quirk_weights below), so a pass adds it from the plane's four signed xy parity sums and nothing is
+// carried between passes or exchanged between lanes; the four lanes' shares simply add up.
 #pragma once
 #include "arb_gridfree.cuh"
-#include "arb_nodes.cuh"
 
 namespace arb {
 namespace gridil4 {
@@ -29,89 +26,87 @@ ARB_HD int64_t plane_first_point(const int* idx, int k, int l, int64_t nx, int64
     return ((((int64_t)idx[3] + l) * nz + idx[2] + k) * ny + idx[1]) * nx + idx[0];
 }
 
-struct Weights {          // Catmull-Rom weights of the query's cell fractions, computed once per query
-    double wx[4], dwx[4], wy[4], dwy[4], wz[4], dwz[4], wt[4], dwt[4];
+struct Weights {          // Catmull-Rom weights of the query's x and y cell fractions, computed once per query
+    double wx[4], dwx[4], wy[4], dwy[4];
 };
 
 ARB_HD void make_weights(const double* f, Weights& W) {
     gridfree::catmull_rom(f[0], W.wx, W.dwx);
     gridfree::catmull_rom(f[1], W.wy, W.dwy);
-    gridfree::catmull_rom(f[2], W.wz, W.dwz);
-    gridfree::catmull_rom(f[3], W.wt, W.dwt);
 }
 
-struct Acc {
-    double v[8];          // this lane's share of: components 0..2, |B| 3, d|B|/du, dv, dw 4..6, d|B|/ds 7
-    double T[2][4][4];    // quirk: [ct][cx + 2 cy][component], parity sums over x, y and t of this lane's z-plane
-};
-
-template <bool QUIRK>
-ARB_HD void clear(Acc& A) {
-    ARB_UNROLL
-    for (int i = 0; i < 8; ++i) A.v[i] = 0.0;
-    if (QUIRK) {
-        ARB_UNROLL
-        for (int ct = 0; ct < 2; ++ct)
-            ARB_UNROLL
-            for (int q = 0; q < 4; ++q)
-                ARB_UNROLL
-                for (int c = 0; c < 4; ++c) A.T[ct][q][c] = 0.0;
-    }
+// The A.py:860 term as point weights.  The reference's matrix adds  sum_c Phi_c (F(c-1) - F(c))  to the M^(x)4 value,
+// c = cx + 2 cy + 4 cz + 8 ct the reference's corner order, F = fxyzt at the corner, F(-1) = 0, Phi_c = the product of the
+// four Hermite slope basis functions of corner c (arb_gridfree.cuh).  Summed by parts that is  sum_c F(c) G(c),
+// G(c) = Phi_(c+1) - Phi_c (Phi_16 = 0), and F(c) is the 1/16 (+-) sum over the 16 neighbourhood points whose index parity
+// per axis equals c's bits -- every point belongs to exactly one corner -- so the term is a second set of weights on the
+// same points:  sum_(i,j,k,l) f[l][k][j][i] s_i s_j s_k s_l G(i&1, j&1, k&1, l&1) / 16,  s = +1 for index >= 2, else -1.
+// For plane (k, l) that is the plane's four signed xy parity sums (gridfree::plane_il4) times the four numbers below;
+// nothing is carried between passes or lanes.  Derivatives: G is multilinear in the four slope vectors, so d/du replaces
+// hx by its derivative, and so on.
+// g[cx + 2 cy] for cz = k & 1, ct = l & 1, including the factor s_k s_l / 16.  X0, X1 / Y0, Y1 / Z, ZN / T, TN are the slope
+// basis values (or derivatives) of x, y at the two corners and of z, t at this corner layer and at the next one in the order
+// (cz, ct) = (0,0), (1,0), (0,1), (1,1) (ZN * TN = 0 after the last).
+ARB_HD void quirk_weights(double X0, double X1, double Y0, double Y1, double ZT, double ZTN, double sgn, double (&g)[4]) {
+    const double dx = X1 - X0;
+    g[0] = sgn * (dx * Y0 * ZT);                                  // Phi(1,0) - Phi(0,0)
+    g[1] = sgn * ((X0 * Y1 - X1 * Y0) * ZT);                      // Phi(0,1) - Phi(1,0)
+    g[2] = sgn * (dx * Y1 * ZT);                                  // Phi(1,1) - Phi(0,1)
+    g[3] = sgn * fma_(X0 * Y0, ZTN, -(X1 * Y1) * ZT);             // Phi(0,0 of the next layer) - Phi(1,1)
 }
 
-// pass l of lane k: slot = [j][i][c], plane (z = k, t = l) of the neighbourhood
+// pass l of lane k: slot = [j][i][c], plane (z = k, t = l) of the neighbourhood; v = this lane's share of: components
+// 0..2, |B| 3, d|B|/du, dv, dw 4..6, d|B|/ds 7
 template <bool BOTH, bool QUIRK>
-ARB_HD void pass(Acc& A, const double* slot, int k, int l, const Weights& W) {
+ARB_HD void pass(double (&v)[8], const double* slot, int k, int l, const double* frac, const Weights& W) {
     constexpr int NC = BOTH ? 4 : 3;
+    double wz[4], dwz[4], wt[4], dwt[4];
+    gridfree::catmull_rom(frac[2], wz, dwz);
+    gridfree::catmull_rom(frac[3], wt, dwt);
     double out[7], Pq[4][4];
-    gridfree::plane_il4<BOTH, QUIRK>(slot, sel4(W.wz, k), sel4(W.dwz, k), W.wx, W.dwx, W.wy, W.dwy, out, Pq);
-    const double w = sel4(W.wt, l), dw = sel4(W.dwt, l);
+    gridfree::plane_il4<BOTH, QUIRK>(slot, sel4(wz, k), sel4(dwz, k), W.wx, W.dwx, W.wy, W.dwy, out, Pq);
+    const double w = sel4(wt, l), dw = sel4(dwt, l);
     ARB_UNROLL
-    for (int c = 0; c < 3; ++c) A.v[c] = fma_(w, out[c], A.v[c]);
+    for (int c = 0; c < 3; ++c) v[c] = fma_(w, out[c], v[c]);
     if (BOTH) {
         ARB_UNROLL
-        for (int c = 3; c < 7; ++c) A.v[c] = fma_(w, out[c], A.v[c]);
-        A.v[7] = fma_(dw, out[3], A.v[7]);
+        for (int c = 3; c < 7; ++c) v[c] = fma_(w, out[c], v[c]);
+        v[7] = fma_(dw, out[3], v[7]);
     }
     if (QUIRK) {
-        const double s0 = (l == 0) ? -1.0 : ((l == 2) ? 1.0 : 0.0), s1 = (l == 1) ? -1.0 : ((l == 3) ? 1.0 : 0.0);
+        double hx[2], dhx[2], hy[2], dhy[2], hz[2], dhz[2], ht[2], dht[2];
+        gridfree::hermite_slope(frac[0], hx, dhx);
+        gridfree::hermite_slope(frac[1], hy, dhy);
+        gridfree::hermite_slope(frac[2], hz, dhz);
+        gridfree::hermite_slope(frac[3], ht, dht);
+        const int cz = k & 1, ct = l & 1;
+        const bool last = cz && ct;                    // corner layer (1, 1): nothing follows
+        const int czn = cz ^ 1, ctn = cz ? 1 : ct;     // (0,0) -> (1,0) -> (0,1) -> (1,1)
+        const double sgn = (((k >> 1) == (l >> 1)) ? 0.0625 : -0.0625);
+        const double z = cz ? hz[1] : hz[0], t = ct ? ht[1] : ht[0];
+        const double zn = last ? 0.0 : (czn ? hz[1] : hz[0]), tn = ctn ? ht[1] : ht[0];
+        double g[4];
+        quirk_weights(hx[0], hx[1], hy[0], hy[1], z * t, zn * tn, sgn, g);
         ARB_UNROLL
-        for (int q = 0; q < 4; ++q)
+        for (int c = 0; c < NC; ++c)
+            v[c] = fma_(Pq[3][c], g[3], fma_(Pq[2][c], g[2], fma_(Pq[1][c], g[1], fma_(Pq[0][c], g[0], v[c]))));
+        if (BOTH) {
+            const double dz = cz ? dhz[1] : dhz[0], dt = ct ? dht[1] : dht[0];
+            const double dzn = last ? 0.0 : (czn ? dhz[1] : dhz[0]), dtn = ctn ? dht[1] : dht[0];
+            double gu[4], gv[4], gw[4], gs[4];
+            quirk_weights(dhx[0], dhx[1], hy[0], hy[1], z * t, zn * tn, sgn, gu);
+            quirk_weights(hx[0], hx[1], dhy[0], dhy[1], z * t, zn * tn, sgn, gv);
+            quirk_weights(hx[0], hx[1], hy[0], hy[1], dz * t, dzn * tn, sgn, gw);
+            quirk_weights(hx[0], hx[1], hy[0], hy[1], z * dt, zn * dtn, sgn, gs);
             ARB_UNROLL
-            for (int c = 0; c < NC; ++c) {
-                A.T[0][q][c] = fma_(s0, Pq[q][c], A.T[0][q][c]);
-                A.T[1][q][c] = fma_(s1, Pq[q][c], A.T[1][q][c]);
-            }
-    }
-}
-
-// fxyzt at the corners (cx, cy, cz = k & 1, ct) from this lane's T and the T of lane k ^ 2
-ARB_HD double corner(double own, double other, int k) {
-    return 0.0625 * ((k >= 2) ? (own - other) : (other - own));
-}
-
-// A.py:860 term of lane k < 2 (corner layer cz = k): F[ct][cx + 2 cy][c] = fxyzt at its corners, F11p[ct][c] = fxyzt of
-// corner (1, 1) of lane k ^ 1 (the corner before this lane's (0, 0) in the reference's order, see the header)
-template <bool BOTH>
-ARB_HD void quirk(Acc& A, const double (&F)[2][4][4], const double (&F11p)[2][4], int k, const double* frac) {
-    constexpr int NC = BOTH ? 4 : 3;
-    const int cz = k & 1;
-    ARB_UNROLL
-    for (int ct = 0; ct < 2; ++ct)
-        ARB_UNROLL
-        for (int c = 0; c < NC; ++c) {
-            const double f15[4] = {F[ct][0][c], F[ct][1][c], F[ct][2][c], F[ct][3][c]};
-            const double prev = (ct == 0) ? (cz ? F11p[0][c] : 0.0) : (cz ? F11p[1][c] : F11p[0][c]);
-            if (BOTH && c == 3) {
-                double g[5] = {A.v[3], A.v[4], A.v[5], A.v[6], A.v[7]};
-                nodes::quirk4_lane<true>(f15, prev, cz, ct, frac, g);
-                A.v[3] = g[0]; A.v[4] = g[1]; A.v[5] = g[2]; A.v[6] = g[3]; A.v[7] = g[4];
-            } else {
-                double g[1] = {A.v[c]};
-                nodes::quirk4_lane<false>(f15, prev, cz, ct, frac, g);
-                A.v[c] = g[0];
+            for (int q = 0; q < 4; ++q) {
+                v[4] = fma_(Pq[q][3], gu[q], v[4]);
+                v[5] = fma_(Pq[q][3], gv[q], v[5]);
+                v[6] = fma_(Pq[q][3], gw[q], v[6]);
+                v[7] = fma_(Pq[q][3], gs[q], v[7]);
             }
         }
+    }
 }
 
 }  // namespace gridil4

@@ -403,15 +403,15 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
                 const uint32_t src16 = (uint32_t)((reinterpret_cast<const char*>(src) - reinterpret_cast<const char*>(p.table)) >> USH);
                 const char* const lane_base = reinterpret_cast<const char*>(p.table) + lane_src;
                 const uint32_t ring0 = smem_u32(ring) + lane * 16;
-                // interleaved nodes in mode 'vector': the |B| block of each node (bytes 192..255 of its 256) is never
-                // read, so the four lanes that would copy it stay idle -- a quarter of the bytes is not moved at all
-                const bool lane_copies = !(KIND == KIND_NODES_IL && MODE == 0 && (lane & 12) == 12);
+                // (interleaved nodes in mode 'vector': leaving the lanes idle that copy the unread |B| block of each node
+                // was measured -- DRAM still moves whole 128-byte lines, 2065 bytes per query either way,
+                // profiles/r02_nodes3d_vector_ncu.txt -- and dropped)
 #pragma unroll 8
                 for (int o = 0; o < 32; ++o) {
                     if ((fmask >> o) & 1u) {
                         const uint32_t s16 = __shfl_sync(0xffffffffu, src16, o);
                         const uint32_t slot_o = (SLOTS == 32) ? (uint32_t)o : (uint32_t)__shfl_sync(0xffffffffu, myslot, o);
-                        if (lane_copies) cp_async_16(ring0 + slot_o * SLOT, lane_base + ((size_t)s16 << USH));
+                        cp_async_16(ring0 + slot_o * SLOT, lane_base + ((size_t)s16 << USH));
                     }
                 }
             } else {
@@ -1077,7 +1077,7 @@ static int dispatch_nodes(const QueryParams& p, cudaStream_t st, int variant, bo
 
 // Table-free 'vector' / 'both' on the component-interleaved grid [nt][nz][ny][nx][4] (Bx, By, Bz, |B| or 0); the 4-D
 // kernel lives in arb_gridil4.cu.
-int query_gridil4_launch(const QueryParams& p, int mode, bool quirk, bool dedup, cudaStream_t st);
+int query_gridil4_launch(const QueryParams& p, int mode, bool quirk, bool dedup, bool wide, cudaStream_t st);
 
 int query_gridil_device(const arb_geom* g, const double* packed, int mode, double* q, int64_t N, int64_t ldq,
                         double* out_comps, double* out_norm, double* out_grad, int64_t* out_cell, int64_t* masked_rows,
@@ -1096,7 +1096,7 @@ int query_gridil_device(const arb_geom* g, const double* packed, int mode, doubl
         return 1;
     }
     const int v = current_query_variant();
-    if (g->d == 4) return query_gridil4_launch(p, mode, !(g->flags & ARB_GEOM_FIXED_D4), v != 73 && v != 20, st);
+    if (g->d == 4) return query_gridil4_launch(p, mode, !(g->flags & ARB_GEOM_FIXED_D4), v != 73 && v != 20, v == 81, st);
     if (mode == ARB_MODE_VECTOR) {
         if (v == 73) return launch_block<3, 0, 128, false, true, 32, true, true, KIND_GRID_IL>(p, st);
         return launch_block<3, 0, 128, true, true, 32, true, true, KIND_GRID_IL>(p, st);

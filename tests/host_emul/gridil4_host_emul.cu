@@ -1,7 +1,6 @@
 // CPU emulation of the 4-D table-free query math on the component-interleaved grid (test infrastructure): the
 // __host__ __device__ pieces of arbinterp_b200/csrc/arb_gridil4.cuh are combined exactly as query_gridil4_kernel
-// combines them -- four "lanes" (z-planes) per query, four passes (t-planes), the two exchanges of the quirk term
-// done by array reads instead of shuffles -- and compared, component by component, with sum_m alpha_m u^i v^j w^k s^l,
+// combines them -- four "lanes" (z-planes) per query, four passes (t-planes), the lanes' shares added up -- and compared, component by component, with sum_m alpha_m u^i v^j w^k s^l,
 // alpha = A f, A = inv(B) D from arb_core.cu (A.py:726-878) with and without the A.py:860 quirk.
 // Exit code 1 above 1e-12 scaled error.
 #include <cmath>
@@ -57,10 +56,9 @@ static double run(int64_t nx, int64_t ny, int64_t nz, int64_t nt, int nq, uint64
         // ---- the kernel's way
         Weights W;
         make_weights(fr, W);
-        Acc acc[4];
+        double acc[4][8];
         for (int k = 0; k < 4; ++k) {
-            clear<QUIRK>(acc[k]);
-            if (!QUIRK) memset(acc[k].T, 0, sizeof(acc[k].T));
+            for (int i = 0; i < 8; ++i) acc[k][i] = 0.0;
             for (int l = 0; l < 4; ++l) {
                 // the kernel's gather: 32 "lanes" bring 16 bytes each, addressed by the kernel's own helpers
                 alignas(16) double slot[64];
@@ -72,25 +70,12 @@ static double run(int64_t nx, int64_t ny, int64_t nz, int64_t nt, int nq, uint64
                 for (int j = 0; j < 4; ++j)
                     for (int i = 0; i < 4; ++i)
                         if (memcmp(slot + (j * 4 + i) * 4, at(ix + i, iy + j, iz + k, it + l), 4 * sizeof(double)) != 0) return 1.0;
-                pass<BOTH, QUIRK>(acc[k], slot, k, l, W);
-            }
-        }
-        if (QUIRK) {
-            double F[4][2][4][4];
-            for (int k = 0; k < 4; ++k)
-                for (int ct = 0; ct < 2; ++ct)
-                    for (int q = 0; q < 4; ++q)
-                        for (int c = 0; c < 4; ++c) F[k][ct][q][c] = corner(acc[k].T[ct][q][c], acc[k ^ 2].T[ct][q][c], k);
-            for (int k = 0; k < 2; ++k) {
-                double F11p[2][4];
-                for (int ct = 0; ct < 2; ++ct)
-                    for (int c = 0; c < 4; ++c) F11p[ct][c] = F[k ^ 1][ct][3][c];
-                quirk<BOTH>(acc[k], F[k], F11p, k, fr);
+                pass<BOTH, QUIRK>(acc[k], slot, k, l, fr, W);
             }
         }
         double got[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int k = 0; k < 4; ++k)
-            for (int i = 0; i < 8; ++i) got[i] += acc[k].v[i];
+            for (int i = 0; i < 8; ++i) got[i] += acc[k][i];
         for (int c = 0; c < 3; ++c) {
             const double err = std::fabs(got[c] - ref[c][0]) / std::fmax(mag[c][0], 1.0);
             if (!(err <= worst)) worst = err;

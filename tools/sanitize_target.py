@@ -77,4 +77,9 @@ for cls, f, d in ((tricubic, f3, 3), (quadcubic, f4, 4)):
         for part in parts:
             part._push_local(p, v, step, 0.02, 12, -0.5, (0.0, 0.0, 0.2))
     whole.push(p.clone(), v.clone(), 0.02, 5, -0.5)
+    # push on node tables: one component, 3-D interleaved ('both'), 4-D with and without the A.py:860 term
+    cls(f[:, :d + 1].copy(), "quiet", table="nodes").push(p.clone(), v.clone(), 0.02, 5, -0.5)
+    cls(f, "quiet", mode="both", table="nodes").push(p.clone(), v.clone(), 0.02, 5, -0.5)
+    if d == 4:
+        cls(f, "quiet", mode="both", table="nodes", fixed_d4=True).push(p.clone(), v.clone(), 0.02, 5, -0.5)
 print("sanitize target done")

@@ -57,13 +57,17 @@ for shape, nq in cases:
         forms = [("planes + TMA boxes", dict(table=False, interleave=False))]
         if mode != "norm":
             forms.append(("interleaved grid", dict(table=False, interleave=True)))
+            if d == 4:
+                forms.append(("interleaved grid, variant 81 (2 CTAs/SM, ~250 registers)", dict(table=False, interleave=True)))
         forms.append(("node table", dict(table="nodes")))
         for name, kw in forms:
             obj = cls(rows, "quiet", mode=mode, **kw)
+            obj._lib.arb_set_query_variant(81 if "variant 81" in name else 0)
             mem = (obj._nodes if obj._nodes is not None else obj._packed if obj._packed is not None else obj._planes).numel() * 8 / 1e9
             line = [f"{k}: {rate(obj, qq):.3e} q/s (x{rate(obj, qq) / base[k]:.2f} of the cell table)"
                     for k, qq in (("uniform random", q), ("cell-sorted", qs))]
             print(f"[tablefree] {grid} {mode} {name} ({mem:.3f} GB vs {tgb:.2f} GB of cell table): " + " | ".join(line), flush=True)
+            obj._lib.arb_set_query_variant(0)
             obj.release()
             del obj
             torch.cuda.empty_cache()
