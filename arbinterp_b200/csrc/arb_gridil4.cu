@@ -15,8 +15,9 @@
 
 namespace arb {
 
-// MINB = 3: the compiler keeps to 168 registers so that three CTAs are resident per SM (the 'both' + quirk form spills
-// ~190 bytes for it); MINB = 2 (query variant 81) lets it take ~250 and two CTAs -- measured in tools/tablefree_bench.py
+// MINB = 3: the compiler keeps to 168 registers so that three CTAs are resident per SM -- 'vector' 0.96 of the cell table
+// against 0.79 with two CTAs; the 'both' + quirk form spills ~190 bytes for it and is better off with MINB = 2 (~250
+// registers, 0.94 against 0.71; profiles/r02_tablefree_bench_4d.log).  The launcher in arb_query.cu picks.
 template <int MODE, bool QUIRK, bool DEDUP, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) query_gridil4_kernel(const QueryParams p) {
     static_assert(MODE == 0 || MODE == 2, "interleaved grid: 'vector' / 'both'");

@@ -1096,7 +1096,13 @@ int query_gridil_device(const arb_geom* g, const double* packed, int mode, doubl
         return 1;
     }
     const int v = current_query_variant();
-    if (g->d == 4) return query_gridil4_launch(p, mode, !(g->flags & ARB_GEOM_FIXED_D4), v != 73 && v != 20, v == 81, st);
+    if (g->d == 4) {
+        // 'both' with the A.py:860 term needs ~250 registers: two CTAs per SM without spills beat three with them (0.94
+        // against 0.71 of the cell table); every other form fits 168 and runs three (variant 81 / 82 force either)
+        const bool quirk = !(g->flags & ARB_GEOM_FIXED_D4);
+        const bool wide = (v == 81) || (v != 82 && quirk && mode == ARB_MODE_BOTH);
+        return query_gridil4_launch(p, mode, quirk, v != 73 && v != 20, wide, st);
+    }
     if (mode == ARB_MODE_VECTOR) {
         if (v == 73) return launch_block<3, 0, 128, false, true, 32, true, true, KIND_GRID_IL>(p, st);
         return launch_block<3, 0, 128, true, true, 32, true, true, KIND_GRID_IL>(p, st);

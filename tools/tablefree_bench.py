@@ -58,11 +58,12 @@ for shape, nq in cases:
         if mode != "norm":
             forms.append(("interleaved grid", dict(table=False, interleave=True)))
             if d == 4:
-                forms.append(("interleaved grid, variant 81 (2 CTAs/SM, ~250 registers)", dict(table=False, interleave=True)))
+                forms.append(("interleaved grid, variant 81 (forced: 2 CTAs/SM, ~250 registers)", dict(table=False, interleave=True)))
+                forms.append(("interleaved grid, variant 82 (forced: 3 CTAs/SM, 168 registers)", dict(table=False, interleave=True)))
         forms.append(("node table", dict(table="nodes")))
         for name, kw in forms:
             obj = cls(rows, "quiet", mode=mode, **kw)
-            obj._lib.arb_set_query_variant(81 if "variant 81" in name else 0)
+            obj._lib.arb_set_query_variant(81 if "variant 81" in name else (82 if "variant 82" in name else 0))
             mem = (obj._nodes if obj._nodes is not None else obj._packed if obj._packed is not None else obj._planes).numel() * 8 / 1e9
             line = [f"{k}: {rate(obj, qq):.3e} q/s (x{rate(obj, qq) / base[k]:.2f} of the cell table)"
                     for k, qq in (("uniform random", q), ("cell-sorted", qs))]
