@@ -55,6 +55,10 @@ ARB_HD void quirk_weights(double X0, double X1, double Y0, double Y1, double ZT,
     g[3] = sgn * fma_(X0 * Y0, ZTN, -(X1 * Y1) * ZT);             // Phi(0,0 of the next layer) - Phi(1,1)
 }
 
+ARB_HD double quirk_dot_a(double X0, double X1, double Y0, double Y1, double P0, double P1, double P2, double P3) {
+    return fma_(X1 - X0, fma_(Y1, P2, Y0 * P0), fma_(fma_(X0, Y1, -(X1 * Y0)), P1, -(X1 * Y1) * P3));
+}
+
 // pass l of lane k: slot = [j][i][c], plane (z = k, t = l) of the neighbourhood; v = this lane's share of: components
 // 0..2, |B| 3, d|B|/du, dv, dw 4..6, d|B|/ds 7
 template <bool BOTH, bool QUIRK>
@@ -91,20 +95,19 @@ ARB_HD void pass(double (&v)[8], const double* slot, int k, int l, const double*
         for (int c = 0; c < NC; ++c)
             v[c] = fma_(Pq[3][c], g[3], fma_(Pq[2][c], g[2], fma_(Pq[1][c], g[1], fma_(Pq[0][c], g[0], v[c]))));
         if (BOTH) {
+            // |B| gradient: the dot of the parity sums with quirk_weights(X, Y, ZT, ZTN) is ZT * A(X, Y) + ZTN * B(X, Y),
+            // A = (X1 - X0)(Y0 P0 + Y1 P2) + (X0 Y1 - X1 Y0) P1 - X1 Y1 P3,  B = X0 Y0 P3; a derivative replaces one vector
             const double dz = cz ? dhz[1] : dhz[0], dt = ct ? dht[1] : dht[0];
             const double dzn = last ? 0.0 : (czn ? dhz[1] : dhz[0]), dtn = ctn ? dht[1] : dht[0];
-            double gu[4], gv[4], gw[4], gs[4];
-            quirk_weights(dhx[0], dhx[1], hy[0], hy[1], z * t, zn * tn, sgn, gu);
-            quirk_weights(hx[0], hx[1], dhy[0], dhy[1], z * t, zn * tn, sgn, gv);
-            quirk_weights(hx[0], hx[1], hy[0], hy[1], dz * t, dzn * tn, sgn, gw);
-            quirk_weights(hx[0], hx[1], hy[0], hy[1], z * dt, zn * dtn, sgn, gs);
-            ARB_UNROLL
-            for (int q = 0; q < 4; ++q) {
-                v[4] = fma_(Pq[q][3], gu[q], v[4]);
-                v[5] = fma_(Pq[q][3], gv[q], v[5]);
-                v[6] = fma_(Pq[q][3], gw[q], v[6]);
-                v[7] = fma_(Pq[q][3], gs[q], v[7]);
-            }
+            const double P0 = Pq[0][3], P1 = Pq[1][3], P2 = Pq[2][3], P3 = Pq[3][3];
+            const double A = quirk_dot_a(hx[0], hx[1], hy[0], hy[1], P0, P1, P2, P3), B = hx[0] * hy[0] * P3;
+            const double Au = quirk_dot_a(dhx[0], dhx[1], hy[0], hy[1], P0, P1, P2, P3), Bu = dhx[0] * hy[0] * P3;
+            const double Av = quirk_dot_a(hx[0], hx[1], dhy[0], dhy[1], P0, P1, P2, P3), Bv = hx[0] * dhy[0] * P3;
+            const double zt = sgn * (z * t), ztn = sgn * (zn * tn);
+            v[4] = fma_(ztn, Bu, fma_(zt, Au, v[4]));
+            v[5] = fma_(ztn, Bv, fma_(zt, Av, v[5]));
+            v[6] = fma_(sgn * (dzn * tn), B, fma_(sgn * (dz * t), A, v[6]));
+            v[7] = fma_(sgn * (zn * dtn), B, fma_(sgn * (z * dt), A, v[7]));
         }
     }
 }
