@@ -189,11 +189,7 @@ ARB_HD void plane_il4(const double* slot, double wzk, double dwzk, const double 
             ARB_UNROLL
             for (int c = 0; c < 4; ++c) Pq[q][c] = 0.0;
     }
-#if defined(__CUDA_ARCH__) && defined(ARB_IL4_ROLL_J)
-#pragma unroll 1
-#else
     ARB_UNROLL
-#endif
     for (int j = 0; j < 4; ++j) {
         double pp[4] = {0.0, 0.0, 0.0, 0.0}, dp = 0.0;
         ARB_UNROLL
