@@ -18,7 +18,7 @@ EXPORTED_SYMBOLS = (
     "arb_version", "arb_last_error", "arb_get_matrix",
     "arb_build_coeffs", "arb_build_coeffs_3d", "arb_build_coeffs_4d",
     "arb_query", "arb_query_host", "arb_query_grid", "arb_query_grid_host",
-    "arb_build_nodes", "arb_query_nodes", "arb_query_nodes_host", "arb_query_gridil", "arb_query_gridil_host", "arb_query_routed", "arb_enable_peer_access", "arb_owner_keys",
+    "arb_build_nodes", "arb_query_nodes", "arb_query_nodes_host", "arb_query_gridil", "arb_query_gridil_host", "arb_query_routed", "arb_enable_peer_access", "arb_owner_keys", "arb_route_rows", "arb_query_inbox",
     "arb_push", "arb_push_steps", "arb_push_nodes", "arb_permute_rows", "arb_set_query_variant", "arb_set_build_variant",
 )
 
@@ -93,6 +93,11 @@ def load():
     lib.arb_query_gridil_host.argtypes = lib.arb_query_host.argtypes
     lib.arb_query_routed.restype = i32
     lib.arb_query_routed.argtypes = [ctypes.POINTER(ArbGeom), vp, i32, vp, i64, i64, vp, vp, ctypes.POINTER(vp), i32, i64, vp]
+    lib.arb_route_rows.restype = i32
+    lib.arb_route_rows.argtypes = [ctypes.POINTER(ArbGeom), vp, i64, i64, vp, i32, i32, ctypes.POINTER(vp), ctypes.POINTER(vp),
+                                   i64, vp, vp, vp, vp]
+    lib.arb_query_inbox.restype = i32
+    lib.arb_query_inbox.argtypes = [ctypes.POINTER(ArbGeom), vp, i32, vp, vp, i64, ctypes.POINTER(vp), i32, i64, vp]
     lib.arb_owner_keys.restype = i32
     lib.arb_owner_keys.argtypes = [ctypes.POINTER(ArbGeom), vp, i64, i64, vp, i32, vp, vp, vp]
     lib.arb_enable_peer_access.restype = i32

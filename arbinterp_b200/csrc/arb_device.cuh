@@ -31,6 +31,10 @@ struct QueryParams {
     const int64_t* home_row;
     double* peer[ARB_MAX_PEERS];
     int64_t peer_ld;
+    // inbox form (arb_query_inbox): q is this rank's inbox, npeers segments of seg_cap rows [coords | home row], segment h
+    // filled by rank h's route kernel (arb_route.cu) with inbox_counts[h] rows (device memory: no host round trip)
+    const int64_t* inbox_counts;
+    int64_t seg_cap;
 };
 
 // --------------------------------------------------------------------------------------

@@ -310,7 +310,16 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
     const int64_t nbatch = (p.N + QPW - 1) / QPW;
     // LOOPC: a work item is a batch and its components are fetched one after the other (one locate per
     // query); otherwise (batch, component) pairs are separate items (more independent items in flight).
-    const int64_t nitem = LOOPC ? nbatch : nbatch * C;
+    int64_t nitem = LOOPC ? nbatch : nbatch * C;
+    // inbox form: the rows sit in npeers segments of seg_cap rows, inbox_counts[h] of them filled; items are numbered
+    // over the filled parts only (a segment's last item may be partly empty)
+    int64_t seg_item0[ROUTED ? ARB_MAX_PEERS + 1 : 1];
+    const bool inbox = ROUTED && p.inbox_counts != nullptr;
+    if (ROUTED && inbox) {
+        seg_item0[0] = 0;
+        for (int h = 0; h < p.npeers; ++h) seg_item0[ROUTED ? h + 1 : 0] = seg_item0[ROUTED ? h : 0] + (p.inbox_counts[h] + QPW - 1) / QPW;
+        nitem = seg_item0[ROUTED ? p.npeers : 0];
+    }
     uint32_t phase = 0;
     double cnext[D];
     if (PREFETCH) {
@@ -320,7 +329,13 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
     }
     for (int64_t item = warp_global; item < nitem; item += nwarps) {
         const int64_t batch = LOOPC ? item : item / C;
-        const int64_t n = batch * QPW + qi;
+        int64_t n = batch * QPW + qi;
+        int seg = 0;
+        if (ROUTED && inbox) {                       // item -> (segment, row of the segment); rows past the count: n = N
+            for (int h = 1; h < p.npeers; ++h) seg = (item >= seg_item0[ROUTED ? h : 0]) ? h : seg;
+            const int64_t nl = (item - seg_item0[ROUTED ? seg : 0]) * QPW + qi;
+            n = (nl < p.inbox_counts[seg]) ? seg * p.seg_cap + nl : p.N;
+        }
         Located<D> L;
         L.ok = false; L.masked = false; L.cell_global = 0; L.cell_local = 0;
         if (PREFETCH) {
@@ -367,7 +382,7 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
         if (comp == 0 && sl == 0 && n < p.N) {
             if (ROUTED) rowv[ROUTED ? OFFC : 0] = __longlong_as_double(L.cell_global);
             else if (o_cell) *o_cell = L.cell_global;
-            if (L.masked) mask_row_in_place(p, n);
+            if (L.masked && !ROUTED) mask_row_in_place(p, n);      // routed rows are copies: the home rank masks the caller's
         }
         const bool grad_comp = (MODE == 1) || (MODE == 2 && (QUAD || comp == 3));     // warp-uniform
         double g[QUAD ? 7 : 5];
@@ -533,9 +548,14 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
         }
         unsigned long long dst = 0;
         if (n < p.N) {
-            int h = 0;
-            for (int r = 1; r < p.npeers; ++r) h = (n >= p.seg_start[r]) ? r : h;
-            dst = reinterpret_cast<unsigned long long>(p.peer[h] + p.home_row[n] * LDS);
+            if (inbox) {                             // the home row number travelled with the row
+                const int64_t home = __double_as_longlong(p.q[n * p.ldq + D]);
+                dst = reinterpret_cast<unsigned long long>(p.peer[seg] + home * LDS);
+            } else {
+                int h = 0;
+                for (int r = 1; r < p.npeers; ++r) h = (n >= p.seg_start[r]) ? r : h;
+                dst = reinterpret_cast<unsigned long long>(p.peer[h] + p.home_row[n] * LDS);
+            }
         }
         __syncwarp();
         constexpr int CPR = LDS / 2, NCH = QPW * CPR;
@@ -1170,6 +1190,44 @@ int query_routed_device(const arb_geom* g, const double* table, int mode, double
     return launch_block<4, 2, 128, true, true, 32, false, false, KIND_CELLS, true, true>(p, st);
 }
 
+// Inbox form of the routed query (both legs of a slab-sharded query fused into kernels): the rows were written into
+// this rank's inbox by the senders' route kernels (arb_route_rows), their counts are in device memory.
+int query_inbox_device(const arb_geom* g, const double* table, int mode, double* inbox, const int64_t* inbox_counts,
+                       int64_t seg_cap, double* const* peers, int npeers, int64_t ld, cudaStream_t st) {
+    if (!g || npeers < 1 || npeers > ARB_MAX_PEERS || seg_cap < 1 || !inbox || !inbox_counts || !peers) {
+        set_error("arb_query_inbox: bad arguments (npeers=%d seg_cap=%lld)", npeers, (long long)seg_cap);
+        return 1;
+    }
+    QueryParams p;
+    const int d = g->d;
+    const int64_t ld_in = (d + 2) / 2 * 2;
+    const int rc = fill_params("arb_query_inbox", g, true, table, mode, inbox, (int64_t)npeers * seg_cap, ld_in, nullptr, nullptr,
+                               nullptr, nullptr, nullptr, nullptr, p, false);
+    if (rc) return rc < 0 ? 0 : rc;
+    const int ncomp_out = (mode == ARB_MODE_NORM) ? 0 : 3, ngrad = (mode == ARB_MODE_VECTOR) ? 0 : 1 + d;
+    const int64_t want_ld = (ncomp_out + ngrad + 2) / 2 * 2;
+    if (ld != want_ld || (reinterpret_cast<uintptr_t>(inbox) & 15)) {
+        set_error("arb_query_inbox: need ld == %lld and a 16-byte aligned inbox (ld=%lld)", (long long)want_ld, (long long)ld);
+        return 1;
+    }
+    p.npeers = npeers;
+    for (int r = 0; r < npeers; ++r) {
+        if (!peers[r] || (reinterpret_cast<uintptr_t>(peers[r]) & 15)) { set_error("arb_query_inbox: peers[%d] is null or not 16-byte aligned", r); return 1; }
+        p.peer[r] = peers[r];
+    }
+    p.peer_ld = ld;
+    p.inbox_counts = inbox_counts;
+    p.seg_cap = seg_cap;
+    if (d == 3) {
+        if (mode == ARB_MODE_VECTOR) return launch_block<3, 0, 128, true, true, 32, false, false, KIND_CELLS, true, true>(p, st);
+        if (mode == ARB_MODE_NORM) return launch_block<3, 1, 128, true, true, 32, false, false, KIND_CELLS, true, true>(p, st);
+        return launch_block<3, 2, 128, true, true, 32, false, false, KIND_CELLS, true, true>(p, st);
+    }
+    if (mode == ARB_MODE_VECTOR) return launch_block<4, 0, 128, true, true, 32, false, false, KIND_CELLS, true, true>(p, st);
+    if (mode == ARB_MODE_NORM) return launch_block<4, 1, 128, true, true, 32, false, false, KIND_CELLS, true, true>(p, st);
+    return launch_block<4, 2, 128, true, true, 32, false, false, KIND_CELLS, true, true>(p, st);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1285,6 +1343,11 @@ int arb_query_routed(const arb_geom* g, const double* table, int mode, double* q
                      void* stream) {
     return arb::query_routed_device(g, table, mode, q, N, ldq, seg_start, home_row, peers, npeers, ld,
                                     (cudaStream_t)stream);
+}
+
+int arb_query_inbox(const arb_geom* g, const double* table, int mode, double* inbox, const int64_t* inbox_counts,
+                    int64_t seg_cap, double* const* peers, int npeers, int64_t ld, void* stream) {
+    return arb::query_inbox_device(g, table, mode, inbox, inbox_counts, seg_cap, peers, npeers, ld, (cudaStream_t)stream);
 }
 
 int arb_query_gridil(const arb_geom* g, const double* packed, int mode, double* q, int64_t N, int64_t ldq,

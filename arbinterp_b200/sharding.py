@@ -335,6 +335,7 @@ class SlabShardedInterp:
         # it on CUDA + NCCL and falls back to the all-to-all return when the peer mapping is not available
         self.fused = kwargs_fused
         self._peer = None
+        self._inbox = None
         self._peer_error = None
 
     def Query(self, q, timing: Optional[dict] = None):
@@ -367,7 +368,15 @@ class SlabShardedInterp:
 
         mark("start")
         g = self.local._geo
-        if coords.is_cuda and self.world <= 16:
+        widths = {"vector": (3,), "norm": (1, d), "both": (3, 1, d)}[mode]
+        flat = outside = None
+        if self.fused in ("both", "auto") and coords.is_cuda and self.world <= 16:
+            got = self._query_both_legs(coords, sum(widths) + 1, mark)      # None: peer mapping unavailable
+            if got is not None:
+                flat, outside = got
+        if flat is not None:
+            pass
+        elif coords.is_cuda and self.world <= 16:
             # one kernel for both (arb_owner_keys): owner rank of every row and the out-of-volume mask
             import ctypes
             from . import _lib
@@ -384,8 +393,8 @@ class SlabShardedInterp:
             hi = torch.tensor(g.int_max, dtype=torch.float64, device=dev)
             outside = ((coords < lo) | (coords > hi)).any(dim=1)                # A.py:1069-1076
             owner = owner_ranks(coords[:, d - 1], *self._slow, self.slabs)
-        mark("owner")
-        widths = {"vector": (3,), "norm": (1, d), "both": (3, 1, d)}[mode]
+        if flat is None:
+            mark("owner")
 
         def evaluate(rows):
             res = self.local.Query(rows)
@@ -393,8 +402,7 @@ class SlabShardedInterp:
             cells = self.local._last_cells.view(torch.float64).unsqueeze(1)     # int64 bits ride along exactly
             return torch.cat(list(res) + [cells], dim=1)
 
-        flat = None
-        if self.fused and self.world <= 16:
+        if flat is None and self.fused and self.world <= 16:
             flat = self._query_fused(coords, owner, sum(widths) + 1, mark)
         if flat is None:
             flat = exchange_and_query(coords, owner, evaluate, sum(widths) + 1, self.group, mark)
@@ -418,6 +426,73 @@ class SlabShardedInterp:
             timing["total_ms"] = timing.get("total_ms", 0.0) + ev[0][1].elapsed_time(ev[-1][1])
         return outs[0] if len(outs) == 1 else tuple(outs)
 
+    def _ensure_peer_buffers(self, n, ld, inbox: bool):
+        """(Re)map, collectively, the buffers the fused legs store into: every rank's result buffer (its own batch, ``ld``
+        doubles per row) and -- for the fused forward leg -- its inbox (``world`` segments of ``cap`` rows) and the
+        per-sender row counts.  Returns False when no peer mapping works (remembered: the group falls back together)."""
+        import torch.distributed as dist
+        loc = self.local
+        dev = loc._device
+        if self._peer_error is not None or dev.type != "cuda" or dist.get_backend(self.group) != "nccl":
+            return False
+        need = torch.tensor([n], dtype=torch.int64, device=dev)
+        dist.all_reduce(need, op=dist.ReduceOp.MAX, group=self.group)
+        need = int(need.item())
+        try:
+            if self._peer is None or self._peer.rows < need or self._peer.ld != ld:
+                self._peer = PeerResults(loc._lib, dev, self.group, max(need, 1) * 5 // 4 + 1024, ld)
+                self._inbox = None
+            if inbox and getattr(self, "_inbox", None) is None:
+                cap = self._peer.rows
+                ld_in = (self.d + 2) // 2 * 2
+                self._inbox = PeerResults(loc._lib, dev, self.group, self.world * cap, ld_in)
+                self._counts = PeerResults(loc._lib, dev, self.group, 1, 16)          # int64 [world] behind a float64 row
+                self._cursor = torch.zeros(self.world + 2, dtype=torch.int64, device=dev)   # [world] cursors + the ticket
+                self._inbox_cap = cap
+        except Exception as e:                                   # noqa: BLE001 -- remembered: the group falls back together
+            self._peer, self._inbox, self._peer_error = None, None, f"{type(e).__name__}: {e}"
+            if self.fused in (True, "both"):
+                raise
+            return False
+        return True
+
+    def _query_both_legs(self, coords, ld, mark):
+        """Both legs of a routed query inside kernels, no NCCL all-to-all and no host round trip: ``arb_route_rows`` stores
+        every row, with its row number here, into the inbox of the rank that owns its slab (peer memory over NVLink; the
+        owner and the out-of-volume mask come out of the same kernel), a barrier, ``arb_query_inbox`` on the owner evaluates
+        its inbox -- the per-sender counts are read on the device -- and stores every row's outputs into the home rank's
+        result buffer at its home row, a barrier.  Returns ``(result rows (n, ld), outside mask)`` or None when the peer
+        mapping is unavailable."""
+        import ctypes
+        import torch.distributed as dist
+        from . import _lib
+        loc = self.local
+        dev = loc._device
+        d, n, world = self.d, coords.shape[0], self.world
+        ld = (ld + 1) // 2 * 2
+        if not self._ensure_peer_buffers(n, ld, inbox=True):
+            return None
+        peer, inbox, counts = self._peer, self._inbox, self._counts
+        outside = torch.empty(n, dtype=torch.bool, device=dev)
+        his = (ctypes.c_int64 * world)(*[s_[1] for s_ in self.slabs])
+        self._cursor.zero_()
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(loc._lib.arb_route_rows(ctypes.byref(loc._cgeom), coords.data_ptr(), n, coords.shape[1], his, world,
+                                               self.rank, inbox.cptrs, counts.cptrs, self._inbox_cap,
+                                               self._cursor.data_ptr(), self._cursor[world + 1:].data_ptr(),
+                                               outside.data_ptr(), stream), "arb_route_rows")
+            mark("owner")
+            dist.barrier(group=self.group)      # every rank's rows and counts have landed in the inboxes
+            mark("alltoall")
+            _lib.check(loc._lib.arb_query_inbox(ctypes.byref(loc._cgeom), loc.table.data_ptr(), loc._mode_code,
+                                                inbox.buf.data_ptr(), counts.buf.data_ptr(), self._inbox_cap, peer.cptrs,
+                                                world, peer.ld, stream), "arb_query_inbox")
+            mark("kernel")
+            dist.barrier(group=self.group)      # every rank's kernel has finished: all rows of this batch have landed
+            mark("alltoall_back")
+        return peer.buf[:n], outside
+
     def _query_fused(self, coords, owner, ld, mark):
         """Rows travel to their owner with their home row number; the owner's kernel (``arb_query_routed``) stores every
         row's outputs into the home rank's result buffer at that row -- peer memory over NVLink, each result row as
@@ -429,22 +504,10 @@ class SlabShardedInterp:
         from . import _lib
         loc = self.local
         dev = loc._device
-        if self._peer_error is not None or dev.type != "cuda" or dist.get_backend(self.group) != "nccl":
-            return None
         d, n = self.d, coords.shape[0]
-        # every rank's buffer must hold its own batch; (re)map collectively when any rank's batch outgrows it
-        need = torch.tensor([n], dtype=torch.int64, device=dev)
-        dist.all_reduce(need, op=dist.ReduceOp.MAX, group=self.group)
-        need = int(need.item())
         ld = (ld + 1) // 2 * 2                  # result rows leave the kernel as 16-byte pieces
-        if self._peer is None or self._peer.rows < need or self._peer.ld != ld:
-            try:
-                self._peer = PeerResults(loc._lib, dev, self.group, max(need, 1) * 5 // 4 + 1024, ld)
-            except Exception as e:                               # noqa: BLE001 -- remembered: the group falls back together
-                self._peer, self._peer_error = None, f"{type(e).__name__}: {e}"
-                if self.fused is True:
-                    raise
-                return None
+        if not self._ensure_peer_buffers(n, ld, inbox=False):
+            return None
         peer = self._peer
         recv, _, _, recv_split, home_rows = route_rows(coords, owner, self.group, mark, with_home_rows=True)
         m = recv.shape[0]

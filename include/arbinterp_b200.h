@@ -173,6 +173,22 @@ int arb_query_gridil_host(const arb_geom* g, const double* packed, int mode, dou
 int arb_query_routed(const arb_geom* g, const double* table, int mode, double* q, int64_t N, int64_t ldq,
                      const int64_t* seg_start, const int64_t* home_row, double* const* peers, int npeers, int64_t ld,
                      void* stream);
+/* Both legs fused (no NCCL all-to-all, no sort, no host round trip on the query path of a slab-sharded table).
+ * arb_route_rows: every row of this rank's batch q [n][ldq] is stored into the inbox of the rank that owns its slab
+ * (owner as in arb_owner_keys), followed by its row number here: inbox row = [coords (d) | home row (int64 bits) | pad to
+ * an even count] = 4 (d = 3) or 6 (d = 4) doubles.  Rank o's inbox is nslab segments of seg_cap rows (n <= seg_cap),
+ * segment r written by rank r only; when the kernel ends counts[o][my_rank] on rank o holds the rows this rank sent there.
+ *   inboxes / counts : host arrays of nslab device pointers, entry o = rank o's inbox / int64 [nslab] counts mapped into
+ *                      this process (symmetric memory / CUDA IPC); cursor: device uint64 [nslab], ticket: device uint32,
+ *                      both local and ZERO on entry; outside: optional device [n], 1 = a coordinate outside the volume.
+ * arb_query_inbox: the owner's side -- evaluates the rows of its inbox (counts read on the device) and stores every row's
+ * outputs into peers[sender] at the row's home row, exactly like arb_query_routed (same result row layout, same ld).
+ * The caller orders route kernels, query kernels and readers with a barrier across the ranks after each kernel. */
+int arb_route_rows(const arb_geom* g, const double* q, int64_t n, int64_t ldq, const int64_t* slab_hi, int nslab,
+                   int my_rank, double* const* inboxes, int64_t* const* counts, int64_t seg_cap,
+                   unsigned long long* cursor, unsigned int* ticket, unsigned char* outside, void* stream);
+int arb_query_inbox(const arb_geom* g, const double* table, int mode, double* inbox, const int64_t* inbox_counts,
+                    int64_t seg_cap, double* const* peers, int npeers, int64_t ld, void* stream);
 /* Routing keys of a slab-sharded table: owner[n] = the rank whose slab [slab_hi[r-1], slab_hi[r]) holds row n's
  * slowest-axis cell layer floor((t - tIntMin) / ht) (A.py:1081-1086; rows without a layer go to rank 0), outside[n] = 1
  * when a coordinate lies outside the interpolation volume (A.py:1069-1076).  q: device [n][ldq]; g->slab_* are ignored. */

@@ -315,3 +315,79 @@ def test_pageable_rows_staged_ahead(monkeypatch):
         assert np.array_equal(obj.queryInds, ref_inds)
         assert np.isnan(qh[bad]).all() and np.array_equal(np.delete(qh, bad, axis=0), np.delete(q, bad, axis=0))
     assert torch.isnan(dev_q[bad]).all()
+
+
+@pytest.mark.parametrize("d,mode", [(4, "both"), (3, "norm"), (3, "vector")])
+def test_route_rows_and_inbox_query_virtual_ranks(d, mode):
+    """Both legs of a slab-sharded query as kernels (arb_route_rows -> arb_query_inbox), exercised on ONE GPU with three
+    virtual ranks whose inboxes, counts and result buffers all live on the same device: every sender's rows (one batch
+    is empty, one has out-of-volume / NaN / layer-boundary rows) must come back at their home rows bit-identical to the
+    unsharded table's answers, with the global cell index, and the out-of-volume mask must be the reference's bounds
+    test (A.py:1069-1076).  The multi-process form over NVLink is tests/test_multi_gpu.py."""
+    import ctypes
+    from arbinterp_b200 import _lib, quadcubic, tricubic
+    from test_gpu_parity import _analytic_field3, _analytic_field4, _uniform_queries
+    rng = np.random.default_rng(90 + d)
+    cls = tricubic if d == 3 else quadcubic
+    field = _analytic_field3(14, 12, 16, rng=rng) if d == 3 else _analytic_field4(10, 9, 8, 13, rng=rng)
+    whole = cls(field.copy(), "quiet", mode=mode)
+    lib = whole._lib
+    nslow = whole._geo.ncell[d - 1]
+    W = 3
+    his = [nslow // 3, 2 * nslow // 3, nslow]
+    slabs = [(0 if r == 0 else his[r - 1], his[r]) for r in range(W)]
+    parts = [cls(field.copy(), "quiet", mode=mode, slab=s) for s in slabs]
+    sizes = [70_001, 0, 12_345]
+    dev = torch.device("cuda", 0)
+    batches = []
+    for r, n in enumerate(sizes):
+        q = _uniform_queries(whole, d, max(n, 1), rng)[:n]
+        if n:
+            q[::97, 0] = 9.0                                    # outside the volume in x: owner by t / z, NaN outputs
+            q[5::211, d - 1] = np.nan                           # no layer: rank 0 answers NaN
+            q[7::301, d - 1] = -50.0
+            lo_s, h_s = whole._geo.int_min[d - 1], whole._geo.h[d - 1]
+            for k, b in enumerate(his[:-1]):                    # exactly on the slab boundaries
+                q[11 + k, d - 1] = lo_s + b * h_s
+        batches.append(torch.from_numpy(q).to(dev))
+    cap = max(sizes) + 100
+    ld_in = (d + 2) // 2 * 2
+    ncomp_out, ngrad = (0 if mode == "norm" else 3), (0 if mode == "vector" else 1 + d)
+    ld = (ncomp_out + ngrad + 2) // 2 * 2
+    inbox = [torch.full((W * cap, ld_in), float("nan"), dtype=torch.float64, device=dev) for _ in range(W)]
+    counts = [torch.full((16,), -1, dtype=torch.int64, device=dev) for _ in range(W)]
+    results = [torch.full((max(n, 1), ld), 123.0, dtype=torch.float64, device=dev) for n in sizes]
+    vp = ctypes.c_void_p
+    inbox_ptrs = (vp * W)(*[t.data_ptr() for t in inbox])
+    count_ptrs = (vp * W)(*[t.data_ptr() for t in counts])
+    result_ptrs = (vp * W)(*[t.data_ptr() for t in results])
+    hi_arr = (ctypes.c_int64 * W)(*his)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    outside = []
+    for r in range(W):
+        cursor = torch.zeros(W + 2, dtype=torch.int64, device=dev)
+        out = torch.empty(sizes[r], dtype=torch.bool, device=dev)
+        _lib.check(lib.arb_route_rows(ctypes.byref(whole._cgeom), batches[r].data_ptr(), sizes[r], d, hi_arr, W, r, inbox_ptrs,
+                                      count_ptrs, cap, cursor.data_ptr(), cursor[W + 1:].data_ptr(), out.data_ptr(), st),
+                   "arb_route_rows")
+        outside.append(out)
+    torch.cuda.synchronize()
+    sent = torch.stack([c[:W] for c in counts])                 # [owner][sender]
+    assert sent.sum(dim=0).tolist() == sizes and int(sent.min()) >= 0
+    for o in range(W):
+        _lib.check(lib.arb_query_inbox(ctypes.byref(parts[o]._cgeom), parts[o].table.data_ptr(), parts[o]._mode_code,
+                                       inbox[o].data_ptr(), counts[o].data_ptr(), cap, result_ptrs, W, ld, st), "arb_query_inbox")
+    torch.cuda.synchronize()
+    for r, n in enumerate(sizes):
+        if n == 0:
+            assert bool((results[r] == 123.0).all())
+            continue
+        q = batches[r].clone()
+        ref = whole.Query(q)
+        ref = ref if isinstance(ref, tuple) else (ref,)
+        flat = torch.cat([t.reshape(n, -1) for t in ref] + [whole._last_cells.view(torch.float64).unsqueeze(1)], dim=1)
+        got = results[r][:, :flat.shape[1]]
+        assert torch.equal(got.view(torch.int64), flat.view(torch.int64)), f"sender {r}"
+        lo = torch.tensor(whole._geo.int_min, dtype=torch.float64, device=dev)
+        hi = torch.tensor(whole._geo.int_max, dtype=torch.float64, device=dev)
+        assert torch.equal(outside[r], ((batches[r] < lo) | (batches[r] > hi)).any(dim=1))

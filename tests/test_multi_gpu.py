@@ -131,13 +131,14 @@ def _fused_worker(rank, world, port, out_dir):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     rng = np.random.default_rng(100 + rank)
-    ok, how = True, ""
+    ok, ok_both, how = True, True, ""
     for cls, gname, d in ((quadcubic, "quad_8x7x7x6", 4), (tricubic, "tri_12x10x9", 3)):
         field = load_golden(gname)["field"]
         for mode in ("vector", "norm", "both"):
             whole = cls(field.copy(), "quiet", mode=mode)
             fused = SlabShardedInterp(cls, field if rank == 0 else None, "quiet", mode=mode, fused=True)
             plain = SlabShardedInterp(cls, field if rank == 0 else None, "quiet", mode=mode, fused=False)
+            both = SlabShardedInterp(cls, field if rank == 0 else None, "quiet", mode=mode, fused="both")
             lo = np.array(whole._geo.int_min); hi = np.array(whole._geo.int_max)
             for n in (5000 + 37 * rank, 11, 0, 20000):            # growing, shrinking and empty batches re-use / re-map the buffers
                 q = lo + rng.uniform(-0.05, 1.05, (n, d + 1))[:, :d] * (hi - lo)
@@ -155,8 +156,15 @@ def _fused_worker(rank, world, port, out_dir):
                     ok &= bool(np.array_equal(fused.queryInds, whole.queryInds)) and bool(np.array_equal(qb, qa, equal_nan=True))
                 ok &= all(np.array_equal(x, y, equal_nan=True) for x, y in zip(rb, rc))
                 ok &= bool(np.array_equal(fused.queryInds, plain.queryInds))
+                # both legs as kernels (arb_route_rows -> arb_query_inbox): no all-to-all at all
+                qd = q.copy()
+                rd = both.Query(qd)
+                rd = rd if isinstance(rd, tuple) else (rd,)
+                ok_both &= all(np.array_equal(x, y, equal_nan=True) for x, y in zip(rd, rb))
+                ok_both &= bool(np.array_equal(both.queryInds, fused.queryInds)) and bool(np.array_equal(qd, qb, equal_nan=True))
+                ok_both &= both._inbox is not None
             how = fused._peer.how if fused._peer is not None else "none"
-    np.save(os.path.join(out_dir, f"fused{rank}.npy"), np.array([ok]))
+    np.save(os.path.join(out_dir, f"fused{rank}.npy"), np.array([ok, ok_both]))
     with open(os.path.join(out_dir, f"how{rank}.txt"), "w") as f:
         f.write(how)
     dist.barrier()
@@ -167,10 +175,13 @@ def _fused_worker(rank, world, port, out_dir):
 def test_fused_peer_store_return_world2(tmp_path):
     """SlabShardedInterp.Query with the return leg fused into the kernel (arb_query_routed: results stored into the home
     rank's buffer over NVLink) is bit-identical to the all-to-all return and to the unsharded table -- outputs, global
-    queryInds and in-place NaN rows; 3-D and 4-D, every mode, batches that grow, shrink and are empty."""
+    queryInds and in-place NaN rows; 3-D and 4-D, every mode, batches that grow, shrink and are empty.  The same for
+    fused='both': the forward leg as a kernel too (arb_route_rows stores the rows into the owners' inboxes, arb_query_inbox
+    evaluates them), no all-to-all on the query path."""
     import torch.multiprocessing as mp
     world = 2
     mp.spawn(_fused_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     for rank in range(world):
         assert bool(np.load(tmp_path / f"fused{rank}.npy")[0])
+        assert bool(np.load(tmp_path / f"fused{rank}.npy")[1]), "both legs fused (route kernel + inbox query) differ"
         assert open(tmp_path / f"how{rank}.txt").read() in ("symmetric_memory", "cuda_ipc")
