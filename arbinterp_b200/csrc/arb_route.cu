@@ -9,8 +9,8 @@
 // Inbox of rank o: `nslab` segments of `seg_cap` rows, segment r filled by rank r only, so positions come from a
 // counter that is local to the sender: no remote atomics.  A CTA takes tiles of 256 rows: lanes that go to the same
 // owner are numbered with __match_any_sync / __popc, a shared-memory counter per owner numbers the warps' groups within
-// the tile, one global atomicAdd per owner and tile reserves the tile's range in the segment, and each row leaves as
-// 16-byte pieces (rows to one owner land contiguously: the stores of a warp coalesce).  The last CTA to finish
+// the tile, one global atomicAdd per owner and tile reserves the tile's range in the segment, the tile is staged in
+// shared memory ordered by owner, and every owner's run leaves as 16-byte pieces from consecutive threads.  The last CTA to finish
 // publishes how many rows this rank put into every inbox (counts[o][my_rank] on rank o).
 #include "arb_device.cuh"
 
@@ -33,8 +33,11 @@ struct RouteParams {
 template <int D>
 __global__ void __launch_bounds__(256) route_rows_kernel(const RouteParams p) {
     constexpr int LD = (D + 2) / 2 * 2;                   // 4 (d = 3) or 6 (d = 4) doubles per inbox row
+    constexpr int CPR = LD / 2;                           // 16-byte pieces per row
     __shared__ unsigned int s_cnt[ARB_MAX_PEERS];
-    __shared__ unsigned long long s_base[ARB_MAX_PEERS];
+    __shared__ unsigned int s_off[ARB_MAX_PEERS + 1];     // where an owner's rows start in the staged tile
+    __shared__ unsigned long long s_base[ARB_MAX_PEERS];  // ... and in this rank's segment of the owner's inbox
+    __shared__ __align__(16) double s_rows[256 * LD];
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31;
     const int64_t ntile = (p.n + 255) / 256;
@@ -75,21 +78,33 @@ __global__ void __launch_bounds__(256) route_rows_kernel(const RouteParams p) {
             const unsigned int cnt = s_cnt[threadIdx.x];
             s_base[threadIdx.x] = cnt ? atomicAdd(&p.cursor[threadIdx.x], (unsigned long long)cnt) : 0ULL;
         }
-        __syncthreads();
-        if (have) {
-            const int64_t pos = (int64_t)s_base[owner] + group_base + in_group;
-            double* dst = p.inbox[owner] + ((int64_t)p.my_rank * p.seg_cap + pos) * LD;
-            const double home = __longlong_as_double((long long)i);
-            if (D == 3) {
-                stg_stream_d2(dst, c[0], c[1]);
-                stg_stream_d2(dst + 2, c[2], home);
-            } else {
-                stg_stream_d2(dst, c[0], c[1]);
-                stg_stream_d2(dst + 2, c[2], c[D - 1]);
-                stg_stream_d2(dst + 4, home, 0.0);
-            }
+        if (threadIdx.x == 0) {
+            unsigned int run = 0;
+            for (int o = 0; o < p.nslab; ++o) { s_off[o] = run; run += s_cnt[o]; }
+            s_off[p.nslab] = run;
         }
-        __syncthreads();                                  // s_cnt / s_base are reused by the next tile
+        __syncthreads();
+        // stage the tile ordered by owner, then store every owner's run as 16-byte pieces from consecutive threads:
+        // small scattered remote stores are what NVLink is worst at (48-byte rows stored by their own threads: 0.68 ms
+        // for 4 M rows at two ranks)
+        if (have) {
+            double* srow = s_rows + (size_t)(s_off[owner] + group_base + in_group) * LD;
+#pragma unroll
+            for (int a = 0; a < D; ++a) srow[a] = c[a];
+            srow[D] = __longlong_as_double((long long)i);
+            if (LD > D + 1) srow[D + 1] = 0.0;
+        }
+        __syncthreads();
+        const int npiece = (int)s_off[p.nslab] * CPR;
+        for (int k = threadIdx.x; k < npiece; k += 256) {
+            const int r = k / CPR, part = k - r * CPR;
+            int o = 0;
+            for (int h = 1; h < p.nslab; ++h) o = (r >= (int)s_off[h]) ? h : o;
+            double* dst = p.inbox[o] + ((int64_t)p.my_rank * p.seg_cap + (int64_t)s_base[o] + (r - (int)s_off[o])) * LD + part * 2;
+            const double2 v = *reinterpret_cast<const double2*>(s_rows + (size_t)r * LD + part * 2);
+            stg_stream_d2(dst, v.x, v.y);
+        }
+        __syncthreads();                                  // the shared arrays are reused by the next tile
     }
     // the last CTA publishes this rank's row counts in every owner's inbox header
     __threadfence_system();
