@@ -675,8 +675,8 @@ def run_sharded(torch, dist, args, rank, world, device):
     vel[:, 3] = (hi_t[3] - lo_t[3]) * 0.01
     only_space = torch.tensor([1, 1, 1, 0], dtype=torch.float64, device=device)
     span = (hi_t - lo_t) * (1 - 1e-9)
-    timing, timing_plain = {}, {}
-    step_ms, plain_ms = [], []
+    timing, timing_plain, timing_ret = {}, {}, {}
+    step_ms, plain_ms, ret_ms = [], [], []
     node_ms = []
     finite, same_fused = True, True
     for step in range(args.warmup + args.steps):
@@ -702,11 +702,22 @@ def run_sharded(torch, dist, args, rank, world, device):
         res_plain = obj.Query(q, timing=timing_plain if timed else None)
         e5.record()
         torch.cuda.synchronize()
-        obj.fused = was
         same_fused &= all(bool(torch.equal(a.view(torch.int64), b.view(torch.int64))) for a, b in zip(res, res_plain)) and \
+            bool(torch.equal(cells_plain, obj._last_cells))
+        # ... and with only the return leg fused (round 2's first form: rows travel by NCCL all-to-all after a sort)
+        obj.fused = True
+        dist.barrier()
+        e6, e7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e6.record()
+        res_ret = obj.Query(q, timing=timing_ret if timed else None)
+        e7.record()
+        torch.cuda.synchronize()
+        obj.fused = was
+        same_fused &= all(bool(torch.equal(a.view(torch.int64), b.view(torch.int64))) for a, b in zip(res, res_ret)) and \
             bool(torch.equal(cells_plain, obj._last_cells))
         if timed:
             plain_ms.append(e4.elapsed_time(e5))
+            ret_ms.append(e6.elapsed_time(e7))
         dist.barrier()
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e2.record()
@@ -722,9 +733,16 @@ def run_sharded(torch, dist, args, rank, world, device):
     node_err = scaled_error(tuple(r[:m].cpu().numpy() for r in res_n), tuple(r[:m].cpu().numpy() for r in res), 4,
                             g.h, float(torch.stack([r.abs().max() for r in res[:2]]).max()))
     same_cells = bool(torch.equal(rep.local._last_cells, obj._last_cells))
-    tn = torch.tensor([sum(node_ms), node_err, float(not same_cells), sum(plain_ms), float(not same_fused)],
+    tn = torch.tensor([sum(node_ms), node_err, float(not same_cells), sum(plain_ms), float(not same_fused), sum(ret_ms)],
                       dtype=torch.float64, device=device)
     dist.all_reduce(tn, op=dist.ReduceOp.MAX)
+    ret_s = float(tn[5]) / 1e3
+    phr = torch.tensor([timing_ret.get(k + "_ms", 0.0) for k in
+                        ("owner", "sort", "counts", "permute", "alltoall", "kernel", "alltoall_back", "scatter", "unpack")],
+                       dtype=torch.float64, device=device)
+    dist.all_reduce(phr, op=dist.ReduceOp.MAX)
+    phr = (phr / args.steps).tolist()
+    both_legs = getattr(obj, "_inbox", None) is not None
     node_s, node_err, cells_differ = float(tn[0]) / 1e3, float(tn[1]), bool(tn[2] > 0)
     plain_s, fused_differs = float(tn[3]) / 1e3, bool(tn[4] > 0)
     php = torch.tensor([timing_plain.get(k + "_ms", 0.0) for k in
@@ -759,8 +777,13 @@ def run_sharded(torch, dist, args, rank, world, device):
             "sort + permute + scatter": ph[1] + ph[3] + ph[7], "owner + unpack": ph[0] + ph[8],
             "each": dict(zip(("owner", "sort", "counts", "permute", "alltoall", "kernel", "alltoall_back", "scatter", "unpack"), ph))},
         "kernel_frac_of_measured_hbm": (ALG_BYTES[(4, "both")] * n / (ph[5] * 1e-3) / 1e9 / measured_peak()[0]) if ph[5] > 0 else None,
+        "forward_leg": ("fused into a kernel (the library default): arb_route_rows stores every row, with its home row number, "
+                        "into the inbox of the rank that owns its slab over NVLink -- no sort, no counts exchange, no all-to-all, "
+                        "no host round trip; the owner's kernel (arb_query_inbox) reads the per-sender counts on the device; "
+                        "in the phase split 'owner' is that kernel and 'alltoall' the barrier after it") if both_legs else
+                       "NCCL all-to-all of the rows after a 16-bit sort by owner (route_rows)",
         "return_leg": ("fused into the query kernel (the library default): every row's outputs are stored into its home "
-                       f"rank's result buffer over NVLink (arb_query_routed, peer mapping: {peer_how})") if peer_how else
+                       f"rank's result buffer over NVLink (peer mapping: {peer_how})") if peer_how else
                       ("NCCL all-to-all of the result rows + a re-ordering pass (peer mapping of the result buffers "
                        "unavailable: " + str(getattr(obj, "_peer_error", None)) + ")"),
         "all_to_all_return": {
@@ -769,6 +792,13 @@ def run_sharded(torch, dist, args, rank, world, device):
             "fused_speedup": plain_s / total_s, "bit_identical_to_fused": not fused_differs,
             "phase_ms_per_step_max_over_ranks": dict(zip(("owner", "sort", "counts", "permute", "alltoall", "kernel",
                                                           "alltoall_back", "scatter", "unpack"), php))},
+        "return_leg_only_fused": {
+            "what": "the same rows with only the return leg fused (fused=True): rows sorted by owner, exchanged with two NCCL "
+                    "all-to-alls, results stored into the home rank's buffer by the query kernel",
+            "value": world * n * args.steps / ret_s, "unit": "queries/s", "ms_per_step": 1e3 * ret_s / args.steps,
+            "both_legs_speedup": ret_s / total_s,
+            "phase_ms_per_step_max_over_ranks": dict(zip(("owner", "sort", "counts", "permute", "alltoall", "kernel",
+                                                          "alltoall_back", "scatter", "unpack"), phr))},
         "replicated_node_table": {
             "what": "the same field as a node (Hermite) table replicated on every rank (quadcubic(table='nodes') via "
                     "sharding.ReplicatedInterp): each rank answers its own rows, no exchange; same queries as above",
