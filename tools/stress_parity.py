@@ -28,7 +28,7 @@ for case in range(a.cases):
     form = int(rng.integers(0, 6))                 # 0-2 cell table, 3 table-free, 4 table-free planes (round-1 kernels), 5 node table
     table_free = form in (3, 4)
     bv = int(rng.integers(0, 10))
-    qv = int(rng.choice([0, 1, 2, 10, 11, 20, 21, 22, 23, 30, 24, 25, 40, 41, 42, 43, 44, 45, 50, 51, 60, 61, 62, 63, 71, 72, 73]))
+    qv = int(rng.choice([0, 1, 2, 10, 11, 20, 21, 22, 23, 30, 24, 25, 40, 41, 42, 43, 44, 45, 50, 51, 60, 61, 62, 63, 71, 72, 73, 81, 82]))
     kw = {} if scalar else {"mode": mode}
     if table_free:
         kw["table"] = False
