@@ -237,6 +237,15 @@ def test_argument_validation_without_gpu():
     assert lib.arb_get_matrix(2, 0, 1, None) != 0
     old = lib.arb_set_query_variant(1)
     assert lib.arb_set_query_variant(old) == 1
+    # the fused legs of slab-sharded queries: argument checks come before any CUDA call
+    hi = (ctypes.c_int64 * 2)(2, 5)
+    vp2 = (ctypes.c_void_p * 2)(None, None)
+    assert lib.arb_route_rows(ctypes.byref(g), None, 10, 3, hi, 2, 0, vp2, vp2, 4, None, None, None, None) != 0      # n > seg_cap
+    assert b"arb_route_rows" in lib.arb_last_error()
+    assert lib.arb_route_rows(ctypes.byref(g), None, 0, 3, hi, 2, 5, vp2, vp2, 4, None, None, None, None) != 0       # rank out of range
+    assert lib.arb_query_inbox(ctypes.byref(g), None, _lib.MODE_NORM, None, None, 4, vp2, 2, 6, None) != 0
+    assert b"arb_query_inbox" in lib.arb_last_error()
+    assert lib.arb_query_gridil(ctypes.byref(g), None, _lib.MODE_NORM, None, 4, 3, None, None, None, None, None, None, None) != 0
 
 
 def test_wrong_shape_exits_like_reference():
