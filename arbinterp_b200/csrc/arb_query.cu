@@ -313,11 +313,22 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
     int64_t nitem = LOOPC ? nbatch : nbatch * C;
     // inbox form: the rows sit in npeers segments of seg_cap rows, inbox_counts[h] of them filled; items are numbered
     // over the filled parts only (a segment's last item may be partly empty)
-    int64_t seg_item0[ROUTED ? ARB_MAX_PEERS + 1 : 1];
+    // (kept in shared memory: per-thread arrays indexed by the segment went to local memory and, with the per-item
+    // reads of the counts from global memory, cost the inbox form ~5 % against the plain kernel)
+    __shared__ int64_t seg_item0[ROUTED ? ARB_MAX_PEERS + 1 : 1], seg_rows[ROUTED ? ARB_MAX_PEERS : 1];
     const bool inbox = ROUTED && p.inbox_counts != nullptr;
     if (ROUTED && inbox) {
-        seg_item0[0] = 0;
-        for (int h = 0; h < p.npeers; ++h) seg_item0[ROUTED ? h + 1 : 0] = seg_item0[ROUTED ? h : 0] + (p.inbox_counts[h] + QPW - 1) / QPW;
+        if (threadIdx.x == 0) {
+            int64_t run = 0;
+            for (int h = 0; h < p.npeers; ++h) {
+                const int64_t c = p.inbox_counts[h];
+                seg_rows[ROUTED ? h : 0] = c;
+                seg_item0[ROUTED ? h : 0] = run;
+                run += (c + QPW - 1) / QPW;
+            }
+            seg_item0[ROUTED ? p.npeers : 0] = run;
+        }
+        __syncthreads();
         nitem = seg_item0[ROUTED ? p.npeers : 0];
     }
     uint32_t phase = 0;
@@ -334,7 +345,7 @@ __global__ void __launch_bounds__(THREADS) query_block_kernel(const QueryParams 
         if (ROUTED && inbox) {                       // item -> (segment, row of the segment); rows past the count: n = N
             for (int h = 1; h < p.npeers; ++h) seg = (item >= seg_item0[ROUTED ? h : 0]) ? h : seg;
             const int64_t nl = (item - seg_item0[ROUTED ? seg : 0]) * QPW + qi;
-            n = (nl < p.inbox_counts[seg]) ? seg * p.seg_cap + nl : p.N;
+            n = (nl < seg_rows[ROUTED ? seg : 0]) ? seg * p.seg_cap + nl : p.N;
         }
         Located<D> L;
         L.ok = false; L.masked = false; L.cell_global = 0; L.cell_local = 0;
